@@ -1,0 +1,163 @@
+"""Host side of the fused GridConv block (reference: segmentation/models/gcn_module_g_att.py).
+
+``GridConv`` holds one layer's parameters with eval-mode BatchNorm folded into the 1x1 convs and
+launches ONE fused kernel (C-ABI ``gridgcn_gridconv_fwd``) that subsumes ``batch_take_g``
+(utils/ops.py:78-93) and ``sub_g_update`` (gcn_module_g_att.py:172-287).  ``sub_g_update`` below
+keeps the reference's call signature for callers that already hold gathered neighbours.
+
+Parameter names follow the reference's scopes so a converted checkpoint can be loaded by name:
+  {scope}/conv{j}_weight, _bias, {scope}/conv{j}/bn_gamma, _beta, _moving_mean, _moving_var
+  {scope}/update_att_mlp2d_frst/conv1_*, {scope}/update_att_mlp2d_scnd/conv1_*
+(utils/ops.py:149-158, gcn_module_g_att.py:135,141,152).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-3  # MXNet BatchNorm default eps (utils/ops.py:152 does not override it)
+
+PRECISION = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+
+
+def init_stage(rng, cin, cout):
+    """Random parameters of one conv1x1 + BN stage (Xavier-like weights, non-trivial BN stats)."""
+    lim = np.sqrt(6.0 / (cin + cout))
+    return dict(weight=rng.uniform(-lim, lim, size=(cout, cin)).astype(np.float32),
+                bias=rng.uniform(-0.1, 0.1, size=cout).astype(np.float32),
+                gamma=rng.uniform(0.8, 1.2, size=cout).astype(np.float32),
+                beta=rng.uniform(-0.1, 0.1, size=cout).astype(np.float32),
+                moving_mean=rng.uniform(-0.1, 0.1, size=cout).astype(np.float32),
+                moving_var=rng.uniform(0.5, 1.5, size=cout).astype(np.float32))
+
+
+def init_layer(rng, cin, pt_mlp_lst, attfdim):
+    """Parameter dict of one GridConv layer, keyed like the reference's scopes."""
+    feat_in = 3 if cin == 0 else cin
+    stages, w = [], feat_in
+    for c in pt_mlp_lst:
+        stages.append(init_stage(rng, w, c))
+        w = c
+    C = pt_mlp_lst[-1]
+    att = []
+    if attfdim > 0:
+        ain = 3 if attfdim <= 3 else (4 if attfdim < 10 else 10)
+        att = [init_stage(rng, ain, C // 4), init_stage(rng, C // 4, C)]
+    return dict(feat=stages, att=att, attfdim=attfdim, cin=cin)
+
+
+def fold_bn(weight, bias, gamma, beta, moving_mean, moving_var, eps=BN_EPS):
+    """conv1x1 -> BatchNorm(eval, fix_gamma=False) == conv1x1 with W' = W*s, b' = (b-mean)*s+beta,
+    s = gamma / sqrt(var + eps).  Folded in float64, returned as float32."""
+    s = np.asarray(gamma, np.float64) / np.sqrt(np.asarray(moving_var, np.float64) + eps)
+    w = np.asarray(weight, np.float64).reshape(len(s), -1) * s[:, None]
+    b = (np.asarray(bias, np.float64) - np.asarray(moving_mean, np.float64)) * s + \
+        np.asarray(beta, np.float64)
+    return w.astype(np.float32), b.astype(np.float32)
+
+
+def named_params(layer, scope):
+    """Flatten a layer dict ({'feat': [...], 'att': [...]}) into reference-style names."""
+    out = {}
+    def put(prefix, st):
+        out[prefix + "_weight"] = st["weight"]
+        out[prefix + "_bias"] = st["bias"]
+        for k in ("gamma", "beta", "moving_mean", "moving_var"):
+            out[prefix + "/bn_" + k] = st[k]
+    for j, st in enumerate(layer["feat"]):
+        put("%s/conv%d" % (scope, j + 1), st)
+    if layer["att"]:
+        put(scope + "/update_att_mlp2d_frst/conv1", layer["att"][0])
+        put(scope + "/update_att_mlp2d_scnd/conv1", layer["att"][1])
+    return out
+
+
+class GridConv:
+    """One GridConv layer: ``out_table = layer(table, nebidx, cent, centmsk)``.
+
+    table  (B, Nprev, 4+Cin) f32  rows [x y z w | feats]   nebidx (B, O, K) i32
+    cent   (B, O, 4) f32                                   centmsk (B, O) f32
+    out    (B, O, 4+Cout) f32     rows [cent | feats] -- the next layer's table
+                                  (ggcn_models_g.py:186); ``features_nco(out)`` gives the
+                                  reference's (B, Cout, O) layout.
+    """
+
+    def __init__(self, layer, device, pre_relu=True, precision="fp32"):
+        self.cin = int(layer["cin"])
+        self.attfdim = int(layer["attfdim"])
+        self.pre_relu = bool(pre_relu)
+        self.precision = precision
+        self.device = torch.device(device)
+        stages = list(layer["feat"]) + list(layer["att"])
+        self.widths = [int(st["weight"].shape[0]) for st in stages]
+        self.cout = int(layer["feat"][-1]["weight"].shape[0])
+        self._w, self._b = [], []
+        for st in stages:
+            w, b = fold_bn(st["weight"], st["bias"], st["gamma"], st["beta"], st["moving_mean"],
+                           st["moving_var"])
+            self._w.append(torch.from_numpy(w).to(self.device).contiguous())
+            self._b.append(torch.from_numpy(b).to(self.device).contiguous())
+        d = _lib.MlpDesc()
+        d.n_feat_stages = len(layer["feat"])
+        d.attfdim = self.attfdim
+        d.feat_in = 3 if self.cin == 0 else self.cin
+        d.pre_relu = 1 if self.pre_relu else 0
+        for i, (w, b) in enumerate(zip(self._w, self._b)):
+            d.widths[i] = self.widths[i]
+            d.weight[i] = w.data_ptr()
+            d.bias[i] = b.data_ptr()
+        self._desc = d
+
+    def __call__(self, table, nebidx, cent, centmsk, out=None):
+        L = _lib.lib()
+        if not table.is_cuda:
+            raise _lib.GridGcnError("GridConv needs CUDA tensors: there is no CPU path")
+        table = table.contiguous()
+        nebidx = nebidx.contiguous()
+        cent = cent.contiguous()
+        centmsk = centmsk.contiguous()
+        B, Nprev, roww = table.shape
+        if roww != 4 + self.cin:
+            raise ValueError("table rows should be 4+%d wide, got %d" % (self.cin, roww))
+        _, O, K = nebidx.shape
+        if out is None:
+            out = torch.empty((B, O, 4 + self.cout), dtype=torch.float32, device=table.device)
+        with torch.cuda.device(table.device):
+            rc = L.gridgcn_gridconv_fwd(
+                table.data_ptr(), nebidx.data_ptr(), cent.data_ptr(), centmsk.data_ptr(), B, Nprev,
+                self.cin, O, K, ctypes.byref(self._desc), PRECISION[self.precision], out.data_ptr(),
+                torch.cuda.current_stream(table.device).cuda_stream)
+        _lib.check(rc, "gridgcn_gridconv_fwd")
+        return out
+
+
+def features_nco(out_table):
+    """(B, O, 4+C) [cent | feats] -> (B, C, O), the layout sub_g_update returns (BN=True path)."""
+    return out_table[:, :, 4:].transpose(1, 2)
+
+
+def sub_g_update(centers_xyz, center_den, neighbors, has_feats, center_masks, neighbor_masks,
+                 attfdim, center_ori_feats=None, pt_mlp_lst=None, outDim=(), cntxt_mlp=None,
+                 shape=None, scope="layer", aggtype="gcn", pool_type="max_pooling", att_full="",
+                 center_dim=(), recalden=False, bn_decay=0.9, *, layer=None, pre_relu=True,
+                 precision="fp32"):
+    """Reference call signature (gcn_module_g_att.py:172-174) on already gathered neighbours.
+
+    centers_xyz (B,3,O), center_den (B,1,O), neighbors (B,4+C,O,P), center_masks (B,O) -> (B,C,O).
+    ``layer`` carries the parameters.  The gathered tensor is viewed as a table with an identity
+    index so that the same fused kernel runs.  Only the configuration the shipped seg config uses
+    is supported here (aggtype gcn, max pooling, no context MLP, empty outDim)."""
+    if aggtype != "gcn" or pool_type not in ("max_pooling", "max") or cntxt_mlp is not None \
+            or len(outDim) != 0 or center_ori_feats is not None or att_full:
+        raise NotImplementedError("sub_g_update: unsupported configuration for the fused kernel")
+    B, C4, O, P = neighbors.shape
+    table = neighbors.permute(0, 2, 3, 1).reshape(B, O * P, C4).contiguous()
+    idx = torch.arange(O * P, dtype=torch.int32, device=neighbors.device).reshape(1, O, P)
+    idx = idx.expand(B, O, P).contiguous()
+    cent = torch.cat([centers_xyz.transpose(1, 2), center_den.transpose(1, 2)], dim=2).contiguous()
+    if center_masks is None:
+        center_masks = torch.ones((B, O), dtype=torch.float32, device=neighbors.device)
+    conv = GridConv(layer, neighbors.device, pre_relu=pre_relu, precision=precision)
+    return features_nco(conv(table, idx, cent, center_masks))

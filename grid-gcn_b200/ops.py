@@ -1,0 +1,155 @@
+"""Host-side mirror of the reference's native operators, on torch CUDA tensors.
+
+Same names, argument order, keyword names, output order, shapes and dtypes as the MXNet operators
+registered by gridifyop/additional.so (reference paths relative to /root/reference):
+
+  Gridify / GridifyKNN   gridifyop/gridify-inl.h:144-215, call site
+                         segmentation/models/ggcn_models_g.py:154-159
+  GridifyUp              gridifyop/gridify_up-inl.h:137-190, call site ggcn_models_g.py:207-210
+  contrib.KNN            gridifyop/k_nn.cc:14-65, call site ggcn_models_g.py:83
+  contrib.BallKNN        gridifyop/ball_k_nn.cc:14-65, call site ggcn_models_g.py:85
+
+PyTorch only provides device memory and the current stream here; the compute is the C-ABI
+library (include/gridgcn_b200.h).  No autograd: the reference declares no backward dependency
+(gridify-inl.h:227-231) / zero gradients (k_nn.cc:60).
+"""
+import torch
+
+from . import _lib
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_cuda(name, t, dtype, ndim):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise _lib.GridGcnError("%s must live on a CUDA device: gridgcn_b200 has no CPU path "
+                                "(the reference has none either, gridify.cc:30-39)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.dim() != ndim:
+        raise ValueError("%s should be a %dD tensor" % (name, ndim))  # gridify-inl.h:176,180
+    return t.contiguous()
+
+
+def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_size, stride, loc,
+             coord_shift, voxel_size, grid_size, flags):
+    L = _lib.lib()
+    data = _check_cuda("data", data, torch.float32, 3)
+    actual_numpoints = _check_cuda("actualnum", actual_numpoints, torch.int32, 2)
+    B, N, C = data.shape
+    if C != 4:
+        raise ValueError("data should be (B, N, 4): x, y, z, w")
+    if actual_numpoints.shape[0] != B:
+        raise ValueError("actualnum should be (B, 1)")
+    O, P = int(max_o_grid), int(max_p_grid)
+    dev = data.device
+    grid = _lib.triple_i(grid_size)
+    ws_bytes = L.gridgcn_gridify_workspace_bytes(B, N, O, grid) if B > 0 else 0
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    nebidx = torch.empty((B, O, P), dtype=torch.int32, device=dev)
+    nebidxmsk = torch.empty((B, O, P), dtype=torch.float32, device=dev)
+    cent = torch.empty((B, O, 4), dtype=torch.float32, device=dev)
+    centmsk = torch.empty((B, O), dtype=torch.float32, device=dev)
+    actual_centnum = torch.empty((B, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = getattr(L, fn_name)(
+            data.data_ptr(), actual_numpoints.data_ptr(), B, N, O, P, int(kernel_size), int(stride),
+            int(loc), _lib.triple_f(coord_shift), _lib.triple_f(voxel_size), grid, int(flags),
+            nebidx.data_ptr(), nebidxmsk.data_ptr(), cent.data_ptr(), centmsk.data_ptr(),
+            actual_centnum.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+    _lib.check(rc, fn_name)
+    return nebidx, nebidxmsk, cent, centmsk, actual_centnum
+
+
+def Gridify(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_size=0, stride=0, loc=0,
+            coord_shift=(), voxel_size=(), grid_size=()):
+    """Voxel hash + centre sampling + first-P neighbour gather (canonical RVS, keep-first).
+
+    Returns ``(nebidx i32 [B,O,P], nebidxmsk f32 [B,O,P], cent f32 [B,O,4], centmsk f32 [B,O],
+    actual_centnum i32 [B,1])`` exactly as gridify-inl.h:190-196,207-212 infer them."""
+    return _gridify("gridgcn_gridify_fwd", data, actual_numpoints, max_p_grid, max_o_grid,
+                    kernel_size, stride, loc, coord_shift, voxel_size, grid_size, 0)
+
+
+def GridifyKNN(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_size=0, stride=0,
+               loc=0, coord_shift=(), voxel_size=(), grid_size=(), dist_fma=False):
+    """Same signature as Gridify (gridifyknn-inl.h is a rename of gridify-inl.h); neighbours are
+    the P nearest (to the voxel centre) points of the expanding Chebyshev shells, sorted by
+    distance.  ``dist_fma`` (extension) selects the FMA contraction of the reference's cubin."""
+    return _gridify("gridgcn_gridify_knn_fwd", data, actual_numpoints, max_p_grid, max_o_grid,
+                    kernel_size, stride, loc, coord_shift, voxel_size, grid_size,
+                    1 if dist_fma else 0)
+
+
+def GridifyUp(downdata, updata, down_actual_numpoints, up_actual_numpoints, *, max_p_grid=0,
+              max_o_grid=0, kernel_size=0, coord_shift=(), voxel_size=(), grid_size=()):
+    """Returns ``(nebidx i32 [B,O,P], nebidxmsk f32 [B,O,P])`` (gridify_up-inl.h:183-184)."""
+    L = _lib.lib()
+    downdata = _check_cuda("downdata", downdata, torch.float32, 3)
+    updata = _check_cuda("updata", updata, torch.float32, 3)
+    dn = _check_cuda("down_actual_numpoints", down_actual_numpoints, torch.int32, 2)
+    un = _check_cuda("up_actual_numpoints", up_actual_numpoints, torch.int32, 2)
+    B, N, C = downdata.shape
+    O, P = int(max_o_grid), int(max_p_grid)
+    if C != 4 or tuple(updata.shape) != (B, O, 4):
+        raise ValueError("downdata should be (B, N, 4) and updata (B, max_o_grid, 4)")
+    dev = downdata.device
+    grid = _lib.triple_i(grid_size)
+    ws_bytes = L.gridgcn_gridify_up_workspace_bytes(B, N, grid) if B > 0 else 0
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    nebidx = torch.empty((B, O, P), dtype=torch.int32, device=dev)
+    nebidxmsk = torch.empty((B, O, P), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.gridgcn_gridify_up_fwd(
+            downdata.data_ptr(), updata.data_ptr(), dn.data_ptr(), un.data_ptr(), B, N, O, P,
+            int(kernel_size), _lib.triple_f(coord_shift), _lib.triple_f(voxel_size), grid,
+            nebidx.data_ptr(), nebidxmsk.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+    _lib.check(rc, "gridgcn_gridify_up_fwd")
+    return nebidx, nebidxmsk
+
+
+class contrib:
+    """``mx.sym.contrib`` namespace of the reference (ggcn_models_g.py:83,85)."""
+
+    @staticmethod
+    def _knn(unknown, known, downnum, upnum, k, radius, dist_fma):
+        L = _lib.lib()
+        unknown = _check_cuda("unknown", unknown, torch.float32, 3)
+        known = _check_cuda("known", known, torch.float32, 3)
+        downnum = _check_cuda("downnum", downnum, torch.int32, 2)
+        upnum = _check_cuda("upnum", upnum, torch.int32, 2)
+        if unknown.shape[2] != 3:
+            raise ValueError("Last dim of unknown should be 3")  # k_nn.cc:35
+        if known.shape[2] != 3:
+            raise ValueError("Last dim of known should be 3")    # k_nn.cc:39
+        B, n, _ = unknown.shape
+        m = known.shape[1]
+        idx = torch.empty((B, n, int(k)), dtype=torch.int32, device=unknown.device)
+        flags = 1 if dist_fma else 0
+        with torch.cuda.device(unknown.device):
+            if radius is None:
+                rc = L.gridgcn_knn_fwd(unknown.data_ptr(), known.data_ptr(), downnum.data_ptr(),
+                                       upnum.data_ptr(), B, n, m, int(k), flags, idx.data_ptr(),
+                                       _stream_ptr(unknown.device))
+            else:
+                rc = L.gridgcn_ball_knn_fwd(unknown.data_ptr(), known.data_ptr(),
+                                            downnum.data_ptr(), upnum.data_ptr(), B, n, m, int(k),
+                                            float(radius), flags, idx.data_ptr(),
+                                            _stream_ptr(unknown.device))
+        _lib.check(rc, "gridgcn_knn_fwd" if radius is None else "gridgcn_ball_knn_fwd")
+        return idx
+
+    @staticmethod
+    def KNN(unknown, known, downnum, upnum, *, k=3, dist_fma=False):
+        """idx i32 [B,n,k]: the k nearest known points of every unknown row (k_nn.cc:23-57)."""
+        return contrib._knn(unknown, known, downnum, upnum, k, None, dist_fma)
+
+    @staticmethod
+    def BallKNN(unknown, known, downnum, upnum, *, k=3, radius=0.1, dist_fma=False):
+        """As KNN but only neighbours with d2 <= radius^2; misses are -1; k <= 6
+        (ball_k_nn-inl.h:33-39,63-64,69,77)."""
+        return contrib._knn(unknown, known, downnum, upnum, k, radius, dist_fma)

@@ -1,0 +1,150 @@
+/*
+ * gridgcn_b200.h -- C-ABI of libgridgcn_b200.so (sm_100a).
+ *
+ * These entry points are what the reference's operator plugin binds for the hot path named by
+ * BASELINE.json:north_star: each one replaces the `Forward` of one MXNet operator registered by
+ * gridifyop/additional.so (reference paths are relative to /root/reference/gridifyop/).
+ * Plain pointers and sizes only; no torch / MXNet types.  See INTEGRATION.md for the
+ * reference-side stub a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter name ends in `_host` or is one of the
+ *    three-element parameter triples (coord_shift / voxel_size / grid_size), which are HOST arrays;
+ *  - all tensors are dense, row-major, fp32 (`float`) or int32 (`int`), exactly the dtypes the
+ *    reference infers (gridify-inl.h:203-213);
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); all calls are
+ *    asynchronous and re-entrant (no global state), the caller owns outputs AND workspace;
+ *  - return value: 0 on success; a negative GRIDGCN_E* code for rejected arguments (nothing was
+ *    launched); a positive value is a `cudaError_t` reported by a launch.  The library never
+ *    aborts the process (the reference LOG(FATAL)s, gridify.cu:386).
+ *
+ * Canonical semantics: the reference kernels are non-deterministic
+ * (atomics arrival order, time-seeded reservoirs).  These kernels produce the output of the
+ * canonical schedule -- threads executed in ascending index, build before query, keep-first on
+ * overflow -- which is the schedule the CPU oracle (oracle/gridgcn_oracle.c) restates.
+ */
+#ifndef GRIDGCN_B200_H_
+#define GRIDGCN_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRIDGCN_ABI_VERSION 1
+
+/* rejected-argument codes (negative) */
+#define GRIDGCN_EINVAL      (-1)  /* null pointer, negative size, even kernel_size, ...          */
+#define GRIDGCN_ELIMIT      (-2)  /* outside the supported range (see each function)             */
+#define GRIDGCN_EWORKSPACE  (-3)  /* workspace missing or smaller than *_workspace_bytes()       */
+
+/* flags */
+#define GRIDGCN_FLAG_DIST_FMA  1  /* d2 = fma(dz,dz,fma(dy,dy,dx*dx)) -- the contraction found in
+                                     the reference's shipped sm_75 cubin -- instead of the
+                                     canonical ((dx*dx+dy*dy)+dz*dz) of SURVEY.md s8c rule 10   */
+
+int gridgcn_abi_version(void);
+
+/* Human-readable text for a return code of this library (static storage). */
+const char *gridgcn_strerror(int code);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Gridify   -- replaces GridifyOp<gpu>::Forward, gridify-inl.h:99-128 + GridifyForward<gpu>,   */
+/*              gridify.cu:294-413 (kernels gridify.cu:102-291).                                */
+/* GridifyKNN-- replaces GridifyKNNOp<gpu>::Forward, gridifyknn-inl.h:99-128 + gridifyknn.cu    */
+/*              :336-455 (kernels :115-333).  Same signature (the reference headers differ in   */
+/*              identifiers only).                                                              */
+/*                                                                                              */
+/*  data      (B,N,4) f32  x,y,z,w           actual_numpoints (B) i32                           */
+/*  nebidx    (B,O,P) i32  nebidxmsk (B,O,P) f32  cent (B,O,4) f32  centmsk (B,O) f32           */
+/*  actual_centnum (B) i32          O = max_o_grid, P = max_p_grid  (gridify-inl.h:190-196)     */
+/*  stride is accepted and ignored, as in the reference (gridify.cu:112, never read).           */
+/*  Limits: kernel_size odd; P <= 128; grid_size[0]*[1]*[2] <= 262144; N < 2^24.                */
+/* ------------------------------------------------------------------------------------------ */
+size_t gridgcn_gridify_workspace_bytes(int B, int N, int max_o_grid, const int grid_size[3]);
+
+int gridgcn_gridify_fwd(const float *data, const int *actual_numpoints, int B, int N,
+                        int max_o_grid, int max_p_grid, int kernel_size, int stride, int loc,
+                        const float coord_shift[3], const float voxel_size[3],
+                        const int grid_size[3], int flags, int *nebidx, float *nebidxmsk,
+                        float *cent, float *centmsk, int *actual_centnum, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+int gridgcn_gridify_knn_fwd(const float *data, const int *actual_numpoints, int B, int N,
+                            int max_o_grid, int max_p_grid, int kernel_size, int stride, int loc,
+                            const float coord_shift[3], const float voxel_size[3],
+                            const int grid_size[3], int flags, int *nebidx, float *nebidxmsk,
+                            float *cent, float *centmsk, int *actual_centnum, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* GridifyUp -- replaces GridifyUpOp<gpu>::Forward, gridify_up-inl.h:93-119 +                   */
+/*              GridifyUpForward<gpu>, gridify_up.cu:228-324 (kernels :102-225).                */
+/*  downdata (B,N,4) f32   updata (B,O,4) f32   down/up_actual_numpoints (B) i32                */
+/*  nebidx (B,O,P) i32     nebidxmsk (B,O,P) f32                                               */
+/* ------------------------------------------------------------------------------------------ */
+size_t gridgcn_gridify_up_workspace_bytes(int B, int N, const int grid_size[3]);
+
+int gridgcn_gridify_up_fwd(const float *downdata, const float *updata,
+                           const int *down_actual_numpoints, const int *up_actual_numpoints,
+                           int B, int N, int max_o_grid, int max_p_grid, int kernel_size,
+                           const float coord_shift[3], const float voxel_size[3],
+                           const int grid_size[3], int *nebidx, float *nebidxmsk,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* KNN      -- replaces KNNForward<gpu>, k_nn-inl.h:94-113 (KNNKernel::Map :40-92,             */
+/*             registration k_nn.cc:14-65).   Limit: k <= 128.                                  */
+/* BallKNN  -- replaces BallKNNForward<gpu>, ball_k_nn-inl.h:97-116 (BallKNNKernel::Map        */
+/*             :43-95, registration ball_k_nn.cc:14-65).   Limit: k <= 6 (best[6], :63-64).     */
+/*  unknown (B,n,3) f32   known (B,m,3) f32   downnum, upnum (B) i32   idx (B,n,k) i32         */
+/*  Rows >= upnum[b] are written as 0 (the reference leaves them unwritten, k_nn-inl.h:49-51). */
+/* ------------------------------------------------------------------------------------------ */
+int gridgcn_knn_fwd(const float *unknown, const float *known, const int *downnum,
+                    const int *upnum, int B, int n, int m, int k, int flags, int *idx,
+                    void *stream);
+
+int gridgcn_ball_knn_fwd(const float *unknown, const float *known, const int *downnum,
+                         const int *upnum, int B, int n, int m, int k, float radius, int flags,
+                         int *idx, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* GridConv -- one fused launch per layer that replaces batch_take_g (utils/ops.py:78-93) +     */
+/*             sub_g_update (segmentation/models/gcn_module_g_att.py:172-287: geo features,     */
+/*             verts_pair_func :120-170, aggregation_func :45-79 max pooling, update_func       */
+/*             :24-43, centre mask :284-285), eval-mode BatchNorm folded into the 1x1 convs    */
+/*             (utils/ops.py:149-158).                                                          */
+/*                                                                                              */
+/*  table   (B,Nprev,4+Cin) f32  rows [x y z w | Cin features] of the previous layer           */
+/*                               (Cin = 0 for the first layer: has_feats=False)                 */
+/*  nebidx  (B,O,K) i32          cent (B,O,4) f32       centmsk (B,O) f32                      */
+/*  out     (B,O,4+Cout) f32     rows [cent x y z w | Cout features] = the next layer's table  */
+/*                               (ggcn_models_g.py:186 concat(centers, center_feats))          */
+/*  The MLP is described by `gridgcn_mlp_t`: folded weights W'(C_out,C_in) row-major and bias   */
+/*  b'(C_out) per stage, feature chain first, then the two attention stages.                    */
+/* ------------------------------------------------------------------------------------------ */
+#define GRIDGCN_MAX_STAGES 8
+
+typedef struct {
+    int n_feat_stages;                         /* len(pt_mlp_lst), 1..GRIDGCN_MAX_STAGES-2     */
+    int attfdim;                               /* 10 (seg flavour) or 4 (dist, dxyz) or 0       */
+    int feat_in;                               /* 3 (geo) when Cin==0, else Cin                 */
+    int widths[GRIDGCN_MAX_STAGES];            /* out width of feat stages, then C/4, C for att */
+    const float *weight[GRIDGCN_MAX_STAGES];   /* device, (C_out, C_in) row-major, BN folded    */
+    const float *bias[GRIDGCN_MAX_STAGES];     /* device, (C_out), BN folded                    */
+    int pre_relu;                              /* configs["relu"], gcn_module_g_att.py:31-32    */
+} gridgcn_mlp_t;
+
+#define GRIDGCN_PRECISION_FP32   0  /* CUDA-core fp32 FMA                                      */
+#define GRIDGCN_PRECISION_TF32   1  /* tcgen05 kind::tf32, fp32 accumulate                     */
+#define GRIDGCN_PRECISION_TF32X3 2  /* tcgen05 kind::tf32, 3-term error-compensated split      */
+
+int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cent,
+                         const float *centmsk, int B, int Nprev, int Cin, int O, int K,
+                         const gridgcn_mlp_t *mlp_host, int precision, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDGCN_B200_H_ */

@@ -1,0 +1,84 @@
+"""CPU restatement of the GridConv block -- TEST INFRASTRUCTURE (numpy fp32, op by op).
+
+Follows, op for op, the symbol graph the reference builds for one encoder layer:
+  batch_take_g                       utils/ops.py:78-93   (take mode "clip" after the arange(B)*N offset)
+  transpose to (B, 4+C, O, P)        segmentation/models/ggcn_models_g.py:172-175
+  sub_g_update                       segmentation/models/gcn_module_g_att.py:172-287
+    geo_vec, geo_dist                :189-194
+    att_vec by attfdim               :209-222
+    neighbor_feats (geo when !has_feats) :242-250
+    verts_pair_func                  :120-170  (mlp2d_c = conv1x1 -> BatchNorm(eval) -> relu,
+                                                utils/ops.py:149-158,254-260)
+    max pooling over P               :57-59  (no neighbour mask for max pooling, :259)
+    update_func pre-relu             :31-32
+    centre mask                      :284-285
+  concat(centers, center_feats)      ggcn_models_g.py:186
+BatchNorm runs in eval mode (moving statistics), eps = 1e-3 (MXNet BatchNorm default), fix_gamma
+False -- the mode the reference's own timing harness uses (train_gpu_speed_profiling.py:108).
+
+Parity status: "parity unpinned" (the reference ships no test or golden value for this block and
+MXNet cannot be imported here); this restatement is the pin.  Only tests/, smoke() and bench.py's
+CPU-baseline legs may import it.
+"""
+import numpy as np
+
+F = np.float32
+BN_EPS = 1e-3
+
+
+def _conv_bn_relu(x, st):
+    """x: (B, Cin, O, P) -> (B, Cout, O, P); Convolution(kernel 1x1) -> BatchNorm eval -> relu."""
+    y = np.einsum("oc,bcnp->bonp", st["weight"], x, optimize=True).astype(F)
+    y = (y + st["bias"][None, :, None, None]).astype(F)
+    inv = (F(1.0) / np.sqrt(st["moving_var"] + F(BN_EPS))).astype(F)
+    y = ((y - st["moving_mean"][None, :, None, None]) * inv[None, :, None, None]).astype(F)
+    y = (y * st["gamma"][None, :, None, None] + st["beta"][None, :, None, None]).astype(F)
+    return np.maximum(y, F(0))
+
+
+def batch_take_g(data, index):
+    """data (B, N, C), index (B, O, P) -> (B, O, P, C); utils/ops.py:78-93."""
+    B, N, C = data.shape
+    flat = data.reshape(B * N, C)
+    gi = index.astype(np.int64) + (np.arange(B, dtype=np.int64) * N)[:, None, None]
+    gi = np.clip(gi, 0, B * N - 1)  # mx.symbol.take default mode = clip
+    return flat[gi]
+
+
+def gridconv_layer(table, nebidx, cent, centmsk, layer, pre_relu=True):
+    """One encoder GridConv layer.  table (B,Nprev,4+Cin), nebidx (B,O,P), cent (B,O,4),
+    centmsk (B,O) -> next table (B,O,4+Cout) = concat(cent, feats)."""
+    table = np.asarray(table, F)
+    cent = np.asarray(cent, F)
+    B, O, P = nebidx.shape
+    has_feats = layer["cin"] > 0
+    neighbors = batch_take_g(table, nebidx).transpose(0, 3, 1, 2)  # (B, 4+C, O, P)
+    centers_xyz = cent[:, :, :3].transpose(0, 2, 1)                # (B, 3, O)
+    centers_expand = np.broadcast_to(centers_xyz[:, :, :, None], (B, 3, O, P))
+    nloc = neighbors[:, 0:3]
+    geo_vec = (nloc - centers_expand).astype(F)
+    geo_dist = np.sqrt(np.sum(np.square(geo_vec), axis=1, keepdims=True)).astype(F)
+    attfdim = layer["attfdim"]
+    if attfdim <= 3:
+        att_vec = geo_vec
+    elif attfdim == 4:
+        att_vec = np.concatenate([geo_dist, geo_vec], axis=1)
+    elif attfdim == 10:
+        att_vec = np.concatenate([geo_dist, geo_vec, centers_expand, nloc], axis=1)
+    else:
+        raise NotImplementedError("attfdim %d" % attfdim)
+    feats = neighbors[:, 4:] if has_feats else geo_vec  # localfdim == 0 (seg config)
+    for st in layer["feat"]:
+        feats = _conv_bn_relu(feats, st)
+    if attfdim > 0:
+        a = att_vec
+        for st in layer["att"]:
+            a = _conv_bn_relu(a, st)
+        pair = (a * feats).astype(F)
+    else:
+        pair = feats
+    agg = pair.max(axis=3)  # (B, C, O)
+    if pre_relu:
+        agg = np.maximum(agg, F(0))
+    agg = (agg * np.asarray(centmsk, F)[:, None, :]).astype(F)
+    return np.concatenate([cent, agg.transpose(0, 2, 1)], axis=2).astype(F)

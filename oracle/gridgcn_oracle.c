@@ -1,0 +1,595 @@
+/*
+ * gridgcn_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Sequential CPU restatement of the Grid-GCN native operators (Gridify, GridifyKNN,
+ * GridifyUp, KNN, BallKNN) under the canonical schedule of SURVEY.md section 8(c):
+ * the CUDA "threads" of each reference kernel are executed one after the other in
+ * ascending global thread index, the build kernel completely before the query kernel.
+ * That is a legal schedule of the reference kernels, hence a legal reference output,
+ * and it is the one the sm_100a kernels in grid-gcn_b200/csrc are compared against.
+ *
+ * PARITY STATUS: "parity unpinned" at the reference level.  The reference ships no
+ * tests, golden vectors or known-answer values for these operators, its
+ * Gridify/GridifyKNN/GridifyUp CPU specialisations are LOG(FATAL) stubs
+ * (gridifyop/gridify.cc:30-39, gridifyknn.cc:30-39, gridify_up.cc:29-38) and MXNet is
+ * not installable here, so the restatement below cannot be checked against a run of the
+ * reference.  It is pinned instead by (i) the 27-point lattice sanity vector of
+ * utils/ops.py:282-299, (ii) a second, independently written numpy twin
+ * (oracle/np_twin.py) and (iii) for KNN / BallKNN only, the reference's own kernel bodies
+ * compiled from /root/reference through a shim (oracle/ref_shim, `make ref`).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * may load this library.  Nothing under grid-gcn_b200/ imports it.
+ *
+ * Build:  gcc -O2 -march=native -ffp-contract=off -fopenmp -shared -fPIC  (see Makefile)
+ * -ffp-contract=off is REQUIRED: every fp32 expression below must round exactly where the
+ * source says it rounds (SURVEY.md s8c rule 2, 5, 10).
+ *
+ * Each function cites the reference file:line it follows (paths relative to
+ * /root/reference/gridifyop/).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define DATA_NDIM 4 /* gridify-inl.h: data rows are x,y,z,w */
+
+/* ---------------------------------------------------------------------------------- */
+/* XORWOW, for the optional strict reproduction of K2's schedule-independent reservoir  */
+/* (gridify.cu:260-262).  Follows /usr/local/cuda/include/curand_kernel.h:772-798       */
+/* (curand_init with subsequence 0, offset 0 => no skip-ahead) and :863-874 (curand),   */
+/* curand_uniform.h:69-72.                                                              */
+/* ---------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t d, v[5];
+} xorwow_t;
+
+static void xorwow_init(xorwow_t *s, uint64_t seed) {
+    uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u;
+    uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    uint32_t t0 = 1099087573u * s0;
+    uint32_t t1 = 2591861531u * s1;
+    s->d = 6615241u + t1 + t0;
+    s->v[0] = 123456789u + t0;
+    s->v[1] = 362436069u ^ t0;
+    s->v[2] = 521288629u + t1;
+    s->v[3] = 88675123u ^ t1;
+    s->v[4] = 5783321u + t0;
+}
+
+static uint32_t xorwow_next(xorwow_t *s) {
+    uint32_t t = (s->v[0] ^ (s->v[0] >> 2));
+    s->v[0] = s->v[1];
+    s->v[1] = s->v[2];
+    s->v[2] = s->v[3];
+    s->v[3] = s->v[4];
+    s->v[4] = (s->v[4] ^ (s->v[4] << 4)) ^ (t ^ (t << 1));
+    s->d += 362437u;
+    return s->v[4] + s->d;
+}
+
+/* curand_uniform: x * 2^-32 + 2^-33.  nvcc contracts this to one FFMA on the device, so
+ * the strict mode uses fmaf (the only place in this file where an FMA is intended).    */
+static float xorwow_uniform(xorwow_t *s) {
+    return fmaf((float)xorwow_next(s), 2.3283064e-10f, 2.3283064e-10f / 2.0f);
+}
+
+/* ---------------------------------------------------------------------------------- */
+/* Shared pieces                                                                        */
+/* ---------------------------------------------------------------------------------- */
+
+/* gridify.cu:134-140 (identical in gridifyknn.cu:147-153, gridify_up.cu:133-139,190-197):
+ *   int c = floor((p[j] + shift[j]) / voxel[j]);  if (c < 0 || c >= grid[j]) return;
+ * fp32 add, IEEE fp32 divide, floor, int conversion; the upper bound is tested against
+ * the FLOAT grid size (d_grid_size is float*).                                          */
+static int voxelise(const float *p, const float *shift, const float *voxel,
+                    const float *gridf, int coor[3]) {
+    for (int j = 0; j < 3; j++) {
+        float t = p[j] + shift[j];
+        float q = t / voxel[j];
+        int c = (int)floorf(q);
+        if (c < 0 || (float)c >= gridf[j]) return 0;
+        coor[j] = c;
+    }
+    return 1;
+}
+
+/* gridify.cu:141-142: the linear index is evaluated in float and truncated.            */
+static int linear_index(const int coor[3], const float *gridf) {
+    float f = (float)coor[2] * (gridf[0] * gridf[1]) + (float)coor[1] * gridf[0] + (float)coor[0];
+    return (int)f;
+}
+
+/* gridify.cu:244-246: neighbour voxel index inside one cloud, float evaluation.        */
+static int linear_index3(int d, int h, int w, const float *gridf) {
+    float f = (float)d * (gridf[0] * gridf[1]) + (float)h * gridf[0] + (float)w;
+    return (int)f;
+}
+
+/* gridify.cu:231-234: decode the centre voxel with float divisions + int truncation.   */
+static void decode_center(int coor, const float *gridf, int *c2, int *c1, int *c0) {
+    float gxy = gridf[0] * gridf[1];
+    int coor2 = (int)((float)coor / gxy);
+    int coor1 = (int)(((float)coor - (float)coor2 * gxy) / gridf[0]);
+    int coor0 = (int)((float)coor - (float)coor2 * gxy - (float)coor1 * gridf[0]);
+    *c2 = coor2;
+    *c1 = coor1;
+    *c0 = coor0;
+}
+
+static inline int in_grid(int d, int h, int w, const float *gridf) {
+    return d >= 0 && (float)d < gridf[2] && h >= 0 && (float)h < gridf[1] && w >= 0 &&
+           (float)w < gridf[0];
+}
+
+/* squared distance, gridifyknn.cu:287 / k_nn-inl.h:73 / ball_k_nn-inl.h:76.
+ * fma_mode 0 (canonical, SURVEY s8c rule 10): ((dx*dx + dy*dy) + dz*dz), every product and
+ * sum rounded.  fma_mode 1: the contraction ptxas chose in the shipped sm_75 cubin of
+ * additional.so (FMUL, FFMA, FFMA at SASS offsets 0x0df0-0x0e20 of
+ * gridifyKNN_kernel_query_neighs<float>): fma(dz,dz, fma(dy,dy, dx*dx)).                */
+static inline float dist2(float ux, float uy, float uz, float x, float y, float z, int fma_mode) {
+    float dx = ux - x, dy = uy - y, dz = uz - z;
+    if (fma_mode) return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    float a = dx * dx;
+    float b = dy * dy;
+    float c = dz * dz;
+    float ab = a + b;
+    return ab + c;
+}
+
+typedef struct {
+    int *coor_to_voxelidx; /* G   : -1 empty, 0 claimed (gridify.cu:165-171)            */
+    int *voxelidx_to_coor; /* O                                                          */
+    int *coor_to_pntidx;   /* G*P                                                        */
+    float *coor_to_locxyzw; /* G*4                                                       */
+    int *coor_counter;     /* G                                                          */
+} gridify_scratch_t;
+
+static int scratch_alloc(gridify_scratch_t *s, int G, int O, int P) {
+    s->coor_to_voxelidx = (int *)malloc(sizeof(int) * (size_t)G);
+    s->voxelidx_to_coor = (int *)malloc(sizeof(int) * (size_t)(O > 0 ? O : 1));
+    s->coor_to_pntidx = (int *)malloc(sizeof(int) * (size_t)G * (size_t)P);
+    s->coor_to_locxyzw = (float *)malloc(sizeof(float) * (size_t)G * DATA_NDIM);
+    s->coor_counter = (int *)malloc(sizeof(int) * (size_t)G);
+    return s->coor_to_voxelidx && s->voxelidx_to_coor && s->coor_to_pntidx &&
+           s->coor_to_locxyzw && s->coor_counter;
+}
+
+static void scratch_free(gridify_scratch_t *s) {
+    free(s->coor_to_voxelidx);
+    free(s->voxelidx_to_coor);
+    free(s->coor_to_pntidx);
+    free(s->coor_to_locxyzw);
+    free(s->coor_counter);
+}
+
+/* gridify.cu:361-365 : the per-call memsets (coor_to_pntidx is NOT cleared there).      */
+static void scratch_reset(gridify_scratch_t *s, int G) {
+    memset(s->coor_to_locxyzw, 0, sizeof(float) * (size_t)G * DATA_NDIM);
+    memset(s->coor_counter, 0, sizeof(int) * (size_t)G);
+    memset(s->coor_to_voxelidx, 0xff, sizeof(int) * (size_t)G);
+}
+
+/* GridifyOp::Forward output initialisation, gridify-inl.h:117-121.                      */
+static void init_outputs(int *nebidx, float *nebmsk, float *cent, float *centmsk, int *centnum,
+                         int O, int P) {
+    for (int i = 0; i < O * P; i++) nebidx[i] = 0;
+    for (int i = 0; i < O * P; i++) nebmsk[i] = 0.0f;
+    for (int i = 0; i < O * DATA_NDIM; i++) cent[i] = 1.0f;
+    for (int i = 0; i < O; i++) centmsk[i] = 0.0f;
+    centnum[0] = 0;
+}
+
+/* K1 = K3: gridify_kernel_build_index, gridify.cu:126-190 (== gridifyknn.cu:139-203),
+ * one cloud, threads i_pt = 0..npts-1 executed in ascending order.
+ * Canonical overflow rule (SURVEY s8c rule 7): keep-first, i.e. the time-seeded reservoir
+ * branches (gridify.cu:148-153, :181-186) never replace.                                */
+static void build_index_cloud(const float *data, int npts, int O, int P, int loc,
+                              const float *shift, const float *voxel, const float *gridf,
+                              gridify_scratch_t *s, float *centmsk, int *centcount) {
+    int ncent = 0;
+    for (int i_pt = 0; i_pt < npts; i_pt++) {
+        const float *p_pt = data + (size_t)i_pt * DATA_NDIM;
+        int coor[3];
+        if (!voxelise(p_pt, shift, voxel, gridf, coor)) continue; /* :136-138 return */
+        int coor_indx = linear_index(coor, gridf);                  /* :141-142 */
+        int grid_pntidx = s->coor_counter[coor_indx]++;             /* :145 atomicAdd */
+        if (grid_pntidx < P) {
+            s->coor_to_pntidx[(size_t)coor_indx * P + grid_pntidx] = i_pt; /* :147 */
+        } /* else: keep-first */
+        if (loc == 1) { /* :155-162, product rounded, then added */
+            float *acc = s->coor_to_locxyzw + (size_t)coor_indx * DATA_NDIM;
+            float weight = p_pt[3];
+            float px = p_pt[0] * weight;
+            float py = p_pt[1] * weight;
+            float pz = p_pt[2] * weight;
+            acc[0] = acc[0] + px;
+            acc[1] = acc[1] + py;
+            acc[2] = acc[2] + pz;
+            acc[3] = acc[3] + weight;
+        }
+        if (s->coor_to_voxelidx[coor_indx] == -1) { /* :165-171 CAS -1 -> 0 */
+            s->coor_to_voxelidx[coor_indx] = 0;
+            int tmp = ncent++; /* :175 atomicAdd(out_actual_centnum) */
+            if (tmp < O) {
+                s->voxelidx_to_coor[tmp] = coor_indx; /* :178 */
+                centmsk[tmp] = 1.0f;                  /* :179 */
+            } /* else: keep-first */
+        }
+    }
+    *centcount = ncent;
+}
+
+/* loc==1 epilogue common to K2 and K4: gridify.cu:280-288 / gridifyknn.cu:322-330.      */
+static void write_center_xyz(float *cent_row, const float *acc) {
+    float xsum = acc[0], ysum = acc[1], zsum = acc[2], wsum = acc[3];
+    cent_row[0] = xsum / wsum;
+    cent_row[1] = ysum / wsum;
+    cent_row[2] = zsum / wsum;
+}
+
+/* K2: gridify_kernel_query_neighs, gridify.cu:218-290, one cloud, centres ascending.
+ * strict != 0 reproduces the deterministic-seed reservoir of :259-270 with host XORWOW;
+ * strict == 0 is the canonical keep-first rule.                                          */
+static void query_neighs_cloud(const float *data, int b, int O, int P, int ks, int loc,
+                               const float *gridf, const gridify_scratch_t *s, int ncent_raw,
+                               int strict, int *nebidx, float *nebmsk, float *cent,
+                               int *centnum) {
+    int ncent = ncent_raw > O ? O : ncent_raw; /* :222-224 */
+    centnum[0] = ncent;
+    const int size = ks * ks * ks;
+    const int r = (ks - 1) / 2;
+    for (int o = 0; o < ncent; o++) {
+        int coor2, coor1, coor0;
+        decode_center(s->voxelidx_to_coor[o], gridf, &coor2, &coor1, &coor0);
+        int grid_pntidx = 0, initID = 0, origin = -1;
+        float total_weight = 0.0f;
+        int *row = nebidx + (size_t)o * P;
+        float *mrow = nebmsk + (size_t)o * P;
+        for (int nei_idx = 0; nei_idx < size; nei_idx++) {
+            int d = nei_idx / (ks * ks) - r + coor2;
+            int h = (nei_idx % (ks * ks)) / ks - r + coor1;
+            int w = nei_idx % ks - r + coor0;
+            if (!in_grid(d, h, w, gridf)) continue;
+            int v = linear_index3(d, h, w, gridf);
+            if (nei_idx * 2 + 1 == size) origin = v; /* :248 */
+            int amount = s->coor_counter[v] < P ? s->coor_counter[v] : P; /* :249 */
+            for (int j = 0; j < amount; j++) {
+                if (grid_pntidx++ < P) { /* :251-258 */
+                    int idx = s->coor_to_pntidx[(size_t)v * P + j];
+                    if (grid_pntidx == 1) initID = idx;
+                    int eleweight = (int)data[(size_t)idx * DATA_NDIM + 3]; /* int decl :227 */
+                    row[grid_pntidx - 1] = idx;
+                    mrow[grid_pntidx - 1] = 1.0f;
+                    total_weight = total_weight + (float)eleweight;
+                } else if (strict) { /* :259-270 */
+                    /* seed = index_P * size + grid_pntidx evaluated in 32-bit int */
+                    uint32_t index_P = (uint32_t)(b * O + o) * (uint32_t)P;
+                    int32_t seed32 = (int32_t)(index_P * (uint32_t)size + (uint32_t)grid_pntidx);
+                    xorwow_t st;
+                    xorwow_init(&st, (uint64_t)(int64_t)seed32);
+                    int insrtidx = (int)(ceilf(xorwow_uniform(&st) * (float)grid_pntidx)) - 1;
+                    if (insrtidx < P) {
+                        float oldweight = data[(size_t)row[insrtidx] * DATA_NDIM + 3];
+                        int idx = s->coor_to_pntidx[(size_t)v * P + j];
+                        int eleweight = (int)data[(size_t)idx * DATA_NDIM + 3];
+                        row[insrtidx] = idx;
+                        total_weight = total_weight + ((float)eleweight - oldweight);
+                    }
+                }
+            }
+        }
+        cent[(size_t)o * DATA_NDIM + 3] = total_weight; /* :274 */
+        if (grid_pntidx < P) {                           /* :275-279 */
+            for (int j = grid_pntidx; j < P; j++) row[j] = initID;
+        }
+        if (loc == 1 && origin >= 0) /* :280-288 */
+            write_center_xyz(cent + (size_t)o * DATA_NDIM,
+                             s->coor_to_locxyzw + (size_t)origin * DATA_NDIM);
+    }
+}
+
+/* K4: gridifyKNN_kernel_query_neighs, gridifyknn.cu:231-332, one cloud.
+ * Oracle definitions for the reference's uninitialised reads (SURVEY s8c rule 8):
+ * best[0..P) = FLT_MAX; when fewer than P candidates exist the weight sum runs over the
+ * found candidates only and slots [found,P) are padded with besti[0].                    */
+static void query_knn_cloud(const float *data, int O, int P, int ks, int loc,
+                            const float *voxel, const float *gridf, const gridify_scratch_t *s,
+                            int ncent_raw, int fma_mode, int *nebidx, float *nebmsk, float *cent,
+                            int *centnum, float *best, int *besti) {
+    int ncent = ncent_raw > O ? O : ncent_raw; /* :235-237 */
+    centnum[0] = ncent;
+    for (int o = 0; o < ncent; o++) {
+        int coor2, coor1, coor0;
+        decode_center(s->voxelidx_to_coor[o], gridf, &coor2, &coor1, &coor0);
+        /* :253-255  (int + 0.5) is double, times float -> double, rounded to float */
+        float ux = (float)(((double)coor0 + 0.5) * (double)voxel[0]);
+        float uy = (float)(((double)coor1 + 0.5) * (double)voxel[1]);
+        float uz = (float)(((double)coor2 + 0.5) * (double)voxel[2]);
+        for (int l = 0; l < P; l++) {
+            best[l] = FLT_MAX;
+            besti[l] = 0;
+        }
+        int need_P = P, found = 0, origin = -1;
+        for (int layer = 0; layer < (ks + 1) / 2; layer++) { /* :264 */
+            int amount_layer = 0;
+            for (int w = -layer; w < layer + 1; w++)
+                for (int h = -layer; h < layer + 1; h++)
+                    for (int d = -layer; d < layer + 1; d++) {
+                        int aw = w < 0 ? -w : w, ah = h < 0 ? -h : h, ad = d < 0 ? -d : d;
+                        int m = aw > ah ? aw : ah;
+                        m = m > ad ? m : ad;
+                        if (m != layer) continue; /* :269 */
+                        int dc = d + coor2, hc = h + coor1, wc = w + coor0;
+                        if (!in_grid(dc, hc, wc, gridf)) continue;
+                        int v = linear_index3(dc, hc, wc, gridf);
+                        if (layer == 0) origin = v; /* :279 */
+                        int amount = s->coor_counter[v] < P ? s->coor_counter[v] : P;
+                        amount_layer += amount;
+                        for (int g = 0; g < amount; g++) {
+                            int idx = s->coor_to_pntidx[(size_t)v * P + g];
+                            const float *q = data + (size_t)idx * DATA_NDIM;
+                            float dst = dist2(ux, uy, uz, q[0], q[1], q[2], fma_mode);
+                            for (int l = 0; l < P; l++) { /* :288-298 strict < */
+                                if (dst < best[l]) {
+                                    for (int j = P - 1; j > l; j--) {
+                                        best[j] = best[j - 1];
+                                        besti[j] = besti[j - 1];
+                                    }
+                                    best[l] = dst;
+                                    besti[l] = idx;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+            found += amount_layer;
+            need_P = need_P - amount_layer; /* :304 */
+            if (need_P <= 0) break;         /* :305 */
+        }
+        if (found > P) found = P;
+        int *row = nebidx + (size_t)o * P;
+        float *mrow = nebmsk + (size_t)o * P;
+        float total_weight = 0.0f;
+        for (int l = 0; l < P; l++) { /* :308-314 */
+            mrow[l] = 1.0f;
+            if (l < found) {
+                row[l] = besti[l];
+                int eleweight = (int)data[(size_t)besti[l] * DATA_NDIM + 3];
+                total_weight = total_weight + (float)eleweight;
+            }
+        }
+        cent[(size_t)o * DATA_NDIM + 3] = total_weight; /* :316 */
+        for (int j = found; j < P; j++) row[j] = besti[0]; /* :317-321 */
+        if (loc == 1 && origin >= 0)
+            write_center_xyz(cent + (size_t)o * DATA_NDIM,
+                             s->coor_to_locxyzw + (size_t)origin * DATA_NDIM);
+    }
+}
+
+static void set_gridf(const int grid[3], float gridf[3]) {
+    for (int j = 0; j < 3; j++) gridf[j] = (float)grid[j]; /* gridify.cu:343-347 */
+}
+
+static int g_num_threads = 1;
+
+void gridgcn_oracle_set_threads(int n) { g_num_threads = n > 0 ? n : 1; }
+
+int gridgcn_oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* Gridify: gridify-inl.h:99-128 + gridify.cu:294-413.  Returns 0, or -1 on allocation
+ * failure / invalid arguments.  Clouds are independent (i_batch only offsets the tables,
+ * gridify.cu:127,143), so they may run on different host threads without changing the
+ * canonical result.                                                                      */
+static int gridify_common(int knn, const float *data, const int *npts, int B, int N, int O, int P,
+                          int ks, int loc, const float shift[3], const float voxel[3],
+                          const int grid[3], int mode, int *nebidx, float *nebmsk, float *cent,
+                          float *centmsk, int *centnum) {
+    if (B < 0 || N < 0 || O < 1 || P < 1 || ks < 1 || (ks & 1) == 0) return -1;
+    float gridf[3];
+    set_gridf(grid, gridf);
+    const long G = (long)grid[0] * grid[1] * grid[2];
+    if (G <= 0 || G >= (1L << 24)) return -1; /* float linear index exact only below 2^24 */
+    int err = 0;
+#pragma omp parallel num_threads(g_num_threads)
+    {
+        gridify_scratch_t s;
+        float *best = (float *)malloc(sizeof(float) * (size_t)P);
+        int *besti = (int *)malloc(sizeof(int) * (size_t)P);
+        int ok = scratch_alloc(&s, (int)G, O, P) && best && besti;
+        if (!ok) {
+#pragma omp atomic write
+            err = -1;
+        }
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; b++) {
+            if (!ok) continue;
+            int *nb = nebidx + (size_t)b * O * P;
+            float *nm = nebmsk + (size_t)b * O * P;
+            float *ce = cent + (size_t)b * O * DATA_NDIM;
+            float *cm = centmsk + (size_t)b * O;
+            int *cn = centnum + b;
+            const float *d = data + (size_t)b * N * DATA_NDIM;
+            int n = npts[b] < N ? npts[b] : N;
+            init_outputs(nb, nm, ce, cm, cn, O, P);
+            scratch_reset(&s, (int)G);
+            int ncent = 0;
+            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &ncent);
+            if (knn)
+                query_knn_cloud(d, O, P, ks, loc, voxel, gridf, &s, ncent, mode, nb, nm, ce, cn,
+                                best, besti);
+            else
+                query_neighs_cloud(d, b, O, P, ks, loc, gridf, &s, ncent, mode, nb, nm, ce, cn);
+        }
+        scratch_free(&s);
+        free(best);
+        free(besti);
+    }
+    return err;
+}
+
+int gridgcn_oracle_gridify(const float *data, const int *npts, int B, int N, int O, int P, int ks,
+                           int loc, const float shift[3], const float voxel[3],
+                           const int grid[3], int strict_reservoir, int *nebidx, float *nebmsk,
+                           float *cent, float *centmsk, int *centnum) {
+    return gridify_common(0, data, npts, B, N, O, P, ks, loc, shift, voxel, grid,
+                          strict_reservoir, nebidx, nebmsk, cent, centmsk, centnum);
+}
+
+int gridgcn_oracle_gridify_knn(const float *data, const int *npts, int B, int N, int O, int P,
+                               int ks, int loc, const float shift[3], const float voxel[3],
+                               const int grid[3], int dist_fma, int *nebidx, float *nebmsk,
+                               float *cent, float *centmsk, int *centnum) {
+    return gridify_common(1, data, npts, B, N, O, P, ks, loc, shift, voxel, grid, dist_fma,
+                          nebidx, nebmsk, cent, centmsk, centnum);
+}
+
+/* GridifyUp: gridify_up-inl.h:111-112 (outputs 0) + gridify_up.cu:121-169 (K5 build, the
+ * B*N*size thread grid is i-major / t-minor, :121-123) + :190-224 (K6 query).
+ * Keep-first on bucket overflow; empty bucket => ids 0 (oracle definition for the
+ * reference's uninitialised initID, gridify_up.cu:211-221).                              */
+int gridgcn_oracle_gridify_up(const float *downdata, const float *updata, const int *downnum,
+                              const int *upnum, int B, int N, int O, int P, int ks,
+                              const float shift[3], const float voxel[3], const int grid[3],
+                              int *nebidx, float *nebmsk) {
+    if (B < 0 || N < 0 || O < 1 || P < 1 || ks < 1 || (ks & 1) == 0) return -1;
+    float gridf[3];
+    set_gridf(grid, gridf);
+    const long G = (long)grid[0] * grid[1] * grid[2];
+    if (G <= 0 || G >= (1L << 24)) return -1;
+    const int size = ks * ks * ks, r = (ks - 1) / 2;
+    int err = 0;
+#pragma omp parallel num_threads(g_num_threads)
+    {
+        int *bucket = (int *)malloc(sizeof(int) * (size_t)G * P);
+        int *counter = (int *)malloc(sizeof(int) * (size_t)G);
+        int ok = bucket && counter;
+        if (!ok) {
+#pragma omp atomic write
+            err = -1;
+        }
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; b++) {
+            if (!ok) continue;
+            int *nb = nebidx + (size_t)b * O * P;
+            float *nm = nebmsk + (size_t)b * O * P;
+            for (int i = 0; i < O * P; i++) {
+                nb[i] = 0;
+                nm[i] = 0.0f;
+            }
+            memset(counter, 0, sizeof(int) * (size_t)G);
+            memset(bucket, 0, sizeof(int) * (size_t)G * P); /* gridify_up.cu:290 */
+            const float *dd = downdata + (size_t)b * N * DATA_NDIM;
+            int nd = downnum[b] < N ? downnum[b] : N;
+            for (int i_pt = 0; i_pt < nd; i_pt++) {
+                int coor[3];
+                if (!voxelise(dd + (size_t)i_pt * DATA_NDIM, shift, voxel, gridf, coor)) continue;
+                for (int t = 0; t < size; t++) {
+                    int d = t / (ks * ks) - r + coor[2];
+                    int h = (t % (ks * ks)) / ks - r + coor[1];
+                    int w = t % ks - r + coor[0];
+                    if (!in_grid(d, h, w, gridf)) continue;
+                    int v = linear_index3(d, h, w, gridf);
+                    int slot = counter[v]++; /* :157 atomicAdd */
+                    if (slot < P) bucket[(size_t)v * P + slot] = i_pt;
+                }
+            }
+            const float *ud = updata + (size_t)b * O * DATA_NDIM;
+            int nu = upnum[b] < O ? upnum[b] : O;
+            for (int o = 0; o < nu; o++) {
+                int coor[3];
+                if (!voxelise(ud + (size_t)o * DATA_NDIM, shift, voxel, gridf, coor)) continue;
+                int v = linear_index(coor, gridf);
+                int countlimit = counter[v];
+                int initID = 0;
+                for (int j = 0; j < P; j++) { /* :211-222 */
+                    if (j < countlimit) {
+                        int idx = bucket[(size_t)v * P + j];
+                        if (j == 0) initID = idx;
+                        nb[(size_t)o * P + j] = idx;
+                        nm[(size_t)o * P + j] = 1.0f;
+                    } else {
+                        nb[(size_t)o * P + j] = initID;
+                    }
+                }
+            }
+        }
+        free(bucket);
+        free(counter);
+    }
+    return err;
+}
+
+/* KNNKernel::Map, k_nn-inl.h:46-91.  ball_radius < 0 => KNN; otherwise
+ * BallKNNKernel::Map, ball_k_nn-inl.h:49-93 (besti init -1, `d > radius*radius` skip).
+ * Rows >= upnum[b] are never written by the reference (k_nn-inl.h:49-51); the oracle
+ * defines them as 0.  KNN slots beyond the number of known points: oracle defines 0.
+ * The row loop is an OpenMP for, as MXNet's CPU launcher (k_nn-inl.h:109) is.           */
+static int knn_common(const float *unknown, const float *known, const int *downnum,
+                      const int *upnum, int B, int n, int m, int k, int is_ball, float radius,
+                      int fma_mode, int *idx) {
+    if (B < 0 || n < 0 || m < 0 || k < 1) return -1;
+    if (is_ball && k > 6) return -1; /* best[6], ball_k_nn-inl.h:63-64 */
+    const float r2 = radius * radius;
+#pragma omp parallel num_threads(g_num_threads)
+    {
+        float *best = (float *)malloc(sizeof(float) * (size_t)k);
+        int *besti = (int *)malloc(sizeof(int) * (size_t)k);
+#pragma omp for schedule(static)
+        for (long i = 0; i < (long)B * n; i++) {
+            int b = (int)(i / n);
+            int *out = idx + (size_t)i * k;
+            for (int l = 0; l < k; l++) out[l] = 0;
+            int downnum_val = downnum[b] < m ? downnum[b] : m;
+            if ((int)(i % n) >= upnum[b]) continue;
+            const float *kn = known + (size_t)b * m * 3;
+            const float *u = unknown + (size_t)i * 3;
+            float ux = u[0], uy = u[1], uz = u[2];
+            for (int l = 0; l < k; l++) {
+                best[l] = FLT_MAX;
+                besti[l] = is_ball ? -1 : 0;
+            }
+            for (int kk = 0; kk < downnum_val; ++kk) {
+                float d = dist2(ux, uy, uz, kn[kk * 3 + 0], kn[kk * 3 + 1], kn[kk * 3 + 2], fma_mode);
+                if (is_ball && d > r2) continue;
+                for (int l = 0; l < k; l++) {
+                    if (d < best[l]) {
+                        for (int j = k - 1; j > l; j--) {
+                            best[j] = best[j - 1];
+                            besti[j] = besti[j - 1];
+                        }
+                        best[l] = d;
+                        besti[l] = kk;
+                        break;
+                    }
+                }
+            }
+            for (int l = 0; l < k; l++) out[l] = besti[l];
+        }
+        free(best);
+        free(besti);
+    }
+    return 0;
+}
+
+int gridgcn_oracle_knn(const float *unknown, const float *known, const int *downnum,
+                       const int *upnum, int B, int n, int m, int k, int dist_fma, int *idx) {
+    return knn_common(unknown, known, downnum, upnum, B, n, m, k, 0, 0.0f, dist_fma, idx);
+}
+
+int gridgcn_oracle_ball_knn(const float *unknown, const float *known, const int *downnum,
+                            const int *upnum, int B, int n, int m, int k, float radius,
+                            int dist_fma, int *idx) {
+    return knn_common(unknown, known, downnum, upnum, B, n, m, k, 1, radius, dist_fma, idx);
+}

@@ -1,0 +1,88 @@
+"""CPU suite, part 2: the C-ABI library builds for sm_100a without a GPU, loads, and exports every
+symbol include/gridgcn_b200.h declares; argument validation returns codes instead of launching."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gridgcn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gridgcn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    syms = _declared_symbols()
+    for s in ("gridgcn_gridify_fwd", "gridgcn_gridify_knn_fwd", "gridgcn_gridify_up_fwd",
+              "gridgcn_knn_fwd", "gridgcn_ball_knn_fwd", "gridgcn_gridconv_fwd"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(gg):
+    lib = ctypes.CDLL(gg._lib.LIB_PATH)
+    for s in _declared_symbols():
+        assert hasattr(lib, s), "libgridgcn_b200.so does not export %s" % s
+    assert set(gg._lib.SIGNATURES) == set(_declared_symbols())
+    assert gg._lib.lib().gridgcn_abi_version() == 1
+
+
+def test_library_is_sm100a_native(gg):
+    """The cubin inside the library targets sm_100a (no PTX-JIT fallback to an older arch)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", gg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_argument_validation_without_gpu(gg):
+    """Rejected arguments never reach a launch, so these calls are safe on a CPU-only box."""
+    L = gg._lib.lib()
+    g3, f3 = gg._lib.triple_i([40] * 3), gg._lib.triple_f([0.05] * 3)
+    assert L.gridgcn_gridify_workspace_bytes(2, 1024, 1024, g3) > 0
+    assert L.gridgcn_gridify_workspace_bytes(2, 1024, 1024, gg._lib.triple_i([128] * 3)) == 0
+    null = None
+    # null pointers
+    rc = L.gridgcn_gridify_fwd(null, null, 1, 8, 4, 4, 3, 1, 1, f3, f3, g3, 0, null, null, null, null,
+                               null, null, 0, null)
+    assert rc == -1
+    # even kernel size (coor_indx_b_origin undefined in the reference, gridify.cu:248)
+    rc = L.gridgcn_gridify_fwd(16, 16, 1, 8, 4, 4, 2, 1, 1, f3, f3, g3, 0, 16, 16, 16, 16, 16, 16, 0, null)
+    assert rc == -1
+    # P > 128 (best[128], gridifyknn.cu:257)
+    rc = L.gridgcn_gridify_knn_fwd(16, 16, 1, 8, 4, 129, 3, 1, 1, f3, f3, g3, 0, 16, 16, 16, 16, 16, 16,
+                                   0, null)
+    assert rc == -2
+    # workspace too small
+    rc = L.gridgcn_gridify_fwd(16, 16, 1, 8, 4, 4, 3, 1, 1, f3, f3, g3, 0, 16, 16, 16, 16, 16, 16, 8, null)
+    assert rc == -3
+    # BallKNN k > 6 (best[6], ball_k_nn-inl.h:63-64)
+    assert L.gridgcn_ball_knn_fwd(16, 16, 16, 16, 1, 4, 4, 7, 0.5, 0, 16, null) == -2
+    assert L.gridgcn_knn_fwd(16, 16, 16, 16, 1, 4, 4, 0, 0, 16, null) == -1
+    assert b"range" in L.gridgcn_strerror(-2)
+
+
+def test_ops_refuse_cpu_tensors(gg):
+    import torch
+    data = torch.zeros(1, 8, 4)
+    num = torch.full((1, 1), 8, dtype=torch.int32)
+    kw = dict(max_p_grid=4, max_o_grid=4, kernel_size=3, coord_shift=[1] * 3, voxel_size=[0.5] * 3,
+              grid_size=[4] * 3)
+    for fn in (gg.Gridify, gg.GridifyKNN):
+        with pytest.raises(gg._lib.GridGcnError):
+            fn(data, num, **kw)
+    with pytest.raises(gg._lib.GridGcnError):
+        gg.contrib.KNN(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3), num, num, k=3)
+
+
+def test_missing_library_fails_loudly(gg, monkeypatch):
+    monkeypatch.setattr(gg._lib, "_lib", None)
+    monkeypatch.setattr(gg._lib, "LIB_PATH", "/nonexistent/libgridgcn_b200.so")
+    with pytest.raises(gg._lib.GridGcnError):
+        gg._lib.lib()

@@ -1,0 +1,59 @@
+"""CPU suite, part 3: host-side logic of the product (BN folding, parameter naming, ladders,
+synthetic inputs) -- no GPU needed."""
+import numpy as np
+
+from gridgcn_b200 import gridconv, stack, synth
+
+
+def test_fold_bn_matches_conv_bn():
+    from oracle import gridconv_oracle
+    rng = np.random.default_rng(0)
+    st = gridconv.init_stage(rng, 10, 16)
+    x = rng.normal(size=(2, 10, 3, 5)).astype(np.float32)
+    ref = gridconv_oracle._conv_bn_relu(x, st)
+    w, b = gridconv.fold_bn(st["weight"], st["bias"], st["gamma"], st["beta"], st["moving_mean"],
+                            st["moving_var"])
+    got = np.maximum(np.einsum("oc,bcnp->bonp", w, x) + b[None, :, None, None], 0)
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_named_params_follow_reference_scopes():
+    layer = gridconv.init_layer(np.random.default_rng(0), 0, [32, 32, 64], 10)
+    names = gridconv.named_params(layer, "sub_g_0")
+    assert "sub_g_0/conv1_weight" in names and names["sub_g_0/conv1_weight"].shape == (32, 3)
+    assert names["sub_g_0/conv3/bn_moving_var"].shape == (64,)
+    assert names["sub_g_0/update_att_mlp2d_frst/conv1_weight"].shape == (16, 10)
+    assert names["sub_g_0/update_att_mlp2d_scnd/conv1_weight"].shape == (64, 16)
+
+
+def test_ladders_match_reference_configs():
+    s = stack.seg8192_shipped()  # segmentation/configs/configs.yaml:72-77
+    assert [l.max_o_grid for l in s.layers] == [1024, 256, 24]
+    assert [l.max_p_grid for l in s.layers] == [64, 32, 32]
+    assert [l.grid_size for l in s.layers] == [40, 15, 5]
+    assert stack.seg81920_shipped().layers[0].max_p_grid == 128  # configs.yaml:151
+    s4 = stack.seg8192_4layer(64)
+    assert [l.max_o_grid for l in s4.layers] == [1024, 256, 64, 16]
+    assert [list(l.pt_mlp_lst) for l in s4.layers][3] == [256, 256, 512]
+    params = stack.init_params(s4)
+    assert [p["cin"] for p in params] == [0, 64, 128, 256]
+    # per-edge MAC counts of SURVEY.md s8a
+    macs = []
+    for p in params:
+        m = sum(st["weight"].size for st in p["feat"]) + sum(st["weight"].size for st in p["att"])
+        macs.append(m)
+    assert macs == [4352, 20800, 82560, 328960]
+
+
+def test_synthetic_clouds():
+    data, npts = synth.make_batch(3, 1024, seed0=0)
+    assert data.shape == (3, 1024, 4) and data.dtype == np.float32 and npts.tolist() == [[1024]] * 3
+    assert np.all(data[..., 3] == 1.0)
+    assert np.abs(data[..., :3]).max() <= 1.0 + 1e-6
+    for b in range(3):
+        assert len(np.unique(data[b, :, :3], axis=0)) == 1024  # no duplicates
+    q = (data[..., :3] + np.float32(1.0)) / np.float32(0.05)
+    frac = q - np.floor(q)
+    assert frac.min() > 5e-5 and frac.max() < 1 - 5e-5  # away from voxel faces
+    again, _ = synth.make_batch(3, 1024, seed0=0)
+    assert np.array_equal(data, again)
