@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- points/sec through the 4-layer GridConv stack @ N=8192, K=64 (BASELINE.json metric).
+
+A "step" is one pass of the hot path (per layer: GridifyKNN voxel-hash build + query, fused
+GridConv) over one batch of synthetic 8192-point clouds.  One process per GPU; clouds are
+independent, so ranks shard the batch with no data-path collective ("scaling": "weak").
+
+  python bench.py --gpus 1 --steps 20 --warmup 5            # this framework (CUDA, sm_100a)
+  python bench.py --impl reference ...                      # CPU arm: the oracle port of the
+                                                            # reference's algorithm on host cores
+
+Prints ONE JSON line on rank 0 (see the task contract): value = whole-job points/sec with inputs
+resident in HBM; e2e = the same through the public API with pinned HOST buffers (H2D + D2H inside
+the timed region); roofline = dominant kernel vs MEASURED_PEAKS.json; roofline_hbm = the
+gridifyknn operator vs the measured HBM copy bandwidth; cpu_baseline = the oracle on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                p = json.load(f)
+            if "hbm_gbs" in p and "bf16_tflops" in p:
+                p["_source"] = "measured"
+                return p
+        except Exception:
+            pass
+    p = dict(FALLBACK_PEAKS)
+    p["_source"] = "fallback"
+    return p
+
+
+def gridify_bytes(N, O, P):
+    """Algorithmic HBM bytes of one Gridify/GridifyKNN call per cloud:
+    read 16N, write nebidx + mask 8*O*P, cent 16*O, centmsk 4*O, centnum 4."""
+    return 16 * N + 8 * O * P + 16 * O + 4 * O + 4
+
+
+def layer_macs(params):
+    return [sum(st["weight"].size for st in p["feat"]) + sum(st["weight"].size for st in p["att"])
+            for p in params]
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower() == "active" for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts):
+    """The reference algorithm's CPU port over a batch: oracle query + numpy GridConv per layer."""
+    q = oracle.gridify_knn if cfg.query == "gridifyknn" else oracle.gridify
+    table, loc, num = data, data, npts
+    for l, p in zip(cfg.layers, params):
+        nebidx, _, cent, centmsk, num = q(loc, num, max_p_grid=l.max_p_grid, max_o_grid=l.max_o_grid,
+                                          kernel_size=l.kernel_size, loc=cfg.loc,
+                                          coord_shift=cfg.coord_shift, voxel_size=(l.voxel_size,) * 3,
+                                          grid_size=(l.grid_size,) * 3)
+        table = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, p, pre_relu=cfg.pre_relu)
+        loc = cent
+    return table
+
+
+def time_cpu(cfg, params, clouds, steps, warmup):
+    """Times the CPU port on `clouds` clouds per step with every host thread it can use."""
+    from oracle import oracle, gridconv_oracle
+    from gridgcn_b200 import synth
+    oracle.build()
+    cores = os.cpu_count() or 1
+    oracle.set_threads(min(cores, oracle.max_threads(), max(clouds, 1)))
+    data, npts = synth.make_batch(clouds, cfg.num_points, seed0=0, voxels=cfg.voxels)
+    for _ in range(warmup):
+        cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return clouds * cfg.num_points / dt, dt, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=96, help="clouds per GPU per step")
+    ap.add_argument("--K", type=int, default=64)
+    ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify"])
+    ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "fp32"))
+    ap.add_argument("--cpu-clouds", type=int, default=4, help="clouds per CPU-baseline step")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from gridgcn_b200 import stack
+    cfg = stack.seg8192_4layer(args.K, args.query)
+    params = stack.init_params(cfg, seed=0)
+    macs = layer_macs(params)
+    flops_cloud = [2 * l.max_o_grid * l.max_p_grid * m for l, m in zip(cfg.layers, macs)]
+    config = {"workload": "seg8192 4-layer GridConv encoder (O=1024/256/64/16, K=%d, N=8192), "
+                          "query=%s, synthetic surface clouds" % (args.K, args.query),
+              "clouds_per_gpu": args.batch, "points_per_cloud": cfg.num_points, "K": args.K,
+              "precision": args.precision, "parallelism": "batch-sharded clouds x%d, no collective" % world,
+              "l2": "flushed between timed steps (256 MiB write)"}
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        val, dt, cores = time_cpu(cfg, params, args.cpu_clouds, steps, warmup)
+        line = {"impl": "reference", "metric": "points/sec through 4-layer GridConv @ N=8192, K=%d" % args.K,
+                "value": val, "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
+                                 "sample": "%d clouds of 8192 points per step (oracle C port, OpenMP over "
+                                           "clouds + numpy/BLAS GridConv); the reference has no CPU "
+                                           "Gridify (gridify.cc:30-39)" % args.cpu_clouds},
+                "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this framework
+    import torch
+    import torch.distributed as dist
+    from gridgcn_b200 import synth
+    import gridgcn_b200 as gg
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: gridgcn_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gg.build()
+
+    B = args.batch
+    # rank r owns clouds [r*B, (r+1)*B): seeds are global cloud ids, so any N sees the same data
+    pool = min(B, 32)  # distinct clouds generated per rank, tiled to B (host generation cost)
+    base, npts1 = synth.make_batch(pool, cfg.num_points, seed0=rank * B, voxels=cfg.voxels)
+    reps = (B + pool - 1) // pool
+    data_h = torch.from_numpy(np.tile(base, (reps, 1, 1))[:B].copy()).pin_memory()
+    npts_h = torch.full((B, 1), cfg.num_points, dtype=torch.int32).pin_memory()
+    data_d, npts_d = data_h.to(dev), npts_h.to(dev)
+    enc = stack.GridGcnEncoder(cfg, params, dev, precision=args.precision)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out_h = torch.empty((B, cfg.layers[-1].max_o_grid, 4 + cfg.layers[-1].pt_mlp_lst[-1]),
+                        dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations (outside the event pair)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    def step_device():
+        return enc(data_d, npts_d)
+
+    def step_e2e():
+        d = data_h.to(dev, non_blocking=True)
+        n = npts_h.to(dev, non_blocking=True)
+        out = enc(d, n)
+        out_h.copy_(out, non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, args.steps)
+    barrier()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    sampler.stop_flag = True
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    points_job = world * B * cfg.num_points
+    value = points_job * args.steps / (ms_total * 1e-3)
+    e2e_value = points_job * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ per-kernel rooflines (rank 0)
+    peaks = load_peaks()
+    enc(data_d, npts_d, keep_trace=True)
+    trace = enc.trace
+    reps_k = max(5, min(args.steps, 20))
+    conv_ms = []
+    table, prev = data_d, None
+    for i, (l, conv) in enumerate(zip(cfg.layers, enc.convs)):
+        tr = trace[i]
+        tin = data_d if i == 0 else trace[i - 1]["table"]
+        f = lambda: conv(tin, tr["nebidx"], tr["cent"], tr["centmsk"])
+        for _ in range(3):
+            f()
+        conv_ms.append(timed(f, reps_k) / reps_k)
+    dom = int(np.argmax(conv_ms))
+    tflops = B * flops_cloud[dom] / (conv_ms[dom] * 1e-3) / 1e12
+    l0 = cfg.layers[0]
+    qfn = gg.GridifyKNN
+    kwq = dict(max_o_grid=l0.max_o_grid, max_p_grid=l0.max_p_grid, kernel_size=l0.kernel_size,
+               stride=1, coord_shift=cfg.coord_shift, voxel_size=[l0.voxel_size] * 3,
+               grid_size=[l0.grid_size] * 3, loc=cfg.loc)
+    fq = lambda: qfn(data_d, npts_d, **kwq)
+    for _ in range(3):
+        fq()
+    q_ms = timed(fq, reps_k) / reps_k
+    q_bytes = B * gridify_bytes(cfg.num_points, l0.max_o_grid, l0.max_p_grid)
+    q_gbs = q_bytes / (q_ms * 1e-3) / 1e9
+
+    tensor_peak = peaks["bf16_tflops_sustained"] if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"]
+    roofline = {"kernel": "gridconv layer %d (%s)" % (dom, args.precision), "bound": "tensor",
+                "achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
+                "traffic": None, "ms_per_launch": conv_ms[dom], "layer_ms": conv_ms,
+                "peak_source": peaks["_source"] + " dense bf16 cuBLAS (sustained); tf32 nominal peak is half of bf16"}
+    roofline_hbm = {"kernel": "gridifyknn (build + query) N=8192 O=1024 P=%d" % l0.max_p_grid,
+                    "bound": "hbm", "achieved": q_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": q_gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": q_ms,
+                    "algorithmic_bytes": q_bytes, "peak_source": peaks["_source"]}
+
+    cpu_val, cpu_dt, cores = time_cpu(cfg, params, args.cpu_clouds, 2, 1)
+    line = {"metric": "points/sec through 4-layer GridConv @ N=8192, K=%d" % args.K,
+            "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(world * (data_h.numel() * 4 + npts_h.numel() * 4)),
+                    "d2h_bytes_per_step": int(world * out_h.numel() * 4)},
+            "gpu_launches": args.steps * len(cfg.layers) * 3,
+            "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "cpu_baseline": {"value": cpu_val, "unit": "points/s", "cores": cores, "kind": "port",
+                             "sample": "%d clouds of 8192 points, 2 steps (oracle C port with OpenMP over "
+                                       "clouds + numpy/BLAS GridConv)" % args.cpu_clouds},
+            "clocks": sampler.summary()}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -55,6 +55,8 @@ def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_siz
     cent = torch.empty((B, O, 4), dtype=torch.float32, device=dev)
     centmsk = torch.empty((B, O), dtype=torch.float32, device=dev)
     actual_centnum = torch.empty((B, 1), dtype=torch.int32, device=dev)
+    if B == 0:  # empty batch: torch hands out null data pointers, nothing to launch
+        return nebidx, nebidxmsk, cent, centmsk, actual_centnum
     with torch.cuda.device(dev):
         rc = getattr(L, fn_name)(
             data.data_ptr(), actual_numpoints.data_ptr(), B, N, O, P, int(kernel_size), int(stride),

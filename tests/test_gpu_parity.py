@@ -1,0 +1,322 @@
+"""GPU parity suite (-m gpu): every CUDA entry point, called through the reference-shaped host API
+(which goes through the C-ABI), against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): integer index tensors bit-exact; fp32 `cent` bit-exact as well
+(same IEEE operations in the same order); aggregated GridConv features within 1e-3 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gridgcn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+NAMES = ("nebidx", "nebidxmsk", "cent", "centmsk", "actual_centnum")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _check5(got, want, what):
+    for g, w, n in zip(got, want, NAMES):
+        g = g.cpu().numpy()
+        assert g.dtype == w.dtype and g.shape == w.shape, (what, n, g.dtype, g.shape, w.shape)
+        if not np.array_equal(g, w):
+            bad = np.argwhere(g != w)
+            raise AssertionError("%s: %s differs at %d places, first %s: got %s want %s" % (
+                what, n, len(bad), bad[0], g[tuple(bad[0])], w[tuple(bad[0])]))
+
+
+GRID_CASES = [
+    ("cfg1_P64_k3", 2, 1024, "surface",
+     dict(max_p_grid=64, max_o_grid=1024, kernel_size=3, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("cfg1_P32_k5", 2, 1024, "surface",
+     dict(max_p_grid=32, max_o_grid=1024, kernel_size=5, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("seg8192_L0", 3, 8192, "surface",
+     dict(max_p_grid=64, max_o_grid=1024, kernel_size=3, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("seg8192_L1", 3, 1024, "surface",
+     dict(max_p_grid=32, max_o_grid=256, kernel_size=3, loc=1, voxel_size=(0.133333,) * 3, grid_size=(15,) * 3)),
+    ("overflow", 2, 4096, "ball",
+     dict(max_p_grid=8, max_o_grid=100, kernel_size=3, loc=1, voxel_size=(0.25,) * 3, grid_size=(8,) * 3)),
+    ("P128_k7_cls", 2, 1024, "surface",
+     dict(max_p_grid=128, max_o_grid=128, kernel_size=7, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("one_voxel", 2, 128, "ball",
+     dict(max_p_grid=128, max_o_grid=1, kernel_size=1, loc=1, voxel_size=(2.0,) * 3, grid_size=(1,) * 3)),
+    ("loc0_aniso", 2, 700, "surface",
+     dict(max_p_grid=16, max_o_grid=64, kernel_size=3, loc=0, voxel_size=(0.2, 0.25, 0.5), grid_size=(10, 8, 4))),
+    ("big_cloud_global_path", 1, 20000, "ball",
+     dict(max_p_grid=64, max_o_grid=512, kernel_size=3, loc=1, voxel_size=(0.1,) * 3, grid_size=(20,) * 3)),
+]
+
+
+@pytest.mark.parametrize("name,B,N,kind,kw", GRID_CASES, ids=[c[0] for c in GRID_CASES])
+def test_gridify_and_knn_match_oracle(gg, cuda_dev, oracle_mod, name, B, N, kind, kw):
+    data, npts = synth.make_batch(B, N, seed0=100, kind=kind, voxels=(kw["voxel_size"][0],))
+    npts[-1, 0] = N - N // 7  # ragged
+    kw = dict(kw, coord_shift=(1.0, 1.0, 1.0))
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    _check5(gg.Gridify(d, n, stride=1, **kw), oracle_mod.gridify(data, npts, **kw), name + "/Gridify")
+    _check5(gg.GridifyKNN(d, n, stride=1, **kw), oracle_mod.gridify_knn(data, npts, **kw),
+            name + "/GridifyKNN")
+    _check5(gg.GridifyKNN(d, n, stride=1, dist_fma=True, **kw),
+            oracle_mod.gridify_knn(data, npts, dist_fma=True, **kw), name + "/GridifyKNN fma")
+
+
+def test_edge_cases(gg, cuda_dev, oracle_mod):
+    data, npts = synth.make_batch(3, 64, seed0=1)
+    npts[0, 0] = 0
+    data[1, :, :3] += 10.0
+    data[2, 32:] = data[2, :32]  # duplicates -> exact ties
+    kw = dict(max_p_grid=4, max_o_grid=8, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+              voxel_size=(0.5,) * 3, grid_size=(4,) * 3)
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    _check5(gg.Gridify(d, n, **kw), oracle_mod.gridify(data, npts, **kw), "edge/Gridify")
+    _check5(gg.GridifyKNN(d, n, **kw), oracle_mod.gridify_knn(data, npts, **kw), "edge/GridifyKNN")
+    # B = 0 is a no-op
+    out = gg.Gridify(d[:0], n[:0], **kw)
+    assert out[0].shape == (0, 8, 4)
+
+
+def test_chained_layers_feed_centres_back(gg, cuda_dev, oracle_mod):
+    """Layer i+1 voxelises layer i's centres (ggcn_models_g.py:160): a 1-ulp difference in `cent`
+    could flip a voxel, so the chain is checked end to end, weights w = neighbour counts."""
+    data, npts = synth.make_batch(2, 8192, seed0=7)
+    ladder = [(0.05, 40, 1024, 64), (0.133333, 15, 256, 32), (0.4, 5, 24, 32)]
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    hd, hn = data, npts
+    for vox, grid, O, P in ladder:
+        kw = dict(max_p_grid=P, max_o_grid=O, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+                  voxel_size=(vox,) * 3, grid_size=(grid,) * 3)
+        got = gg.Gridify(d, n, **kw)
+        want = oracle_mod.gridify(hd, hn, **kw)
+        _check5(got, want, "chain vox %g" % vox)
+        d, n = got[2], got[4]
+        hd, hn = want[2], want[4]
+
+
+def test_gridify_up_matches_oracle(gg, cuda_dev, oracle_mod):
+    for (nd, nu, P, ks, vox, grid) in ((24, 256, 5, 3, 0.4, 5), (256, 1024, 5, 3, 0.133333, 15),
+                                       (1024, 8192, 5, 3, 0.05, 40), (300, 900, 40, 5, 0.25, 8),
+                                       (300, 900, 128, 3, 0.5, 4), (64, 100, 3, 1, 0.25, 8)):
+        down, dn = synth.make_batch(2, nd, seed0=21, voxels=(vox,))
+        up, un = synth.make_batch(2, nu, seed0=31, voxels=(vox,))
+        dn[1, 0], un[1, 0] = nd - nd // 5, nu - nu // 9
+        up[0, 5, :3] = 5.0
+        kw = dict(max_p_grid=P, max_o_grid=nu, kernel_size=ks, coord_shift=(1, 1, 1),
+                  voxel_size=(vox,) * 3, grid_size=(grid,) * 3)
+        want = oracle_mod.gridify_up(down, up, dn, un, **kw)
+        got = gg.GridifyUp(_t(down, cuda_dev), _t(up, cuda_dev), _t(dn, cuda_dev), _t(un, cuda_dev), **kw)
+        assert np.array_equal(got[0].cpu().numpy(), want[0]), (nd, nu, P, ks)
+        assert np.array_equal(got[1].cpu().numpy(), want[1]), (nd, nu, P, ks)
+
+
+def test_knn_and_ball_knn_match_oracle(gg, cuda_dev, oracle_mod):
+    rng = np.random.default_rng(0)
+    for (B, n, m) in ((2, 256, 24), (2, 1024, 256), (1, 8192, 1024), (2, 100, 3000)):
+        unknown = rng.uniform(-1, 1, size=(B, n, 3)).astype(np.float32)
+        known = rng.uniform(-1, 1, size=(B, m, 3)).astype(np.float32)
+        known[0, m // 2:] = known[0, :m - m // 2]  # exact ties -> lowest index wins
+        downnum = np.full((B, 1), m, np.int32)
+        upnum = np.full((B, 1), n, np.int32)
+        downnum[-1, 0], upnum[-1, 0] = m - m // 4, n - n // 3
+        args = [_t(a, cuda_dev) for a in (unknown, known, downnum, upnum)]
+        for k in (1, 3, 5, 8, 20):
+            want = oracle_mod.knn(unknown, known, downnum, upnum, k=k)
+            got = gg.contrib.KNN(*args, k=k).cpu().numpy()
+            assert np.array_equal(got, want), ("knn", B, n, m, k)
+        for k, radius in ((5, 0.3), (3, 0.05), (6, 1.02)):
+            want = oracle_mod.ball_knn(unknown, known, downnum, upnum, k=k, radius=radius)
+            got = gg.contrib.BallKNN(*args, k=k, radius=radius).cpu().numpy()
+            assert np.array_equal(got, want), ("ball", B, n, m, k)
+    with pytest.raises(gg._lib.GridGcnError):
+        gg.contrib.BallKNN(*args, k=7, radius=0.5)
+
+
+def test_knn_lattice_vector(gg, cuda_dev):
+    pts = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(3)], np.float32)
+    d2 = ((pts - 1.0) ** 2).sum(1)
+    faces = [i for i in range(27) if d2[i] == 1]
+    edge0 = min(i for i in range(27) if d2[i] == 2)
+    unknown = _t(np.array([[[1.0, 1.0, 1.0]]], np.float32), cuda_dev)
+    known = _t(pts[None], cuda_dev)
+    dn, un = _t(np.array([[27]], np.int32), cuda_dev), _t(np.array([[1]], np.int32), cuda_dev)
+    assert gg.contrib.KNN(unknown, known, dn, un, k=8)[0, 0].tolist() == [13] + faces + [edge0]
+
+
+def _rel_err(got, want):
+    """max |got - want| / (|want| + rms(want)): elementwise relative error with the tensor's RMS as
+    the floor for near-zero entries."""
+    rms = float(np.sqrt(np.mean(want.astype(np.float64) ** 2))) + 1e-30
+    return float(np.max(np.abs(got - want) / (np.abs(want) + rms)))
+
+
+CONV_CASES = [
+    # name, B, N, O, K, Cin, mlp
+    ("l0_K8", 2, 256, 32, 8, 0, [16, 32]),
+    ("l1_K8", 2, 256, 32, 8, 16, [16, 32]),
+    ("l0_seg", 2, 2048, 256, 64, 0, [32, 32, 64]),
+    ("l1_seg", 2, 512, 128, 32, 64, [64, 64, 128]),
+    ("l3_seg", 2, 64, 16, 32, 256, [256, 256, 512]),
+    ("K128", 1, 512, 16, 128, 32, [32, 64]),
+    ("K5_decoder_like", 2, 128, 100, 5, 32, [128]),
+    ("K16_single_stage", 2, 256, 40, 16, 8, [24]),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+@pytest.mark.parametrize("name,B,N,O,K,Cin,mlp", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_gridconv_matches_oracle(gg, cuda_dev, oracle_mod, name, B, N, O, K, Cin, mlp, precision):
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import gridconv
+    rng = np.random.default_rng(5)
+    data, npts = synth.make_batch(B, N, seed0=60, voxels=(0.25,))
+    kw = dict(max_p_grid=K, max_o_grid=O, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+              voxel_size=(0.25,) * 3, grid_size=(8,) * 3)
+    nebidx, _, cent, centmsk, _ = oracle_mod.gridify_knn(data, npts, **kw)
+    table = data if Cin == 0 else np.concatenate(
+        [data, rng.uniform(0, 1, size=(B, N, Cin)).astype(np.float32)], axis=2)
+    layer = gridconv.init_layer(np.random.default_rng(23), Cin, mlp, 10)
+    want = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, layer)
+    conv = gg.GridConv(layer, cuda_dev, precision=precision)
+    got = conv(_t(table, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(centmsk, cuda_dev))
+    got = got.cpu().numpy()
+    assert np.array_equal(got[..., :4], want[..., :4])  # centre columns are copied
+    err = _rel_err(got[..., 4:], want[..., 4:])
+    assert err <= 1e-3, "%s/%s: rel err %.3g" % (name, precision, err)  # north_star: 1e-3 rel fp32
+    assert np.abs(want[..., 4:]).max() > 0  # the comparison is not vacuous
+
+
+def test_gridconv_attention_variants_and_ball_misses(gg, cuda_dev, oracle_mod):
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import gridconv
+    rng = np.random.default_rng(3)
+    B, N, O, K, Cin = 2, 200, 50, 6, 12
+    table = rng.uniform(-1, 1, size=(B, N, 4 + Cin)).astype(np.float32)
+    nebidx = rng.integers(0, N, size=(B, O, K)).astype(np.int32)
+    nebidx[:, :, -1] = -1  # BallKNN miss: take() clips after the batch offset (utils/ops.py:90-92)
+    cent = rng.uniform(-1, 1, size=(B, O, 4)).astype(np.float32)
+    centmsk = (rng.uniform(size=(B, O)) > 0.3).astype(np.float32)
+    for attfdim in (10, 4, 3, 0):
+        layer = gridconv.init_layer(np.random.default_rng(1), Cin, [20, 40], attfdim)
+        want = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, layer, pre_relu=True)
+        got = gg.GridConv(layer, cuda_dev)(_t(table, cuda_dev), _t(nebidx, cuda_dev),
+                                           _t(cent, cuda_dev), _t(centmsk, cuda_dev)).cpu().numpy()
+        assert _rel_err(got[..., 4:], want[..., 4:]) <= 1e-3, attfdim
+
+
+def test_sub_g_update_reference_signature(gg, cuda_dev, oracle_mod):
+    """The reference-shaped entry (gathered neighbours in (B,4+C,O,P)) gives the same features."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import gridconv
+    z = np.load(os.path.join(GOLDEN, "gridconv_l1.npz"))
+    layer = gridconv.init_layer(np.random.default_rng(23), 16, [16, 32], 10)
+    neighbors = gridconv_oracle.batch_take_g(z["table"], z["nebidx"]).transpose(0, 3, 1, 2)
+    cent = z["cent"]
+    feats = gg.sub_g_update(_t(cent[:, :, :3].transpose(0, 2, 1), cuda_dev),
+                            _t(cent[:, :, 3:4].transpose(0, 2, 1), cuda_dev),
+                            _t(neighbors, cuda_dev), True, _t(z["centmsk"], cuda_dev), None, 10,
+                            pt_mlp_lst=[16, 32], layer=layer)
+    want = z["out"][..., 4:].transpose(0, 2, 1)
+    assert feats.shape == want.shape
+    assert _rel_err(feats.cpu().numpy(), want) <= 1e-3
+
+
+def test_golden_fixtures_on_gpu(gg, cuda_dev):
+    from gridgcn_b200 import gridconv
+    kw1 = dict(max_p_grid=64, max_o_grid=1024, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+               voxel_size=(0.05,) * 3, grid_size=(40,) * 3)
+    z = np.load(os.path.join(GOLDEN, "gridify_cfg1.npz"))
+    _check5(gg.Gridify(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), **kw1),
+            [z[n] for n in NAMES], "golden gridify_cfg1")
+    z = np.load(os.path.join(GOLDEN, "gridifyknn_cfg1.npz"))
+    _check5(gg.GridifyKNN(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev),
+                          **dict(kw1, max_p_grid=32, kernel_size=5)),
+            [z[n] for n in NAMES], "golden gridifyknn_cfg1")
+    z = np.load(os.path.join(GOLDEN, "gridify_overflow.npz"))
+    kwo = dict(max_p_grid=8, max_o_grid=100, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+               voxel_size=(0.25,) * 3, grid_size=(8,) * 3)
+    _check5(gg.Gridify(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), **kwo),
+            [z[n] for n in NAMES], "golden overflow")
+    _check5(gg.GridifyKNN(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), **kwo),
+            [z["knn_" + n] for n in NAMES], "golden overflow knn")
+    z = np.load(os.path.join(GOLDEN, "gridify_up.npz"))
+    got = gg.GridifyUp(_t(z["downdata"], cuda_dev), _t(z["updata"], cuda_dev), _t(z["downnum"], cuda_dev),
+                       _t(z["upnum"], cuda_dev), max_p_grid=5, max_o_grid=1024, kernel_size=3,
+                       coord_shift=(1, 1, 1), voxel_size=(0.133333,) * 3, grid_size=(15,) * 3)
+    assert np.array_equal(got[0].cpu().numpy(), z["nebidx"])
+    assert np.array_equal(got[1].cpu().numpy(), z["nebidxmsk"])
+    for case, fn, extra in (("knn", gg.contrib.KNN, {}),
+                            ("ballknn", gg.contrib.BallKNN, dict(radius=0.133333 * 3 * 1.7 / 2))):
+        z = np.load(os.path.join(GOLDEN, case + ".npz"))
+        got = fn(_t(z["unknown"], cuda_dev), _t(z["known"], cuda_dev), _t(z["downnum"], cuda_dev),
+                 _t(z["upnum"], cuda_dev), k=5, **extra)
+        assert np.array_equal(got.cpu().numpy(), z["idx"]), case
+    for case, cin in (("gridconv_l0", 0), ("gridconv_l1", 16)):
+        z = np.load(os.path.join(GOLDEN, case + ".npz"))
+        layer = gridconv.init_layer(np.random.default_rng(23), cin, [16, 32], 10)
+        got = gg.GridConv(layer, cuda_dev)(_t(z["table"], cuda_dev), _t(z["nebidx"], cuda_dev),
+                                           _t(z["cent"], cuda_dev), _t(z["centmsk"], cuda_dev))
+        assert _rel_err(got.cpu().numpy()[..., 4:], z["out"][..., 4:]) <= 1e-3, case
+
+
+def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod):
+    """The whole encoder (query -> GridConv per layer) against the oracle chain, index tensors
+    bit-exact at every layer, features within 1e-3."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import stack
+    for cfg, B in ((stack.tiny(8), 3), (stack.cls1024_4layer(32), 2), (stack.seg8192_4layer(16), 1),
+                   (stack.seg8192_shipped(), 1)):
+        params = stack.init_params(cfg, seed=1)
+        data, npts = synth.make_batch(B, cfg.num_points, seed0=200, voxels=cfg.voxels)
+        enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision="fp32")
+        out = enc(_t(data, cuda_dev), _t(npts, cuda_dev), keep_trace=True)
+        q = oracle_mod.gridify_knn if cfg.query == "gridifyknn" else oracle_mod.gridify
+        table, loc, num = data, data, npts
+        for i, (l, p) in enumerate(zip(cfg.layers, params)):
+            want = q(loc, num, max_p_grid=l.max_p_grid, max_o_grid=l.max_o_grid,
+                     kernel_size=l.kernel_size, loc=cfg.loc, coord_shift=cfg.coord_shift,
+                     voxel_size=(l.voxel_size,) * 3, grid_size=(l.grid_size,) * 3)
+            tr = enc.trace[i]
+            _check5([tr[n] for n in NAMES], want, "%s layer %d" % (cfg.name, i))
+            table = gridconv_oracle.gridconv_layer(table, want[0], want[2], want[3], p,
+                                                   pre_relu=cfg.pre_relu)
+            err = _rel_err(tr["table"].cpu().numpy()[..., 4:], table[..., 4:])
+            assert err <= 1e-3, "%s layer %d: rel err %.3g" % (cfg.name, i, err)
+            loc, num = want[2], want[4]
+        assert out.shape == (B, cfg.layers[-1].max_o_grid, 4 + cfg.layers[-1].pt_mlp_lst[-1])
+
+
+def test_full_size_properties(gg, cuda_dev):
+    """BASELINE sizes (B=16 x 8192 points, K=64) through size-independent properties: masks count
+    the valid slots, every valid id is in range and lies inside the centre's 3x3x3 voxel
+    neighbourhood, KNN rows are sorted by distance, centres are distinct voxels, idempotence."""
+    B, N, O, P = 16, 8192, 1024, 64
+    data, npts = synth.make_batch(B, N, seed0=300)
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    kw = dict(max_p_grid=P, max_o_grid=O, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+              voxel_size=(0.05,) * 3, grid_size=(40,) * 3)
+    for fn in (gg.Gridify, gg.GridifyKNN):
+        a = fn(d, n, **kw)
+        b = fn(d, n, **kw)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)  # deterministic, unlike the reference
+        nebidx, msk, cent, cmsk, num = [t.cpu().numpy() for t in a]
+        assert nebidx.min() >= 0 and nebidx.max() < N
+        assert np.array_equal(cmsk.sum(1).astype(np.int32), num[:, 0])
+        vox = np.floor((data[..., :3] + np.float32(1.0)) / np.float32(0.05)).astype(np.int64)
+        for bb in range(0, B, 5):
+            nc = int(num[bb, 0])
+            cv = np.floor((cent[bb, :nc, :3] + np.float32(1.0)) / np.float32(0.05)).astype(np.int64)
+            assert len(np.unique(cv, axis=0)) == nc  # one centre per occupied voxel
+            nv = vox[bb][nebidx[bb, :nc]]  # (nc, P, 3)
+            assert np.abs(nv - cv[:, None, :]).max() <= 1
+            if fn is gg.GridifyKNN:
+                u = (cv + 0.5) * 0.05  # shifted frame (gridifyknn.cu:253-255), candidates raw
+                dd = ((u[:, None, :] - data[bb][nebidx[bb, :nc]][..., :3]) ** 2).sum(-1)
+                for o in range(0, nc, 97):
+                    if len(set(nebidx[bb, o].tolist())) == P:  # no padding in this row
+                        assert np.all(np.diff(dd[o]) >= -1e-6)
