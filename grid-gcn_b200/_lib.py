@@ -40,6 +40,7 @@ SIGNATURES = {
                                     _vp, _sz, _vp]),
     "gridgcn_knn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "gridgcn_ball_knn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "gridgcn_debug_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "gridgcn_gridconv_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(MlpDesc),
                                   _i, _vp, _vp]),
 }

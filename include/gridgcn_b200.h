@@ -144,6 +144,11 @@ int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cen
                          const float *centmsk, int B, int Nprev, int Cin, int O, int K,
                          const gridgcn_mlp_t *mlp_host, int precision, float *out, void *stream);
 
+/* Self-test of the tcgen05 primitives (not an operator): D[128,N] = A[128,K] * B[N,K]^T on one CTA,
+ * kind::tf32, nsplit 1 (plain) or 3 (error-compensated).  N % 16 == 0, N <= 256, K % 8 == 0. */
+int gridgcn_debug_tc_gemm(const float *A, const float *B, float *D, int N, int K, int nsplit,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,28 @@
+"""GPU: the hand-written tcgen05 / TMEM primitives against a float64 matmul (descriptor encodings,
+K-major no-swizzle operand layout, TMEM addressing, 3-term tf32 split)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,K", [(16, 8), (32, 32), (64, 16), (128, 64), (256, 64), (48, 24), (16, 128)])
+@pytest.mark.parametrize("nsplit", [1, 3])
+def test_tc_gemm_selftest(gg, cuda_dev, N, K, nsplit):
+    L = gg._lib.lib()
+    rng = np.random.default_rng(N * 1000 + K)
+    A = rng.normal(size=(128, K)).astype(np.float32)
+    B = rng.normal(size=(N, K)).astype(np.float32)
+    a, b = torch.from_numpy(A).to(cuda_dev), torch.from_numpy(B).to(cuda_dev)
+    d = torch.full((128, N), float("nan"), dtype=torch.float32, device=cuda_dev)
+    rc = L.gridgcn_debug_tc_gemm(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K, nsplit,
+                                 torch.cuda.current_stream(cuda_dev).cuda_stream)
+    gg._lib.check(rc, "gridgcn_debug_tc_gemm")
+    torch.cuda.synchronize()
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    got = d.cpu().numpy().astype(np.float64)
+    scale = np.sqrt(K)  # typical magnitude of an entry
+    err = np.abs(got - want).max() / scale
+    tol = 2e-3 if nsplit == 1 else 2e-6  # tf32: 2^-11 per operand; split: ~fp32
+    assert err < tol, "N=%d K=%d nsplit=%d: max err / sqrt(K) = %.3g" % (N, K, nsplit, err)
