@@ -41,8 +41,11 @@ SIGNATURES = {
     "gridgcn_knn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "gridgcn_ball_knn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "gridgcn_debug_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "gridgcn_gridconv_packed_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i]),
+    "gridgcn_gridconv_pack": (_i, [ctypes.POINTER(MlpDesc), _i, _vp, _sz, _vp]),
+    "gridgcn_gridconv_workspace_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i, _i, _i]),
     "gridgcn_gridconv_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(MlpDesc),
-                                  _i, _vp, _vp]),
+                                  _i, _vp, _vp, _sz, _vp, _vp]),
 }
 
 _lib = None

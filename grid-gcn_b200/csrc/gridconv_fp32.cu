@@ -129,7 +129,12 @@ gridconv_fp32_kernel(ConvParams p, int num_tiles) {
                 const int b = (int)(center / p.O);
                 const int idx = __ldg(p.nebidx + center * p.K + pslot);
                 const float *src = p.table + take_row(idx, b, p.Nprev, rows_total) * row_w;
-                const float4 head = __ldg(reinterpret_cast<const float4 *>(src));
+                float4 head;
+                if ((row_w & 3) == 0) {
+                    head = __ldg(reinterpret_cast<const float4 *>(src));
+                } else {
+                    head = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
+                }
                 const float4 c4 = __ldg(p.cent + center);
                 float att[10], dx, dy, dz;
                 att_vector(p.attfdim, c4, head.x, head.y, head.z, att, dx, dy, dz);
@@ -215,7 +220,10 @@ gridconv_fp32_kernel(ConvParams p, int num_tiles) {
     }
 }
 
-int launch_gridconv_tc(const ConvParams &p, int precision, cudaStream_t st);  // gridconv_tc.cu
+// gridconv_tc.cu
+int launch_gridconv_tc(const ConvParams &p, int precision, const float *packed, float *ftab, cudaStream_t st);
+int tc_packed_floats(const ConvParams &c);
+int tc_pack(const ConvParams &c, float *packed, cudaStream_t st);
 
 static int launch_gridconv_fp32(const ConvParams &p, cudaStream_t st) {
     ConvSmemLayout s = conv_smem_layout(p);
@@ -240,29 +248,13 @@ static int launch_gridconv_fp32(const ConvParams &p, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-}  // namespace gg
-
-using namespace gg;
-
-extern "C" int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cent,
-                                    const float *centmsk, int B, int Nprev, int Cin, int O, int K,
-                                    const gridgcn_mlp_t *m, int precision, float *out,
-                                    void *stream) {
-    if (!table || !nebidx || !cent || !centmsk || !out || !m) return GRIDGCN_EINVAL;
-    if (B < 0 || Nprev < 1 || Cin < 0 || O < 1 || K < 1) return GRIDGCN_EINVAL;
+// Validates an MLP description and fills the stage tables shared by every GridConv entry point.
+static int fill_mlp(const gridgcn_mlp_t *m, int Cin, ConvParams &p) {
+    if (!m || Cin < 0) return GRIDGCN_EINVAL;
     if (m->n_feat_stages < 1 || m->n_feat_stages > GRIDGCN_MAX_STAGES - 2) return GRIDGCN_EINVAL;
     if (m->attfdim != 0 && m->attfdim != 3 && m->attfdim != 4 && m->attfdim != 10)
         return GRIDGCN_ELIMIT;
-    if (K > 1024) return GRIDGCN_ELIMIT;
-    if ((reinterpret_cast<uintptr_t>(table) & 15) || (reinterpret_cast<uintptr_t>(cent) & 15))
-        return GRIDGCN_EINVAL;
-    ConvParams p{};
-    p.table = table;
-    p.nebidx = nebidx;
-    p.cent = reinterpret_cast<const float4 *>(cent);
-    p.centmsk = centmsk;
-    p.out = out;
-    p.B = B; p.Nprev = Nprev; p.Cin = Cin; p.O = O; p.K = K;
+    p.Cin = Cin;
     p.n_feat = m->n_feat_stages;
     p.attfdim = m->attfdim;
     p.feat_in = Cin == 0 ? 3 : Cin;
@@ -288,10 +280,67 @@ extern "C" int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const
         p.w[i] = m->weight[i];
         p.bias[i] = m->bias[i];
     }
+    return 0;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" size_t gridgcn_gridconv_packed_bytes(const gridgcn_mlp_t *m, int Cin) {
+    ConvParams p{};
+    if (fill_mlp(m, Cin, p)) return 0;
+    int n = tc_packed_floats(p);
+    return n < 0 ? 0 : (size_t)n * sizeof(float);
+}
+
+extern "C" int gridgcn_gridconv_pack(const gridgcn_mlp_t *m, int Cin, void *packed, size_t packed_bytes,
+                                     void *stream) {
+    ConvParams p{};
+    int rc = fill_mlp(m, Cin, p);
+    if (rc) return rc;
+    int n = tc_packed_floats(p);
+    if (n < 0) return GRIDGCN_ELIMIT;
+    if (!packed || packed_bytes < (size_t)n * sizeof(float) || (reinterpret_cast<uintptr_t>(packed) & 15))
+        return GRIDGCN_EWORKSPACE;
+    return tc_pack(p, static_cast<float *>(packed), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t gridgcn_gridconv_workspace_bytes(const gridgcn_mlp_t *m, int B, int Nprev, int Cin) {
+    ConvParams p{};
+    if (fill_mlp(m, Cin, p) || B < 0 || Nprev < 0) return 0;
+    return Cin > 0 ? (size_t)B * Nprev * p.Cout * sizeof(float) : 0;
+}
+
+extern "C" int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cent,
+                                    const float *centmsk, int B, int Nprev, int Cin, int O, int K,
+                                    const gridgcn_mlp_t *m, int precision, const void *packed,
+                                    void *workspace, size_t workspace_bytes, float *out,
+                                    void *stream) {
+    if (!table || !nebidx || !cent || !centmsk || !out || !m) return GRIDGCN_EINVAL;
+    if (B < 0 || Nprev < 1 || Cin < 0 || O < 1 || K < 1) return GRIDGCN_EINVAL;
+    if (K > 1024) return GRIDGCN_ELIMIT;
+    if ((reinterpret_cast<uintptr_t>(table) & 15) || (reinterpret_cast<uintptr_t>(cent) & 15))
+        return GRIDGCN_EINVAL;
+    ConvParams p{};
+    int rc = fill_mlp(m, Cin, p);
+    if (rc) return rc;
+    p.table = table;
+    p.nebidx = nebidx;
+    p.cent = reinterpret_cast<const float4 *>(cent);
+    p.centmsk = centmsk;
+    p.out = out;
+    p.B = B; p.Nprev = Nprev; p.O = O; p.K = K;
     if (B == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (precision == GRIDGCN_PRECISION_FP32) return launch_gridconv_fp32(p, st);
-    if (precision == GRIDGCN_PRECISION_TF32 || precision == GRIDGCN_PRECISION_TF32X3)
-        return launch_gridconv_tc(p, precision, st);
+    if (precision == GRIDGCN_PRECISION_TF32 || precision == GRIDGCN_PRECISION_TF32X3) {
+        if (!packed || (reinterpret_cast<uintptr_t>(packed) & 15)) return GRIDGCN_EWORKSPACE;
+        if (workspace_bytes < gridgcn_gridconv_workspace_bytes(m, B, Nprev, Cin) ||
+            (Cin > 0 && (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15))))
+            return GRIDGCN_EWORKSPACE;
+        return launch_gridconv_tc(p, precision, static_cast<const float *>(packed),
+                                  static_cast<float *>(workspace), st);
+    }
     return GRIDGCN_EINVAL;
 }

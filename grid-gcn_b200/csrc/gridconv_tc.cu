@@ -1,11 +1,822 @@
-// Fused GridConv layer, tcgen05 / TMEM tensor-core path (GRIDGCN_PRECISION_TF32 / TF32X3).
+// Fused GridConv layer on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
+// TMEM, weight slices streamed by the TMA engine's bulk copies) -- GRIDGCN_PRECISION_TF32 / TF32X3.
+//
+// What is computed (reference segmentation/models/gcn_module_g_att.py:172-287, see
+// gridconv_common.cuh) is restructured for the hardware instead of translated:
+//
+//  * Feature MLP hoisting.  For layers with input features (has_feats, localfdim == 0) the feature
+//    MLP of verts_pair_func (:135) is a function of the gathered neighbour ROW only, so
+//    MLP(gather(table)) == gather(MLP(table)): kernel A (`point_mlp_tc_kernel`) applies it once per
+//    source point (B*Nprev rows) instead of once per edge (B*O*K rows, 16x more at K=64), writing a
+//    transformed table F.  The per-edge work that remains is what really depends on the
+//    (centre, neighbour) pair: the attention MLP, the product and the max pool.
+//  * Kernel B (`edge_tc_kernel`), one persistent CTA per SM slot, tiles of 128 edges:
+//      gather neighbour xyz (128-bit loads) -> geo / att_vec in registers -> K-major fp32 operand
+//      images in shared memory -> hidden stages as D[edge, ch] (thread = edge row in the TMEM
+//      epilogue) -> last attention stage (and, for the first layer, last feature stage) TRANSPOSED,
+//      D^T[ch, edge] = W * H^T, so that the max over a centre's K edges is a run of TMEM columns in
+//      ONE thread's registers: no shuffles, no shared-memory transpose -> relu(att) * feat, max,
+//      pre-ReLU, centre mask -> one coalesced [cent | feats] row per centre.
+//  * fp32 parity on tf32 tensor cores: TF32X3 splits every operand into hi + lo tf32 parts and
+//    issues lo*hi, hi*lo, hi*hi into the same TMEM accumulator (error ~2^-21, fp32-class); TF32
+//    issues hi*hi only.
+//
+// Synchronisation is deliberately lock-step (one __syncthreads per phase, one mbarrier for "MMAs of
+// this stage retired", full/empty mbarriers on the weight ring); overlap comes from co-resident
+// CTAs.  Every mbarrier wait is bounded and traps instead of hanging.
 #include "gridconv_common.cuh"
+#include "tc_common.cuh"
 
 namespace gg {
 
-int launch_gridconv_tc(const ConvParams &p, int precision, cudaStream_t st) {
-    (void)p; (void)precision; (void)st;
-    return GRIDGCN_ELIMIT;  // placeholder until the tcgen05 kernel lands
+constexpr int kTcThreads = 160;     // warps 0-3: gather + TMEM epilogue (thread = TMEM lane); warp 4: TMA + MMA issue
+constexpr int kTileRows = 128;
+constexpr int kSliceK = 32;         // k extent of one streamed weight slice
+constexpr int kSlotBytes = 2 * 128 * kSliceK * 4;  // hi + lo images of a [128 x 32] slice
+constexpr int kMaxRing = 4;
+
+struct TcStage {
+    int transposed;  // 0: D[row, ch], weights resident in smem as the B operand; 1: D^T[ch, row], weights streamed as A
+    int Cin, Cout;   // logical dims
+    int Kp, Np;      // Cin padded to 8; Cout padded to 16 (plain) / 128 (transposed)
+    long long w_off; // float offset of this stage inside the packed buffer
+    const float *bias;
+};
+
+struct TcParams {
+    ConvParams c;
+    const float *packed;  // packed hi/lo operand images of every stage
+    float *ftab;          // kernel A output / kernel B input: (B*Nprev, Cout) transformed features
+    int nsplit;           // 1 or 3
+    // kernel A: stages a[0..na)
+    int na;
+    TcStage a[GRIDGCN_MAX_STAGES];
+    int a_rows;           // rows per tile (64 or 128)
+    // kernel B: hidden feature stages (first layer only), last feature stage (first layer only),
+    // attention stage 0 (plain), attention stage 1 (transposed)
+    int nfh;
+    TcStage fh[GRIDGCN_MAX_STAGES];
+    int has_ff;
+    TcStage ff;
+    int has_att;
+    TcStage a0, a1;
+    int ring_slots;
+};
+
+__host__ __device__ inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: folded fp32 W(Cout, Cin) -> hi/lo tf32 operand images in the layouts the MMA
+// descriptors expect (tc_common.cuh).  Plain stage: one [Np x Kp] image (LBO = Np*16).  Transposed
+// stage: for every 128-row chunk, for every 32-wide k slice, a contiguous [128 x kw] hi image
+// followed by its lo image (LBO = 2048), in the order the kernel streams them.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_stage_kernel(const float *__restrict__ W, float *__restrict__ dst, TcStage st) {
+    const int total = st.Np * st.Kp;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int n = e / st.Kp, k = e % st.Kp;
+        const float w = (n < st.Cout && k < st.Cin) ? W[(size_t)n * st.Cin + k] : 0.f;
+        float hi, lo;
+        tc::split_tf32(w, hi, lo);
+        size_t off_hi, off_lo;
+        if (!st.transposed) {
+            size_t o = (size_t)(k >> 2) * st.Np * 4 + (size_t)(n >> 3) * 32 + (n & 7) * 4 + (k & 3);
+            off_hi = o;
+            off_lo = (size_t)st.Np * st.Kp + o;
+        } else {
+            const int j = n >> 7, r = n & 127, t = k / kSliceK, kk = k % kSliceK;
+            const int kw = min(kSliceK, st.Kp - t * kSliceK);
+            size_t base = (size_t)j * 2 * 128 * st.Kp + (size_t)t * 2 * 128 * kSliceK;
+            size_t o = (size_t)(kk >> 2) * 128 * 4 + (size_t)(r >> 3) * 32 + (r & 7) * 4 + (kk & 3);
+            off_hi = base + o;
+            off_lo = base + (size_t)128 * kw + o;
+        }
+        dst[st.w_off + off_hi] = hi;
+        dst[st.w_off + off_lo] = lo;
+    }
+}
+
+// Bounded mbarrier wait (about two seconds), then trap: never hang the GPU.
+__device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!tc::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+struct Ring {
+    uint8_t *slots;       // ring_slots x kSlotBytes
+    uint64_t *full, *empty;
+    int nslots;
+    long long issued;     // producer: slices requested so far (whole kernel)
+    long long consumed;   // consumer: slices whose MMAs were issued so far
+};
+
+// ---- slice sequence bookkeeping ------------------------------------------------------------------
+struct SliceSeq {
+    const TcStage *st[3];
+    int n;            // number of transposed stages per tile
+    int chunk_major;  // 0: stage by stage (kernel A); 1: chunk by chunk across the stages (kernel B)
+    int j, t, s;      // cursor: chunk, slice, stage
+    __device__ void reset() { j = t = s = 0; }
+    __device__ int per_tile() const {
+        int c = 0;
+        for (int i = 0; i < n; i++) c += (st[i]->Np / 128) * ((st[i]->Kp + kSliceK - 1) / kSliceK);
+        return c;
+    }
+    // current slice source (float offset into packed) and size in bytes, then advance (wraps per tile)
+    __device__ void next(long long &off, uint32_t &bytes) {
+        const TcStage &q = *st[s];
+        const int kw = min(kSliceK, q.Kp - t * kSliceK);
+        off = q.w_off + (long long)j * 2 * 128 * q.Kp + (long long)t * 2 * 128 * kSliceK;
+        bytes = (uint32_t)(2 * 128 * kw * 4);
+        const int nslice = (q.Kp + kSliceK - 1) / kSliceK;
+        if (++t < nslice) return;
+        t = 0;
+        if (!chunk_major) {
+            if (++j == q.Np / 128) {
+                j = 0;
+                if (++s == n) s = 0;
+            }
+        } else {
+            if (++s == n) {
+                s = 0;
+                if (++j == q.Np / 128) j = 0;
+            }
+        }
+    }
+};
+
+// Single-thread producer step: request the next slice of the CTA's sequence into the ring.
+__device__ __forceinline__ void ring_request(Ring &ring, SliceSeq &prod, const float *packed,
+                                             long long total_slices, bool wait_empty) {
+    if (ring.issued >= total_slices) return;
+    const int slot = (int)(ring.issued % ring.nslots);
+    if (wait_empty && ring.issued >= ring.nslots)
+        wait_bar(&ring.empty[slot], (uint32_t)(((ring.issued / ring.nslots) - 1) & 1));
+    long long off;
+    uint32_t bytes;
+    prod.next(off, bytes);
+    tc::mbar_expect_tx(&ring.full[slot], bytes);
+    tc::bulk_g2s(ring.slots + (size_t)slot * kSlotBytes, packed + off, bytes, &ring.full[slot]);
+    ring.issued++;
+}
+
+// Issue every MMA of one transposed stage (single thread).  D^T[128 ch of chunk j, ncols] (+)=
+// W_slice * Xop^T; x_hi/x_lo are the shared addresses of the B operand images ([ncols rows x Kp],
+// panel stride x_lbo); weight slices arrive through the ring in the packed order.
+template <int NSPLIT>
+__device__ __forceinline__ void run_transposed_stage(const TcStage &st, Ring &ring, SliceSeq &prod,
+                                                     const float *packed, long long total_slices,
+                                                     bool sticky, uint32_t x_hi, uint32_t x_lo,
+                                                     uint32_t x_lbo, int ncols, uint32_t tmem_base,
+                                                     int col_stride) {
+    const uint32_t idesc = tc::make_idesc_tf32(128, ncols);
+    const int nchunk = st.Np / 128, nslice = (st.Kp + kSliceK - 1) / kSliceK;
+    for (int j = 0; j < nchunk; j++) {
+        const uint32_t d = tmem_base + j * col_stride;
+        uint32_t acc = 0;
+        for (int t = 0; t < nslice; t++) {
+            const int kw = min(kSliceK, st.Kp - t * kSliceK);
+            const int slot = (int)(ring.consumed % ring.nslots);
+            if (!sticky || ring.consumed < ring.nslots)
+                wait_bar(&ring.full[slot], (uint32_t)((ring.consumed / ring.nslots) & 1));
+            const uint32_t a_hi = tc::smem_u32(ring.slots + (size_t)slot * kSlotBytes);
+            const uint32_t a_lo = a_hi + 128 * kw * 4;
+            for (int ks = 0; ks < kw / 8; ks++) {
+                const uint64_t ah = tc::make_sdesc(a_hi + ks * 2 * 2048, 2048);
+                const uint32_t xo = (uint32_t)(t * (kSliceK / 4) + ks * 2) * x_lbo;
+                const uint64_t bh = tc::make_sdesc(x_hi + xo, x_lbo);
+                if (NSPLIT == 3) {
+                    const uint64_t al = tc::make_sdesc(a_lo + ks * 2 * 2048, 2048);
+                    const uint64_t bl = tc::make_sdesc(x_lo + xo, x_lbo);
+                    tc::mma_tf32(d, al, bh, idesc, acc);
+                    tc::mma_tf32(d, ah, bl, idesc, 1);
+                    acc = 1;
+                }
+                tc::mma_tf32(d, ah, bh, idesc, acc);
+                acc = 1;
+            }
+            ring.consumed++;
+            if (!sticky) {
+                tc::mma_commit(&ring.empty[slot]);
+                // Keep the ring full, one slice behind: the slot recycled here belongs to the slice
+                // BEFORE the one just issued, so waiting for it to drain never idles the tensor pipe.
+                if (ring.consumed >= 2) ring_request(ring, prod, packed, total_slices, true);
+            }
+        }
+    }
+}
+
+// Issue the MMAs of one plain stage (single thread): D[128 rows, Np] = X * W^T, W resident.
+template <int NSPLIT>
+__device__ __forceinline__ void run_plain_stage(const TcStage &st, uint32_t x_hi, uint32_t x_lo,
+                                                uint32_t x_lbo, uint32_t w_hi, uint32_t tmem_d) {
+    const uint32_t idesc = tc::make_idesc_tf32(128, st.Np);
+    const uint32_t w_lbo = (uint32_t)st.Np * 16, w_lo = w_hi + (uint32_t)st.Np * st.Kp * 4;
+    uint32_t acc = 0;
+    for (int ks = 0; ks < st.Kp / 8; ks++) {
+        const uint64_t ah = tc::make_sdesc(x_hi + ks * 2 * x_lbo, x_lbo);
+        const uint64_t bh = tc::make_sdesc(w_hi + ks * 2 * w_lbo, w_lbo);
+        if (NSPLIT == 3) {
+            const uint64_t al = tc::make_sdesc(x_lo + ks * 2 * x_lbo, x_lbo);
+            const uint64_t bl = tc::make_sdesc(w_lo + ks * 2 * w_lbo, w_lbo);
+            tc::mma_tf32(tmem_d, al, bh, idesc, acc);
+            tc::mma_tf32(tmem_d, ah, bl, idesc, 1);
+            acc = 1;
+        }
+        tc::mma_tf32(tmem_d, ah, bh, idesc, acc);
+        acc = 1;
+    }
+}
+
+// TMEM epilogue of a plain stage, thread = row: x = relu(D + bias) -> hi/lo images [128 x Kp_next].
+template <int NSPLIT>
+__device__ __forceinline__ void plain_epilogue(const TcStage &st, uint32_t tmem_lane_addr, int row,
+                                               uint8_t *img_hi, uint8_t *img_lo, uint32_t lbo,
+                                               int kp_next) {
+    for (int c0 = 0; c0 < kp_next; c0 += 16) {
+        uint32_t v[16];
+        if (c0 < st.Np) {
+            tc::tmem_ld16(tmem_lane_addr + c0, v);
+            tc::tmem_ld_wait();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = c0 + q * 4;
+            if (c >= kp_next) break;
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float x = 0.f;
+                if (c + i < st.Cout) x = fmaxf(__uint_as_float(v[q * 4 + i]) + __ldg(st.bias + c + i), 0.f);
+                tc::split_tf32(x, hi[i], lo[i]);
+            }
+            const uint32_t off = tc::kmajor_off(row, c, lbo);
+            *reinterpret_cast<float4 *>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            if (NSPLIT == 3)
+                *reinterpret_cast<float4 *>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel A: per-point feature MLP, F = MLP_pt(table[:, 4:]) for B*Nprev rows.
+// Every stage transposed: D^T[ch, row]; thread = channel in the epilogue.
+// ------------------------------------------------------------------------------------------------
+template <int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int TR = p.a_rows;
+    int kmax = 0;
+    for (int s = 0; s < p.na; s++) kmax = max(kmax, p.a[s].Kp);
+    const uint32_t x_lbo = (uint32_t)TR * 16 + 16;  // +16: conflict-free transposed 4-byte stores
+    const uint32_t x_img = (uint32_t)(kmax / 4) * x_lbo;
+    uint8_t *x_hi = smem, *x_lo = smem + x_img;
+    Ring ring;
+    ring.slots = smem + pad_to((NSPLIT == 3 ? 2 : 1) * x_img, 128);
+    ring.nslots = p.ring_slots;
+    ring.full = bars;
+    ring.empty = bars + kMaxRing;
+    ring.issued = ring.consumed = 0;
+    uint64_t *bar_mma = bars + 2 * kMaxRing;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) {
+        for (int i = 0; i < ring.nslots; i++) {
+            tc::mbar_init(&ring.full[i], 1);
+            tc::mbar_init(&ring.empty[i], 1);
+        }
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_init_fence();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    SliceSeq prod;
+    prod.n = p.na;
+    prod.chunk_major = 0;
+    for (int s = 0; s < p.na && s < 3; s++) prod.st[s] = &p.a[s];
+    prod.reset();
+    // NOTE: kernel A supports at most 3 stages in the slice sequence (len(pt_mlp_lst) <= 3)
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_slices = (long long)my_tiles * prod.per_tile();
+    const bool sticky = prod.per_tile() <= ring.nslots;  // whole sequence fits: load once, keep
+    if (sticky) ring.nslots = max(prod.per_tile(), 1);
+    if (warp == 4 && lane == 0) {
+        const long long pre = sticky ? prod.per_tile() : ring.nslots;
+        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+    }
+    uint32_t mma_phase = 0;
+    const long long rows_total = (long long)p.c.B * p.c.Nprev;
+    const int row_w = 4 + p.c.Cin;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * TR;
+        // ---- load X0 = table[row0 .. row0+TR, 4:4+Cin] as hi/lo K-major images ----
+        if (warp < 4) {
+            const int kp0 = p.a[0].Kp;
+            for (int e = tid; e < TR * (kp0 / 4); e += 128) {
+                const int r = e / (kp0 / 4), c = (e % (kp0 / 4)) * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (row0 + r < rows_total) {
+                    const float *src = p.c.table + (row0 + r) * row_w + 4 + c;
+                    if ((row_w & 3) == 0 && c + 3 < p.c.Cin) {
+                        float4 t4 = __ldg(reinterpret_cast<const float4 *>(src));
+                        v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+                    } else {
+                        for (int i = 0; i < 4; i++)
+                            if (c + i < p.c.Cin) v[i] = __ldg(src + i);
+                    }
+                }
+                float hi[4], lo[4];
+                for (int i = 0; i < 4; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+                const uint32_t off = tc::kmajor_off(r, c, x_lbo);
+                *reinterpret_cast<float4 *>(x_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (NSPLIT == 3) *reinterpret_cast<float4 *>(x_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        for (int s = 0; s < p.na; s++) {
+            const TcStage &st = p.a[s];
+            if (warp == 4) {
+                if (lane == 0) {
+                    run_transposed_stage<NSPLIT>(st, ring, prod, p.packed, total_slices, sticky,
+                                                 tc::smem_u32(x_hi), tc::smem_u32(x_lo), x_lbo, TR, tmem, TR);
+                    tc::mma_commit(bar_mma);
+                }
+                __syncwarp();
+            }
+            wait_bar(bar_mma, mma_phase);
+            mma_phase ^= 1;
+            tc::fence_after_sync();
+            if (warp < 4) {
+                const bool last = s + 1 == p.na;
+                const int kp_next = last ? 0 : p.a[s + 1].Kp;
+                for (int j = 0; j < st.Np / 128; j++) {
+                    const int ch = j * 128 + tid;
+                    const float bias = ch < st.Cout ? __ldg(st.bias + ch) : 0.f;
+                    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + j * TR;
+                    for (int r0 = 0; r0 < TR; r0 += 16) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(taddr + r0, v);
+                        tc::tmem_ld_wait();
+                        if (last) {
+                            if (ch < st.Cout) {
+#pragma unroll
+                                for (int i = 0; i < 16; i++)
+                                    if (row0 + r0 + i < rows_total)
+                                        p.ftab[(row0 + r0 + i) * st.Cout + ch] =
+                                            fmaxf(__uint_as_float(v[i]) + bias, 0.f);
+                            }
+                        } else if (ch < kp_next) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                float x = ch < st.Cout ? fmaxf(__uint_as_float(v[i]) + bias, 0.f) : 0.f;
+                                float hi, lo;
+                                tc::split_tf32(x, hi, lo);
+                                const uint32_t off = tc::kmajor_off(r0 + i, ch, x_lbo);
+                                *reinterpret_cast<float *>(x_hi + off) = hi;
+                                if (NSPLIT == 3) *reinterpret_cast<float *>(x_lo + off) = lo;
+                            }
+                        }
+                    }
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B: per-edge attention MLP (+ the per-edge feature MLP of the first layer), product with
+// the (gathered) features, max over the K slots, centre mask, output row.
+// ------------------------------------------------------------------------------------------------
+template <int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int rowidx_s[kTileRows];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const ConvParams &c = p.c;
+    const int K = c.K, C = c.Cout;
+    constexpr uint32_t LBO = kTileRows * 16;  // images with 128 rows: panel = 2 KB
+    constexpr int NIMG = NSPLIT == 3 ? 2 : 1;
+
+    // ---- shared memory carve-up ----
+    int kx = 0;  // feature-path image width (first layer only)
+    for (int s = 0; s < p.nfh; s++) kx = max(kx, max(p.fh[s].Kp, pad_to(p.fh[s].Cout, 8)));
+    if (p.has_ff) kx = max(kx, p.ff.Kp);
+    const int kh = p.has_att ? max(p.a0.Kp, p.a1.Kp) : 0;
+    uint8_t *xf_hi = smem, *xf_lo = xf_hi + (size_t)(kx / 4) * LBO;
+    uint8_t *xa_hi = smem + (size_t)NIMG * (kx / 4) * LBO, *xa_lo = xa_hi + (size_t)(kh / 4) * LBO;
+    uint8_t *wres = xa_hi + (size_t)NIMG * (kh / 4) * LBO;  // resident plain-stage weights (hi, lo per stage)
+    size_t wres_bytes = 0;
+    for (int s = 0; s < p.nfh; s++) wres_bytes += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
+    if (p.has_att) wres_bytes += (size_t)2 * p.a0.Np * p.a0.Kp * 4;
+    Ring ring;
+    ring.slots = wres + pad_to((int)wres_bytes, 128);
+    ring.nslots = p.ring_slots;
+    ring.full = bars;
+    ring.empty = bars + kMaxRing;
+    ring.issued = ring.consumed = 0;
+    uint64_t *bar_mma = bars + 2 * kMaxRing;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) {
+        for (int i = 0; i < ring.nslots; i++) {
+            tc::mbar_init(&ring.full[i], 1);
+            tc::mbar_init(&ring.empty[i], 1);
+        }
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_init_fence();
+    }
+    // resident weights: plain copy (generic proxy) of the packed images
+    {
+        size_t off = 0;
+        for (int s = 0; s <= p.nfh; s++) {
+            if (s == p.nfh && !p.has_att) break;
+            const TcStage &st = s < p.nfh ? p.fh[s] : p.a0;
+            const int n4 = 2 * st.Np * st.Kp / 4;
+            const float4 *src = reinterpret_cast<const float4 *>(p.packed + st.w_off);
+            float4 *dst = reinterpret_cast<float4 *>(wres + off);
+            for (int i = tid; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
+            off += (size_t)n4 * 16;
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    SliceSeq prod;
+    prod.n = 0;
+    prod.chunk_major = 1;
+    if (p.has_ff) prod.st[prod.n++] = &p.ff;
+    if (p.has_att) prod.st[prod.n++] = &p.a1;
+    prod.reset();
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int per_tile = prod.per_tile();
+    const long long total_slices = (long long)my_tiles * per_tile;
+    const bool sticky = per_tile <= ring.nslots;  // whole sequence fits: load once, keep
+    if (sticky) ring.nslots = max(per_tile, 1);
+    if (warp == 4 && lane == 0) {
+        const long long pre = sticky ? per_tile : ring.nslots;
+        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+    }
+    uint32_t mma_phase = 0;
+    const long long rows_total = (long long)c.B * c.Nprev;
+    const long long centers_total = (long long)c.B * c.O;
+    const int row_w = 4 + c.Cin;
+    const int att_w = p.has_att ? p.a0.Cin : 0;
+    const int out_w = 4 + C;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long c_base = (long long)tile * cpt;
+        // ---- gather + geometry: thread = edge row ----
+        if (warp < 4) {
+            const int r = tid, cl = r / K, slot = r % K;
+            const long long center = c_base + cl;
+            const bool valid = cl < cpt && center < centers_total;
+            float att[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) att[i] = 0.f;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            int ridx = -1;
+            if (valid) {
+                const int b = (int)(center / c.O);
+                const int idx = __ldg(c.nebidx + center * K + slot);
+                const long long row = take_row(idx, b, c.Nprev, rows_total);
+                ridx = (int)row;
+                const float *src = c.table + row * row_w;
+                float nx, ny, nz;
+                if ((row_w & 3) == 0) {
+                    const float4 h = __ldg(reinterpret_cast<const float4 *>(src));
+                    nx = h.x; ny = h.y; nz = h.z;
+                } else {
+                    nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
+                }
+                att_vector(c.attfdim, __ldg(c.cent + center), nx, ny, nz, att, dx, dy, dz);
+            }
+            rowidx_s[r] = ridx;
+            if (p.has_att) {
+                for (int q = 0; q < p.a0.Kp / 4; q++) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int z = 0; z < 16; z++) v = (z == q * 4 + i && z < att_w) ? att[z] : v;
+                        tc::split_tf32(v, hi[i], lo[i]);
+                    }
+                    const uint32_t off = tc::kmajor_off(r, q * 4, LBO);
+                    *reinterpret_cast<float4 *>(xa_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    if (NSPLIT == 3)
+                        *reinterpret_cast<float4 *>(xa_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            if (c.Cin == 0) {  // first layer: features are the geo vector (gcn_module_g_att.py:242-243)
+                const int kp0 = p.nfh > 0 ? p.fh[0].Kp : p.ff.Kp;
+                float g[4] = {dx, dy, dz, 0.f};
+                for (int q = 0; q < kp0 / 4; q++) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) tc::split_tf32(q == 0 ? g[i] : 0.f, hi[i], lo[i]);
+                    const uint32_t off = tc::kmajor_off(r, q * 4, LBO);
+                    *reinterpret_cast<float4 *>(xf_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    if (NSPLIT == 3)
+                        *reinterpret_cast<float4 *>(xf_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+
+        // ---- plain (hidden) stages: feature hidden stages of the first layer, then attention stage 0 ----
+        size_t woff = 0;
+        for (int s = 0; s <= p.nfh; s++) {
+            const bool is_att = s == p.nfh;
+            if (is_att && !p.has_att) break;
+            const TcStage &st = is_att ? p.a0 : p.fh[s];
+            uint8_t *xi_hi = is_att ? xa_hi : xf_hi, *xi_lo = is_att ? xa_lo : xf_lo;
+            if (warp == 4) {
+                if (lane == 0) {
+                    run_plain_stage<NSPLIT>(st, tc::smem_u32(xi_hi), tc::smem_u32(xi_lo), LBO,
+                                            tc::smem_u32(wres + woff), tmem);
+                    tc::mma_commit(bar_mma);
+                }
+                __syncwarp();
+            }
+            woff += (size_t)2 * st.Np * st.Kp * 4;
+            wait_bar(bar_mma, mma_phase);
+            mma_phase ^= 1;
+            tc::fence_after_sync();
+            if (warp < 4) {
+                const int kp_next = is_att ? p.a1.Kp : (s + 1 < p.nfh ? p.fh[s + 1].Kp : p.ff.Kp);
+                plain_epilogue<NSPLIT>(st, tmem + ((uint32_t)(warp * 32) << 16), tid, xi_hi, xi_lo, LBO, kp_next);
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+        }
+
+        // ---- transposed stages: last feature stage (first layer) into cols [0,128*nch), last attention
+        //      stage into the following columns, chunk by chunk of 128 channels ----
+        const int nchunk = pad_to(C, 128) / 128;
+        for (int j = 0; j < nchunk; j++) {
+            if (warp == 4) {
+                if (lane == 0) {
+                    // one chunk at a time: build single-chunk views of the stages
+                    if (p.has_ff) {
+                        TcStage v = p.ff;
+                        v.Np = 128;
+                        v.w_off = p.ff.w_off + (long long)j * 2 * 128 * p.ff.Kp;
+                        run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
+                                                     tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO, 128, tmem, 0);
+                    }
+                    if (p.has_att) {
+                        TcStage v = p.a1;
+                        v.Np = 128;
+                        v.w_off = p.a1.w_off + (long long)j * 2 * 128 * p.a1.Kp;
+                        run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
+                                                     tc::smem_u32(xa_hi), tc::smem_u32(xa_lo), LBO, 128,
+                                                     tmem + 128, 0);
+                    }
+                    tc::mma_commit(bar_mma);
+                }
+                __syncwarp();
+            }
+            wait_bar(bar_mma, mma_phase);
+            mma_phase ^= 1;
+            tc::fence_after_sync();
+            if (warp < 4) {
+                const int ch = j * 128 + tid;
+                const bool chv = ch < C;
+                const float bf = (p.has_ff && chv) ? __ldg(p.ff.bias + ch) : 0.f;
+                const float ba = (p.has_att && chv) ? __ldg(p.a1.bias + ch) : 0.f;
+                const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+                float m = -3.402823466e+38f;
+                int pos = 0, cl = 0;
+                for (int e0 = 0; e0 < kTileRows; e0 += 16) {
+                    uint32_t fv[16], gv[16];
+                    if (p.has_ff) tc::tmem_ld16(tl + e0, fv);
+                    if (p.has_att) tc::tmem_ld16(tl + 128 + e0, gv);
+                    float fg[16];
+                    if (!p.has_ff) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const int ri = rowidx_s[e0 + i];
+                            fg[i] = (chv && ri >= 0) ? __ldg(p.ftab + (size_t)ri * C + ch) : 0.f;
+                        }
+                    }
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        float f = p.has_ff ? fmaxf(__uint_as_float(fv[i]) + bf, 0.f) : fg[i];
+                        if (p.has_att) f *= fmaxf(__uint_as_float(gv[i]) + ba, 0.f);
+                        if (cl < cpt) m = fmaxf(m, f);
+                        if (++pos == K) {
+                            const long long center = c_base + cl;
+                            if (chv && cl < cpt && center < centers_total) {
+                                float y = c.pre_relu ? fmaxf(m, 0.f) : m;
+                                c.out[center * out_w + 4 + ch] = y * __ldg(c.centmsk + center);
+                            }
+                            pos = 0;
+                            cl++;
+                            m = -3.402823466e+38f;
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+        }
+        // centre columns of the output rows
+        if (warp < 4) {
+            for (int i = tid; i < cpt * 4; i += 128) {
+                const long long center = c_base + i / 4;
+                if (center < centers_total)
+                    c.out[center * out_w + (i & 3)] =
+                        __ldg(reinterpret_cast<const float *>(c.cent + center) + (i & 3));
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: stage tables, packing, launches.
+// ------------------------------------------------------------------------------------------------
+static void make_stage(TcStage &s, int transposed, int cin, int cout, const float *bias, long long &off) {
+    s.transposed = transposed;
+    s.Cin = cin;
+    s.Cout = cout;
+    s.Kp = pad_to(cin, 8);
+    s.Np = pad_to(cout, transposed ? 128 : 16);
+    s.w_off = off;
+    s.bias = bias;
+    off += 2LL * s.Np * s.Kp;
+}
+
+// Fills the stage tables of both kernels; returns the packed size in floats (or < 0 if unsupported).
+static long long build_tc_plan(const ConvParams &c, TcParams &p) {
+    p.c = c;
+    long long off = 0;
+    const int nf = c.n_feat;
+    p.na = p.nfh = p.has_ff = 0;
+    p.has_att = c.attfdim > 0;
+    if (nf > 3) return -1;  // slice sequence holds up to 3 streamed stages
+    if (c.Cin > 0) {
+        for (int s = 0; s < nf; s++) make_stage(p.a[p.na++], 1, c.cin[s], c.cout[s], c.bias[s], off);
+    } else {
+        for (int s = 0; s + 1 < nf; s++) make_stage(p.fh[p.nfh++], 0, c.cin[s], c.cout[s], c.bias[s], off);
+        make_stage(p.ff, 1, c.cin[nf - 1], c.cout[nf - 1], c.bias[nf - 1], off);
+        p.has_ff = 1;
+    }
+    if (p.has_att) {
+        make_stage(p.a0, 0, c.cin[nf], c.cout[nf], c.bias[nf], off);
+        make_stage(p.a1, 1, c.cin[nf + 1], c.cout[nf + 1], c.bias[nf + 1], off);
+    }
+    for (int s = 0; s < p.nfh; s++)
+        if (p.fh[s].Np > 128) return -1;
+    if (p.has_att && p.a0.Np > 128) return -1;
+    return off;
+}
+
+static size_t kernel_a_smem(const TcParams &p, int TR, int nsplit, int slots) {
+    int kmax = 0;
+    for (int s = 0; s < p.na; s++) kmax = max(kmax, p.a[s].Kp);
+    size_t x_img = (size_t)(kmax / 4) * (TR * 16 + 16);
+    return pad_to((int)((nsplit == 3 ? 2 : 1) * x_img), 128) + (size_t)slots * kSlotBytes + 1024;
+}
+
+static size_t kernel_b_smem(const TcParams &p, int nsplit, int slots) {
+    int kx = 0;
+    for (int s = 0; s < p.nfh; s++) kx = max(kx, max(p.fh[s].Kp, pad_to(p.fh[s].Cout, 8)));
+    if (p.has_ff) kx = max(kx, p.ff.Kp);
+    int kh = p.has_att ? max(p.a0.Kp, p.a1.Kp) : 0;
+    size_t nimg = nsplit == 3 ? 2 : 1;
+    size_t bytes = nimg * (size_t)(kx / 4 + kh / 4) * kTileRows * 16;
+    size_t wres = 0;
+    for (int s = 0; s < p.nfh; s++) wres += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
+    if (p.has_att) wres += (size_t)2 * p.a0.Np * p.a0.Kp * 4;
+    return bytes + pad_to((int)wres, 128) + (size_t)slots * kSlotBytes + 1024;
+}
+
+constexpr size_t kSmemCap = 224 * 1024;  // dynamic part; static barriers/index cache use < 3 KB of the 227 KB
+
+template <int NSPLIT>
+static int launch_tc_t(TcParams &p, cudaStream_t st) {
+    const ConvParams &c = p.c;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(point_mlp_tc_kernel<NSPLIT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(edge_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kSmemCap);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    if (p.na > 0) {  // kernel A
+        int TR = 128, slots = 3;
+        while (kernel_a_smem(p, TR, NSPLIT, slots) > kSmemCap) {
+            if (slots > 2) slots--;
+            else if (TR == 128) { TR = 64; slots = 3; }
+            else return GRIDGCN_ELIMIT;
+        }
+        p.a_rows = TR;
+        p.ring_slots = slots;
+        int chunks = 0;
+        for (int s = 0; s < p.na; s++) chunks = max(chunks, p.a[s].Np / 128);
+        if (chunks * TR > 256) return GRIDGCN_ELIMIT;  // TMEM columns
+        long long rows = (long long)c.B * c.Nprev;
+        long long tiles = (rows + TR - 1) / TR;
+        size_t smem = kernel_a_smem(p, TR, NSPLIT, slots);
+        int per_sm = (int)max((size_t)1, min((size_t)2, kSmemCap / smem));
+        int blocks = (int)min(tiles, (long long)sms * per_sm);
+        point_mlp_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    {  // kernel B
+        if (c.K > kTileRows) return GRIDGCN_ELIMIT;
+        int slots = 3;
+        while (kernel_b_smem(p, NSPLIT, slots) > kSmemCap) {
+            if (slots > 2) slots--;
+            else return GRIDGCN_ELIMIT;
+        }
+        p.ring_slots = slots;
+        const int cpt = kTileRows / c.K;
+        long long centers = (long long)c.B * c.O;
+        long long tiles = (centers + cpt - 1) / cpt;
+        if (tiles > 0x7fffffff) return GRIDGCN_ELIMIT;
+        size_t smem = kernel_b_smem(p, NSPLIT, slots);
+        int per_sm = (int)max((size_t)1, min((size_t)2, kSmemCap / smem));
+        int blocks = (int)min(tiles, (long long)sms * per_sm);
+        edge_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
+        return (int)cudaGetLastError();
+    }
+}
+
+int tc_packed_floats(const ConvParams &c) {
+    TcParams p{};
+    long long n = build_tc_plan(c, p);
+    return n < 0 || n > 0x7fffffff ? -1 : (int)n;
+}
+
+int tc_pack(const ConvParams &c, float *packed, cudaStream_t st) {
+    TcParams p{};
+    if (build_tc_plan(c, p) < 0) return GRIDGCN_ELIMIT;
+    auto run = [&](const TcStage &s, const float *W) {
+        int total = s.Np * s.Kp;
+        pack_stage_kernel<<<(total + 255) / 256, 256, 0, st>>>(W, packed, s);
+    };
+    const int nf = c.n_feat;
+    for (int s = 0; s < p.na; s++) run(p.a[s], c.w[s]);
+    for (int s = 0; s < p.nfh; s++) run(p.fh[s], c.w[s]);
+    if (p.has_ff) run(p.ff, c.w[nf - 1]);
+    if (p.has_att) {
+        run(p.a0, c.w[nf]);
+        run(p.a1, c.w[nf + 1]);
+    }
+    return (int)cudaGetLastError();
+}
+
+int launch_gridconv_tc(const ConvParams &c, int precision, const float *packed, float *ftab,
+                       cudaStream_t st) {
+    TcParams p{};
+    if (build_tc_plan(c, p) < 0) return GRIDGCN_ELIMIT;
+    if (!packed || (c.Cin > 0 && !ftab)) return GRIDGCN_EWORKSPACE;
+    p.packed = packed;
+    p.ftab = ftab;
+    p.nsplit = precision == GRIDGCN_PRECISION_TF32X3 ? 3 : 1;
+    return p.nsplit == 3 ? launch_tc_t<3>(p, st) : launch_tc_t<1>(p, st);
 }
 
 }  // namespace gg

@@ -109,6 +109,17 @@ class GridConv:
             d.weight[i] = w.data_ptr()
             d.bias[i] = b.data_ptr()
         self._desc = d
+        self._packed = None
+        if precision != "fp32":  # tensor-core paths: one-time re-layout of the weights on the device
+            L = _lib.lib()
+            nbytes = L.gridgcn_gridconv_packed_bytes(ctypes.byref(d), self.cin)
+            if nbytes == 0:
+                raise _lib.GridGcnError("this MLP shape is not supported by the tensor-core GridConv")
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = L.gridgcn_gridconv_pack(ctypes.byref(d), self.cin, self._packed.data_ptr(), nbytes,
+                                             torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(rc, "gridgcn_gridconv_pack")
 
     def __call__(self, table, nebidx, cent, centmsk, out=None):
         L = _lib.lib()
@@ -124,10 +135,17 @@ class GridConv:
         _, O, K = nebidx.shape
         if out is None:
             out = torch.empty((B, O, 4 + self.cout), dtype=torch.float32, device=table.device)
+        ws, ws_bytes, packed = None, 0, None
+        if self._packed is not None:
+            packed = self._packed.data_ptr()
+            ws_bytes = L.gridgcn_gridconv_workspace_bytes(ctypes.byref(self._desc), B, Nprev, self.cin)
+            if ws_bytes:
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
         with torch.cuda.device(table.device):
             rc = L.gridgcn_gridconv_fwd(
                 table.data_ptr(), nebidx.data_ptr(), cent.data_ptr(), centmsk.data_ptr(), B, Nprev,
-                self.cin, O, K, ctypes.byref(self._desc), PRECISION[self.precision], out.data_ptr(),
+                self.cin, O, K, ctypes.byref(self._desc), PRECISION[self.precision], packed,
+                ws.data_ptr() if ws is not None else None, ws_bytes, out.data_ptr(),
                 torch.cuda.current_stream(table.device).cuda_stream)
         _lib.check(rc, "gridgcn_gridconv_fwd")
         return out

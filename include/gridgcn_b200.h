@@ -140,9 +140,19 @@ typedef struct {
 #define GRIDGCN_PRECISION_TF32   1  /* tcgen05 kind::tf32, fp32 accumulate                     */
 #define GRIDGCN_PRECISION_TF32X3 2  /* tcgen05 kind::tf32, 3-term error-compensated split      */
 
+/* Tensor-core precisions need the weights re-laid out once per parameter set ("packed": hi/lo
+ * tf32 operand images in tcgen05 shared-memory order) and, for layers with input features, a
+ * workspace that receives the per-point transformed feature table. */
+size_t gridgcn_gridconv_packed_bytes(const gridgcn_mlp_t *mlp_host, int Cin);
+int gridgcn_gridconv_pack(const gridgcn_mlp_t *mlp_host, int Cin, void *packed, size_t packed_bytes,
+                          void *stream);
+size_t gridgcn_gridconv_workspace_bytes(const gridgcn_mlp_t *mlp_host, int B, int Nprev, int Cin);
+
+/* packed / workspace may be NULL for GRIDGCN_PRECISION_FP32. */
 int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cent,
                          const float *centmsk, int B, int Nprev, int Cin, int O, int K,
-                         const gridgcn_mlp_t *mlp_host, int precision, float *out, void *stream);
+                         const gridgcn_mlp_t *mlp_host, int precision, const void *packed,
+                         void *workspace, size_t workspace_bytes, float *out, void *stream);
 
 /* Self-test of the tcgen05 primitives (not an operator): D[128,N] = A[128,K] * B[N,K]^T on one CTA,
  * kind::tf32, nsplit 1 (plain) or 3 (error-compensated).  N % 16 == 0, N <= 256, K % 8 == 0. */

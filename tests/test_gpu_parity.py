@@ -167,7 +167,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["fp32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name,B,N,O,K,Cin,mlp", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_gridconv_matches_oracle(gg, cuda_dev, oracle_mod, name, B, N, O, K, Cin, mlp, precision):
     from oracle import gridconv_oracle

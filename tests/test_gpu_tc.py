@@ -24,5 +24,6 @@ def test_tc_gemm_selftest(gg, cuda_dev, N, K, nsplit):
     got = d.cpu().numpy().astype(np.float64)
     scale = np.sqrt(K)  # typical magnitude of an entry
     err = np.abs(got - want).max() / scale
-    tol = 2e-3 if nsplit == 1 else 2e-6  # tf32: 2^-11 per operand; split: ~fp32
+    tol = 2e-3 if nsplit == 1 else 1e-5  # tf32: 2^-11 per operand; split: fp32-class
+    print("N=%d K=%d nsplit=%d err=%.3g" % (N, K, nsplit, err))
     assert err < tol, "N=%d K=%d nsplit=%d: max err / sqrt(K) = %.3g" % (N, K, nsplit, err)
