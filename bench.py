@@ -131,7 +131,8 @@ def main():
     ap.add_argument("--batch", type=int, default=96, help="clouds per GPU per step")
     ap.add_argument("--K", type=int, default=64)
     ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify"])
-    ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "tf32x3"),
+                    choices=["tf32x3", "tf32", "fp32"])
     ap.add_argument("--cpu-clouds", type=int, default=4, help="clouds per CPU-baseline step")
     args = ap.parse_args()
 
@@ -263,8 +264,34 @@ def main():
         for _ in range(3):
             f()
         conv_ms.append(timed(f, reps_k) / reps_k)
+    query_ms = []
+    for i, l in enumerate(cfg.layers):
+        loc_in = data_d if i == 0 else trace[i - 1]["cent"]
+        num_in = npts_d if i == 0 else trace[i - 1]["actual_centnum"]
+        qf = gg.GridifyKNN if cfg.query == "gridifyknn" else gg.Gridify
+        kwl = dict(max_o_grid=l.max_o_grid, max_p_grid=l.max_p_grid, kernel_size=l.kernel_size, stride=1,
+                   coord_shift=cfg.coord_shift, voxel_size=[l.voxel_size] * 3,
+                   grid_size=[l.grid_size] * 3, loc=cfg.loc)
+        f = lambda: qf(loc_in, num_in, **kwl)
+        for _ in range(3):
+            f()
+        query_ms.append(timed(f, reps_k) / reps_k)
     dom = int(np.argmax(conv_ms))
-    tflops = B * flops_cloud[dom] / (conv_ms[dom] * 1e-3) / 1e12
+    # executed (useful) flops of the restructured layer: the feature MLP runs once per source point
+    # for layers with input features, the attention MLP once per edge ("hoisting")
+    exec_cloud = []
+    nprev = cfg.num_points
+    for i, (l, pr) in enumerate(zip(cfg.layers, params)):
+        mf = sum(st["weight"].size for st in pr["feat"])
+        ma = sum(st["weight"].size for st in pr["att"])
+        edges = l.max_o_grid * l.max_p_grid
+        if args.precision == "fp32" or i == 0:
+            exec_cloud.append(2 * edges * (mf + ma))
+        else:
+            exec_cloud.append(2 * (nprev * mf + edges * ma))
+        nprev = l.max_o_grid
+    tflops = B * exec_cloud[dom] / (conv_ms[dom] * 1e-3) / 1e12
+    tflops_alg = B * flops_cloud[dom] / (conv_ms[dom] * 1e-3) / 1e12
     l0 = cfg.layers[0]
     qfn = gg.GridifyKNN
     kwq = dict(max_o_grid=l0.max_o_grid, max_p_grid=l0.max_p_grid, kernel_size=l0.kernel_size,
@@ -281,6 +308,9 @@ def main():
     roofline = {"kernel": "gridconv layer %d (%s)" % (dom, args.precision), "bound": "tensor",
                 "achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
                 "traffic": None, "ms_per_launch": conv_ms[dom], "layer_ms": conv_ms,
+                "algorithmic_tflops": tflops_alg,
+                "note": "achieved = flops the restructured layer executes (x1, split passes not counted) / "
+                        "duration; algorithmic_tflops uses SURVEY s8d's per-edge formula 2*O*K*MAC",
                 "peak_source": peaks["_source"] + " dense bf16 cuBLAS (sustained); tf32 nominal peak is half of bf16"}
     roofline_hbm = {"kernel": "gridifyknn (build + query) N=8192 O=1024 P=%d" % l0.max_p_grid,
                     "bound": "hbm", "achieved": q_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -296,11 +326,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(world * (data_h.numel() * 4 + npts_h.numel() * 4)),
                     "d2h_bytes_per_step": int(world * out_h.numel() * 4)},
-            "gpu_launches": args.steps * len(cfg.layers) * 3,
+            "gpu_launches": args.steps * (len(cfg.layers) * 3 + (0 if args.precision == "fp32" else len(cfg.layers) - 1)),
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": {"value": cpu_val, "unit": "points/s", "cores": cores, "kind": "port",
                              "sample": "%d clouds of 8192 points, 2 steps (oracle C port with OpenMP over "
                                        "clouds + numpy/BLAS GridConv)" % args.cpu_clouds},
+            "breakdown_ms": {"query": query_ms, "gridconv": conv_ms,
+                             "note": "each operator timed alone, L2 flushed before every call"},
             "clocks": sampler.summary()}
     print(json.dumps(line))
     if world > 1:

@@ -263,7 +263,8 @@ def test_golden_fixtures_on_gpu(gg, cuda_dev):
         assert _rel_err(got.cpu().numpy()[..., 4:], z["out"][..., 4:]) <= 1e-3, case
 
 
-def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod):
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod, precision):
     """The whole encoder (query -> GridConv per layer) against the oracle chain, index tensors
     bit-exact at every layer, features within 1e-3."""
     from oracle import gridconv_oracle
@@ -272,7 +273,7 @@ def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod):
                    (stack.seg8192_shipped(), 1)):
         params = stack.init_params(cfg, seed=1)
         data, npts = synth.make_batch(B, cfg.num_points, seed0=200, voxels=cfg.voxels)
-        enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision="fp32")
+        enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision=precision)
         out = enc(_t(data, cuda_dev), _t(npts, cuda_dev), keep_trace=True)
         q = oracle_mod.gridify_knn if cfg.query == "gridifyknn" else oracle_mod.gridify
         table, loc, num = data, data, npts
@@ -320,3 +321,27 @@ def test_full_size_properties(gg, cuda_dev):
                 for o in range(0, nc, 97):
                     if len(set(nebidx[bb, o].tolist())) == P:  # no padding in this row
                         assert np.all(np.diff(dd[o]) >= -1e-6)
+
+
+def test_gridconv_plain_tf32_is_close(gg, cuda_dev, oracle_mod):
+    """GRIDGCN_PRECISION_TF32 (one tensor-core pass, operands rounded to tf32) is a speed option, not
+    the parity mode: it must stay within 1e-2 of the oracle; TF32X3 is the mode held to 1e-3."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import gridconv
+    rng = np.random.default_rng(5)
+    B, N, O, K, Cin, mlp = 2, 512, 128, 32, 64, [64, 64, 128]
+    data, npts = synth.make_batch(B, N, seed0=60, voxels=(0.25,))
+    kw = dict(max_p_grid=K, max_o_grid=O, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+              voxel_size=(0.25,) * 3, grid_size=(8,) * 3)
+    nebidx, _, cent, centmsk, _ = oracle_mod.gridify_knn(data, npts, **kw)
+    table = np.concatenate([data, rng.uniform(0, 1, size=(B, N, Cin)).astype(np.float32)], axis=2)
+    layer = gridconv.init_layer(np.random.default_rng(23), Cin, mlp, 10)
+    want = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, layer)
+    errs = {}
+    for prec in ("tf32", "tf32x3"):
+        got = gg.GridConv(layer, cuda_dev, precision=prec)(
+            _t(table, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(centmsk, cuda_dev)).cpu().numpy()
+        errs[prec] = _rel_err(got[..., 4:], want[..., 4:])
+    print("rel err:", errs)
+    assert errs["tf32x3"] <= 1e-3 and errs["tf32"] <= 1e-2
+    assert errs["tf32x3"] < errs["tf32"]
