@@ -33,7 +33,7 @@ constexpr int kTcThreads = 160;     // warps 0-3: gather + TMEM epilogue (thread
 constexpr int kTileRows = 128;
 constexpr int kSliceK = 32;         // k extent of one streamed weight slice
 constexpr int kSlotBytes = 2 * 128 * kSliceK * 4;  // hi + lo images of a [128 x 32] slice
-constexpr int kMaxRing = 4;
+constexpr int kMaxRing = 8;
 
 struct TcStage {
     int transposed;  // 0: D[row, ch], weights resident in smem as the B operand; 1: D^T[ch, row], weights streamed as A
@@ -45,22 +45,27 @@ struct TcStage {
 
 struct TcParams {
     ConvParams c;
-    const float *packed;  // packed hi/lo operand images of every stage
+    const float *packed;  // packed hi/lo operand images of every tensor-core stage
     float *ftab;          // kernel A output / kernel B input: (B*Nprev, Cout) transformed features
     int nsplit;           // 1 or 3
     // kernel A: stages a[0..na)
     int na;
     TcStage a[GRIDGCN_MAX_STAGES];
     int a_rows;           // rows per tile (64 or 128)
-    // kernel B: hidden feature stages (first layer only), last feature stage (first layer only),
-    // attention stage 0 (plain), attention stage 1 (transposed)
-    int nfh;
+    // kernel B.  Stages whose K dimension is tiny run on the CUDA cores inside the gather phase
+    // (exact fp32 FMA): the first-layer feature stage 0 (K = 3) and the attention stage 0 (K <= 10).
+    int f0_cuda, f0_cout;
+    const float *f0_w, *f0_b;      // (f0_cout, 3), (f0_cout)
+    int a0_cin, a0_cout;
+    const float *a0_w, *a0_b;      // (a0_cout, a0_cin), (a0_cout)
+    int nfh;                       // remaining first-layer hidden feature stages (tensor core, plain)
     TcStage fh[GRIDGCN_MAX_STAGES];
-    int has_ff;
+    int has_ff;                    // first layer: last feature stage (tensor core, transposed)
     TcStage ff;
-    int has_att;
-    TcStage a0, a1;
-    int ring_slots;
+    int has_att;                   // attention stage 1 (tensor core, transposed)
+    TcStage a1;
+    int ring_slots, ring_sticky;   // weight ring: number of slots; sticky = whole per-tile sequence resident
+    int tmem_cols;
 };
 
 __host__ __device__ inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
@@ -105,7 +110,8 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
 }
 
 struct Ring {
-    uint8_t *slots;       // ring_slots x kSlotBytes
+    uint8_t *slots;
+    uint32_t off[kMaxRing];  // byte offset of every slot (exact-fit in sticky mode, 32 KB apart otherwise)
     uint64_t *full, *empty;
     int nslots;
     long long issued;     // producer: slices requested so far (whole kernel)
@@ -158,7 +164,7 @@ __device__ __forceinline__ void ring_request(Ring &ring, SliceSeq &prod, const f
     uint32_t bytes;
     prod.next(off, bytes);
     tc::mbar_expect_tx(&ring.full[slot], bytes);
-    tc::bulk_g2s(ring.slots + (size_t)slot * kSlotBytes, packed + off, bytes, &ring.full[slot]);
+    tc::bulk_g2s(ring.slots + ring.off[slot], packed + off, bytes, &ring.full[slot]);
     ring.issued++;
 }
 
@@ -181,7 +187,7 @@ __device__ __forceinline__ void run_transposed_stage(const TcStage &st, Ring &ri
             const int slot = (int)(ring.consumed % ring.nslots);
             if (!sticky || ring.consumed < ring.nslots)
                 wait_bar(&ring.full[slot], (uint32_t)((ring.consumed / ring.nslots) & 1));
-            const uint32_t a_hi = tc::smem_u32(ring.slots + (size_t)slot * kSlotBytes);
+            const uint32_t a_hi = tc::smem_u32(ring.slots + ring.off[slot]);
             const uint32_t a_lo = a_hi + 128 * kw * 4;
             for (int ks = 0; ks < kw / 8; ks++) {
                 const uint64_t ah = tc::make_sdesc(a_hi + ks * 2 * 2048, 2048);
@@ -283,6 +289,7 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     ring.full = bars;
     ring.empty = bars + kMaxRing;
     ring.issued = ring.consumed = 0;
+    for (int i = 0; i < kMaxRing; i++) ring.off[i] = (uint32_t)i * kSlotBytes;
     uint64_t *bar_mma = bars + 2 * kMaxRing;
 
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
@@ -405,40 +412,76 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
 // ------------------------------------------------------------------------------------------------
 // Kernel B: per-edge attention MLP (+ the per-edge feature MLP of the first layer), product with
 // the (gathered) features, max over the K slots, centre mask, output row.
+//
+// Per tile of 128 edges:
+//   gather phase (thread = edge): neighbour xyz (128-bit load) -> geo / att_vec -> the tiny-K stages on
+//     the CUDA cores in exact fp32 (attention stage 0, K <= 10; first-layer feature stage 0, K = 3)
+//     -> hi/lo K-major operand images in shared memory;
+//   first layer only: remaining hidden feature stages on the tensor core, D[edge, ch];
+//   per 128-channel chunk: last feature stage (first layer) and attention stage 1 TRANSPOSED on the
+//     tensor core, D^T[ch, edge]; epilogue thread = channel: relu(att) * feat (feat from TMEM for the
+//     first layer, gathered from kernel A's table otherwise), running max over each centre's K
+//     consecutive TMEM columns, pre-ReLU, centre mask, coalesced store.
 // ------------------------------------------------------------------------------------------------
 template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 3)
 edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
     __shared__ uint32_t tmem_base_s;
-    __shared__ int rowidx_s[kTileRows];
+    __shared__ uint32_t rowoff_s[kTileRows];  // element offset of every edge's source row in ftab
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const ConvParams &c = p.c;
     const int K = c.K, C = c.Cout;
     constexpr uint32_t LBO = kTileRows * 16;  // images with 128 rows: panel = 2 KB
     constexpr int NIMG = NSPLIT == 3 ? 2 : 1;
 
-    // ---- shared memory carve-up ----
+    // ---- shared memory carve-up (mirrored by kernel_b_layout on the host) ----
     int kx = 0;  // feature-path image width (first layer only)
+    if (p.f0_cuda) kx = pad_to(p.f0_cout, 8);
     for (int s = 0; s < p.nfh; s++) kx = max(kx, max(p.fh[s].Kp, pad_to(p.fh[s].Cout, 8)));
     if (p.has_ff) kx = max(kx, p.ff.Kp);
-    const int kh = p.has_att ? max(p.a0.Kp, p.a1.Kp) : 0;
+    const int kh = p.has_att ? p.a1.Kp : 0;
     uint8_t *xf_hi = smem, *xf_lo = xf_hi + (size_t)(kx / 4) * LBO;
     uint8_t *xa_hi = smem + (size_t)NIMG * (kx / 4) * LBO, *xa_lo = xa_hi + (size_t)(kh / 4) * LBO;
-    uint8_t *wres = xa_hi + (size_t)NIMG * (kh / 4) * LBO;  // resident plain-stage weights (hi, lo per stage)
+    uint8_t *wres = xa_hi + (size_t)NIMG * (kh / 4) * LBO;  // resident plain-stage operand images
     size_t wres_bytes = 0;
     for (int s = 0; s < p.nfh; s++) wres_bytes += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
-    if (p.has_att) wres_bytes += (size_t)2 * p.a0.Np * p.a0.Kp * 4;
+    float *wa0_s = reinterpret_cast<float *>(wres + wres_bytes);  // [a0_cout][12] fp32 + bias[a0_cout]
+    float *ba0_s = wa0_s + (p.has_att ? p.a0_cout * 12 : 0);
+    float *wf0_s = ba0_s + (p.has_att ? p.a0_cout : 0);          // [f0_cout][4] fp32 (w0 w1 w2 bias)
+    float *small_end = wf0_s + (p.f0_cuda ? p.f0_cout * 4 : 0);
     Ring ring;
-    ring.slots = wres + pad_to((int)wres_bytes, 128);
+    ring.slots = smem + pad_to((int)(reinterpret_cast<uint8_t *>(small_end) - smem), 128);
     ring.nslots = p.ring_slots;
     ring.full = bars;
     ring.empty = bars + kMaxRing;
     ring.issued = ring.consumed = 0;
     uint64_t *bar_mma = bars + 2 * kMaxRing;
 
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    SliceSeq prod;
+    prod.n = 0;
+    prod.chunk_major = 1;
+    if (p.has_ff) prod.st[prod.n++] = &p.ff;
+    if (p.has_att) prod.st[prod.n++] = &p.a1;
+    prod.reset();
+    const int per_tile = prod.per_tile();
+    const bool sticky = p.ring_sticky != 0;
+    if (sticky) {  // exact-fit slots in sequence order
+        SliceSeq tmp = prod;
+        uint32_t o = 0;
+        for (int i = 0; i < per_tile && i < kMaxRing; i++) {
+            long long off;
+            uint32_t bytes;
+            tmp.next(off, bytes);
+            ring.off[i] = o;
+            o += bytes;
+        }
+    } else {
+        for (int i = 0; i < kMaxRing; i++) ring.off[i] = (uint32_t)i * kSlotBytes;
+    }
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
     if (tid == 0) {
         for (int i = 0; i < ring.nslots; i++) {
             tc::mbar_init(&ring.full[i], 1);
@@ -447,18 +490,29 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
         tc::mbar_init(bar_mma, 1);
         tc::mbar_init_fence();
     }
-    // resident weights: plain copy (generic proxy) of the packed images
+    // resident operands: tensor-core images of the plain stages, fp32 weights of the CUDA-core stages
     {
         size_t off = 0;
-        for (int s = 0; s <= p.nfh; s++) {
-            if (s == p.nfh && !p.has_att) break;
-            const TcStage &st = s < p.nfh ? p.fh[s] : p.a0;
+        for (int s = 0; s < p.nfh; s++) {
+            const TcStage &st = p.fh[s];
             const int n4 = 2 * st.Np * st.Kp / 4;
             const float4 *src = reinterpret_cast<const float4 *>(p.packed + st.w_off);
             float4 *dst = reinterpret_cast<float4 *>(wres + off);
             for (int i = tid; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
             off += (size_t)n4 * 16;
         }
+        if (p.has_att) {
+            for (int i = tid; i < p.a0_cout * 12; i += kTcThreads) {
+                const int j = i / 12, q = i % 12;
+                wa0_s[i] = q < p.a0_cin ? __ldg(p.a0_w + (size_t)j * p.a0_cin + q) : 0.f;
+            }
+            for (int i = tid; i < p.a0_cout; i += kTcThreads) ba0_s[i] = __ldg(p.a0_b + i);
+        }
+        if (p.f0_cuda)
+            for (int i = tid; i < p.f0_cout * 4; i += kTcThreads) {
+                const int j = i / 4, q = i % 4;
+                wf0_s[i] = q < 3 ? __ldg(p.f0_w + (size_t)j * 3 + q) : __ldg(p.f0_b + j);
+            }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -466,17 +520,8 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-    SliceSeq prod;
-    prod.n = 0;
-    prod.chunk_major = 1;
-    if (p.has_ff) prod.st[prod.n++] = &p.ff;
-    if (p.has_att) prod.st[prod.n++] = &p.a1;
-    prod.reset();
     const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int per_tile = prod.per_tile();
     const long long total_slices = (long long)my_tiles * per_tile;
-    const bool sticky = per_tile <= ring.nslots;  // whole sequence fits: load once, keep
-    if (sticky) ring.nslots = max(per_tile, 1);
     if (warp == 4 && lane == 0) {
         const long long pre = sticky ? per_tile : ring.nslots;
         for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
@@ -485,19 +530,19 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     const long long rows_total = (long long)c.B * c.Nprev;
     const long long centers_total = (long long)c.B * c.O;
     const int row_w = 4 + c.Cin;
-    const int att_w = p.has_att ? p.a0.Cin : 0;
     const int out_w = 4 + C;
+    const uint32_t tm_f = tmem, tm_g = tmem + (p.has_ff ? 128 : 0);
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long c_base = (long long)tile * cpt;
-        // ---- gather + geometry: thread = edge row ----
+        // ---- gather + geometry + tiny-K stages on the CUDA cores: thread = edge row ----
         if (warp < 4) {
             const int r = tid, cl = r / K, slot = r % K;
             const long long center = c_base + cl;
             const bool valid = cl < cpt && center < centers_total;
-            float att[16];
+            float att[12];
 #pragma unroll
-            for (int i = 0; i < 16; i++) att[i] = 0.f;
+            for (int i = 0; i < 12; i++) att[i] = 0.f;
             float dx = 0.f, dy = 0.f, dz = 0.f;
             int ridx = -1;
             if (valid) {
@@ -515,31 +560,53 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                 }
                 att_vector(c.attfdim, __ldg(c.cent + center), nx, ny, nz, att, dx, dy, dz);
             }
-            rowidx_s[r] = ridx;
-            if (p.has_att) {
-                for (int q = 0; q < p.a0.Kp / 4; q++) {
+            rowoff_s[r] = (uint32_t)(ridx < 0 ? 0 : ridx) * (uint32_t)C;
+            if (p.has_att) {  // attention stage 0: h = relu(W a + b), K <= 10, exact fp32
+                for (int j0 = 0; j0 < kh; j0 += 4) {
                     float hi[4], lo[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        float v = 0.f;
-#pragma unroll
-                        for (int z = 0; z < 16; z++) v = (z == q * 4 + i && z < att_w) ? att[z] : v;
-                        tc::split_tf32(v, hi[i], lo[i]);
+                        const int j = j0 + i;
+                        float acc = 0.f;
+                        if (j < p.a0_cout) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(wa0_s + j * 12);
+                            const float4 w1 = *reinterpret_cast<const float4 *>(wa0_s + j * 12 + 4);
+                            const float4 w2 = *reinterpret_cast<const float4 *>(wa0_s + j * 12 + 8);
+                            acc = ba0_s[j];
+                            acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
+                            acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
+                            acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
+                            acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
+                            acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
+                            acc = fmaxf(acc, 0.f);
+                        }
+                        tc::split_tf32(acc, hi[i], lo[i]);
                     }
-                    const uint32_t off = tc::kmajor_off(r, q * 4, LBO);
+                    const uint32_t off = tc::kmajor_off(r, j0, LBO);
                     *reinterpret_cast<float4 *>(xa_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     if (NSPLIT == 3)
                         *reinterpret_cast<float4 *>(xa_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
-            if (c.Cin == 0) {  // first layer: features are the geo vector (gcn_module_g_att.py:242-243)
-                const int kp0 = p.nfh > 0 ? p.fh[0].Kp : p.ff.Kp;
-                float g[4] = {dx, dy, dz, 0.f};
-                for (int q = 0; q < kp0 / 4; q++) {
+            if (c.Cin == 0) {  // first layer: features start from the geo vector (gcn_module_g_att.py:242-243)
+                const int kw = p.f0_cuda ? pad_to(p.f0_cout, 8) : (p.nfh > 0 ? p.fh[0].Kp : p.ff.Kp);
+                for (int j0 = 0; j0 < kw; j0 += 4) {
                     float hi[4], lo[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) tc::split_tf32(q == 0 ? g[i] : 0.f, hi[i], lo[i]);
-                    const uint32_t off = tc::kmajor_off(r, q * 4, LBO);
+                    for (int i = 0; i < 4; i++) {
+                        const int j = j0 + i;
+                        float v = 0.f;
+                        if (p.f0_cuda) {  // feature stage 0 (K = 3) on the CUDA cores
+                            if (j < p.f0_cout) {
+                                const float4 w = *reinterpret_cast<const float4 *>(wf0_s + j * 4);
+                                v = fmaxf(fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, w.w))), 0.f);
+                            }
+                        } else {
+                            v = j == 0 ? dx : (j == 1 ? dy : (j == 2 ? dz : 0.f));
+                        }
+                        tc::split_tf32(v, hi[i], lo[i]);
+                    }
+                    const uint32_t off = tc::kmajor_off(r, j0, LBO);
                     *reinterpret_cast<float4 *>(xf_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     if (NSPLIT == 3)
                         *reinterpret_cast<float4 *>(xf_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -551,16 +618,13 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
         __syncthreads();
         tc::fence_after_sync();
 
-        // ---- plain (hidden) stages: feature hidden stages of the first layer, then attention stage 0 ----
+        // ---- first layer: remaining hidden feature stages on the tensor core, D[edge, ch] ----
         size_t woff = 0;
-        for (int s = 0; s <= p.nfh; s++) {
-            const bool is_att = s == p.nfh;
-            if (is_att && !p.has_att) break;
-            const TcStage &st = is_att ? p.a0 : p.fh[s];
-            uint8_t *xi_hi = is_att ? xa_hi : xf_hi, *xi_lo = is_att ? xa_lo : xf_lo;
+        for (int s = 0; s < p.nfh; s++) {
+            const TcStage &st = p.fh[s];
             if (warp == 4) {
                 if (lane == 0) {
-                    run_plain_stage<NSPLIT>(st, tc::smem_u32(xi_hi), tc::smem_u32(xi_lo), LBO,
+                    run_plain_stage<NSPLIT>(st, tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO,
                                             tc::smem_u32(wres + woff), tmem);
                     tc::mma_commit(bar_mma);
                 }
@@ -571,8 +635,8 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             mma_phase ^= 1;
             tc::fence_after_sync();
             if (warp < 4) {
-                const int kp_next = is_att ? p.a1.Kp : (s + 1 < p.nfh ? p.fh[s + 1].Kp : p.ff.Kp);
-                plain_epilogue<NSPLIT>(st, tmem + ((uint32_t)(warp * 32) << 16), tid, xi_hi, xi_lo, LBO, kp_next);
+                const int kp_next = s + 1 < p.nfh ? p.fh[s + 1].Kp : p.ff.Kp;
+                plain_epilogue<NSPLIT>(st, tmem + ((uint32_t)(warp * 32) << 16), tid, xf_hi, xf_lo, LBO, kp_next);
             }
             tc::fence_async_smem();
             tc::fence_before_sync();
@@ -580,70 +644,95 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             tc::fence_after_sync();
         }
 
-        // ---- transposed stages: last feature stage (first layer) into cols [0,128*nch), last attention
-        //      stage into the following columns, chunk by chunk of 128 channels ----
+        // ---- transposed stages, one 128-channel chunk at a time ----
         const int nchunk = pad_to(C, 128) / 128;
         for (int j = 0; j < nchunk; j++) {
             if (warp == 4) {
                 if (lane == 0) {
-                    // one chunk at a time: build single-chunk views of the stages
                     if (p.has_ff) {
                         TcStage v = p.ff;
                         v.Np = 128;
                         v.w_off = p.ff.w_off + (long long)j * 2 * 128 * p.ff.Kp;
                         run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
-                                                     tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO, 128, tmem, 0);
+                                                     tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO, 128, tm_f, 0);
                     }
                     if (p.has_att) {
                         TcStage v = p.a1;
                         v.Np = 128;
                         v.w_off = p.a1.w_off + (long long)j * 2 * 128 * p.a1.Kp;
                         run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
-                                                     tc::smem_u32(xa_hi), tc::smem_u32(xa_lo), LBO, 128,
-                                                     tmem + 128, 0);
+                                                     tc::smem_u32(xa_hi), tc::smem_u32(xa_lo), LBO, 128, tm_g, 0);
                     }
                     tc::mma_commit(bar_mma);
                 }
                 __syncwarp();
             }
+            // ---- final epilogue: thread = channel (TMEM lane), 16 edge columns per batch ----
+            const int ch = j * 128 + tid;
+            const bool chv = warp < 4 && ch < C;
+            // gathered feature of edge e for this channel: fbase[rowoff_s[e]] (invalid rows/channels are
+            // clamped to a valid address; their values never reach the output)
+            const float *fbase = p.ftab + (chv ? ch : 0);
+            float fg[16];
+            if (warp < 4 && !p.has_ff) {  // first batch of feature gathers issued under the MMAs
+#pragma unroll
+                for (int i = 0; i < 16; i++) fg[i] = __ldg(fbase + rowoff_s[i]);
+            }
             wait_bar(bar_mma, mma_phase);
             mma_phase ^= 1;
             tc::fence_after_sync();
             if (warp < 4) {
-                const int ch = j * 128 + tid;
-                const bool chv = ch < C;
                 const float bf = (p.has_ff && chv) ? __ldg(p.ff.bias + ch) : 0.f;
                 const float ba = (p.has_att && chv) ? __ldg(p.a1.bias + ch) : 0.f;
-                const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+                const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
                 float m = -3.402823466e+38f;
                 int pos = 0, cl = 0;
                 for (int e0 = 0; e0 < kTileRows; e0 += 16) {
-                    uint32_t fv[16], gv[16];
-                    if (p.has_ff) tc::tmem_ld16(tl + e0, fv);
-                    if (p.has_att) tc::tmem_ld16(tl + 128 + e0, gv);
-                    float fg[16];
-                    if (!p.has_ff) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const int ri = rowidx_s[e0 + i];
-                            fg[i] = (chv && ri >= 0) ? __ldg(p.ftab + (size_t)ri * C + ch) : 0.f;
-                        }
-                    }
+                    uint32_t gv[16], fv[16];
+                    if (p.has_att) tc::tmem_ld16(tm_g + lane_off + e0, gv);
+                    if (p.has_ff) tc::tmem_ld16(tm_f + lane_off + e0, fv);
                     tc::tmem_ld_wait();
+                    float pr[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         float f = p.has_ff ? fmaxf(__uint_as_float(fv[i]) + bf, 0.f) : fg[i];
-                        if (p.has_att) f *= fmaxf(__uint_as_float(gv[i]) + ba, 0.f);
-                        if (cl < cpt) m = fmaxf(m, f);
-                        if (++pos == K) {
+                        if (p.has_att) f *= fmaxf(__uint_as_float(gv[i]) + ba, 0.f);  // :167 att * feats
+                        pr[i] = f;
+                    }
+                    if (!p.has_ff && e0 + 16 < kTileRows) {  // next batch of gathers in flight
+#pragma unroll
+                        for (int i = 0; i < 16; i++) fg[i] = __ldg(fbase + rowoff_s[e0 + 16 + i]);
+                    }
+                    if ((K & 15) == 0) {  // the 16 columns belong to one centre
+                        float mm = pr[0];
+#pragma unroll
+                        for (int i = 1; i < 16; i++) mm = fmaxf(mm, pr[i]);
+                        m = fmaxf(m, mm);
+                        pos += 16;
+                        if (pos == K) {
                             const long long center = c_base + cl;
                             if (chv && cl < cpt && center < centers_total) {
-                                float y = c.pre_relu ? fmaxf(m, 0.f) : m;
+                                const float y = c.pre_relu ? fmaxf(m, 0.f) : m;
                                 c.out[center * out_w + 4 + ch] = y * __ldg(c.centmsk + center);
                             }
                             pos = 0;
                             cl++;
                             m = -3.402823466e+38f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            m = fmaxf(m, pr[i]);
+                            if (++pos == K) {
+                                const long long center = c_base + cl;
+                                if (chv && cl < cpt && center < centers_total) {
+                                    const float y = c.pre_relu ? fmaxf(m, 0.f) : m;
+                                    c.out[center * out_w + 4 + ch] = y * __ldg(c.centmsk + center);
+                                }
+                                pos = 0;
+                                cl++;
+                                m = -3.402823466e+38f;
+                            }
                         }
                     }
                 }
@@ -663,7 +752,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
         }
     }
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -681,27 +770,54 @@ static void make_stage(TcStage &s, int transposed, int cin, int cout, const floa
 }
 
 // Fills the stage tables of both kernels; returns the packed size in floats (or < 0 if unsupported).
-static long long build_tc_plan(const ConvParams &c, TcParams &p) {
+// `src` receives, for every packed stage, the index of its weight matrix in ConvParams::w.
+struct PackList {
+    TcStage st[2 * GRIDGCN_MAX_STAGES];
+    int widx[2 * GRIDGCN_MAX_STAGES];
+    int n;
+};
+
+static long long build_tc_plan(const ConvParams &c, TcParams &p, PackList *pl) {
     p.c = c;
     long long off = 0;
     const int nf = c.n_feat;
-    p.na = p.nfh = p.has_ff = 0;
+    p.na = p.nfh = p.has_ff = p.f0_cuda = 0;
     p.has_att = c.attfdim > 0;
-    if (nf > 3) return -1;  // slice sequence holds up to 3 streamed stages
+    if (pl) pl->n = 0;
+    auto add = [&](TcStage &st, int transposed, int widx) {
+        make_stage(st, transposed, c.cin[widx], c.cout[widx], c.bias[widx], off);
+        if (pl) {
+            pl->st[pl->n] = st;
+            pl->widx[pl->n++] = widx;
+        }
+    };
+    if (nf > 3) return -1;  // the slice sequence holds up to 3 streamed stages
     if (c.Cin > 0) {
-        for (int s = 0; s < nf; s++) make_stage(p.a[p.na++], 1, c.cin[s], c.cout[s], c.bias[s], off);
+        for (int s = 0; s < nf; s++) add(p.a[p.na++], 1, s);
     } else {
-        for (int s = 0; s + 1 < nf; s++) make_stage(p.fh[p.nfh++], 0, c.cin[s], c.cout[s], c.bias[s], off);
-        make_stage(p.ff, 1, c.cin[nf - 1], c.cout[nf - 1], c.bias[nf - 1], off);
+        int first = 0;
+        if (nf >= 2) {  // feature stage 0 (K = 3) runs on the CUDA cores
+            p.f0_cuda = 1;
+            p.f0_cout = c.cout[0];
+            p.f0_w = c.w[0];
+            p.f0_b = c.bias[0];
+            first = 1;
+        }
+        for (int s = first; s + 1 < nf; s++) add(p.fh[p.nfh++], 0, s);
+        add(p.ff, 1, nf - 1);
         p.has_ff = 1;
     }
-    if (p.has_att) {
-        make_stage(p.a0, 0, c.cin[nf], c.cout[nf], c.bias[nf], off);
-        make_stage(p.a1, 1, c.cin[nf + 1], c.cout[nf + 1], c.bias[nf + 1], off);
+    if (p.has_att) {  // attention stage 0 (K <= 10) runs on the CUDA cores
+        p.a0_cin = c.cin[nf];
+        p.a0_cout = c.cout[nf];
+        p.a0_w = c.w[nf];
+        p.a0_b = c.bias[nf];
+        if (p.a0_cin > 10) return -1;
+        add(p.a1, 1, nf + 1);
     }
     for (int s = 0; s < p.nfh; s++)
         if (p.fh[s].Np > 128) return -1;
-    if (p.has_att && p.a0.Np > 128) return -1;
+    p.tmem_cols = p.has_ff ? 256 : 128;
     return off;
 }
 
@@ -712,17 +828,32 @@ static size_t kernel_a_smem(const TcParams &p, int TR, int nsplit, int slots) {
     return pad_to((int)((nsplit == 3 ? 2 : 1) * x_img), 128) + (size_t)slots * kSlotBytes + 1024;
 }
 
-static size_t kernel_b_smem(const TcParams &p, int nsplit, int slots) {
+// Shared-memory bytes of kernel B in front of the ring, and the per-tile slice sequence of the ring.
+static size_t kernel_b_base(const TcParams &p, int nsplit) {
     int kx = 0;
+    if (p.f0_cuda) kx = pad_to(p.f0_cout, 8);
     for (int s = 0; s < p.nfh; s++) kx = max(kx, max(p.fh[s].Kp, pad_to(p.fh[s].Cout, 8)));
     if (p.has_ff) kx = max(kx, p.ff.Kp);
-    int kh = p.has_att ? max(p.a0.Kp, p.a1.Kp) : 0;
+    int kh = p.has_att ? p.a1.Kp : 0;
     size_t nimg = nsplit == 3 ? 2 : 1;
     size_t bytes = nimg * (size_t)(kx / 4 + kh / 4) * kTileRows * 16;
-    size_t wres = 0;
-    for (int s = 0; s < p.nfh; s++) wres += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
-    if (p.has_att) wres += (size_t)2 * p.a0.Np * p.a0.Kp * 4;
-    return bytes + pad_to((int)wres, 128) + (size_t)slots * kSlotBytes + 1024;
+    for (int s = 0; s < p.nfh; s++) bytes += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
+    if (p.has_att) bytes += (size_t)p.a0_cout * 13 * 4;
+    if (p.f0_cuda) bytes += (size_t)p.f0_cout * 4 * 4;
+    return pad_to((int)bytes, 128);
+}
+
+static void kernel_b_sequence(const TcParams &p, int &n_slices, size_t &seq_bytes) {
+    n_slices = 0;
+    seq_bytes = 0;
+    const TcStage *st[2];
+    int n = 0;
+    if (p.has_ff) st[n++] = &p.ff;
+    if (p.has_att) st[n++] = &p.a1;
+    for (int i = 0; i < n; i++) {
+        n_slices += (st[i]->Np / 128) * ((st[i]->Kp + kSliceK - 1) / kSliceK);
+        seq_bytes += (size_t)2 * st[i]->Np * st[i]->Kp * 4;
+    }
 }
 
 constexpr size_t kSmemCap = 224 * 1024;  // dynamic part; static barriers/index cache use < 3 KB of the 227 KB
@@ -744,17 +875,18 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         attr_set = true;
     }
     if (p.na > 0) {  // kernel A
-        int TR = 128, slots = 3;
+        int chunks = 0;
+        for (int s = 0; s < p.na; s++) chunks = max(chunks, p.a[s].Np / 128);
+        int TR = chunks * 128 > 256 ? 64 : 128, slots = 3;  // TMEM: chunks * TR columns <= 256
         while (kernel_a_smem(p, TR, NSPLIT, slots) > kSmemCap) {
             if (slots > 2) slots--;
             else if (TR == 128) { TR = 64; slots = 3; }
             else return GRIDGCN_ELIMIT;
         }
+        if (chunks * TR > 256) return GRIDGCN_ELIMIT;
         p.a_rows = TR;
         p.ring_slots = slots;
-        int chunks = 0;
-        for (int s = 0; s < p.na; s++) chunks = max(chunks, p.a[s].Np / 128);
-        if (chunks * TR > 256) return GRIDGCN_ELIMIT;  // TMEM columns
+        p.ring_sticky = 0;
         long long rows = (long long)c.B * c.Nprev;
         long long tiles = (rows + TR - 1) / TR;
         size_t smem = kernel_a_smem(p, TR, NSPLIT, slots);
@@ -766,18 +898,33 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
     }
     {  // kernel B
         if (c.K > kTileRows) return GRIDGCN_ELIMIT;
-        int slots = 3;
-        while (kernel_b_smem(p, NSPLIT, slots) > kSmemCap) {
-            if (slots > 2) slots--;
-            else return GRIDGCN_ELIMIT;
+        if ((long long)c.B * c.Nprev * c.Cout >= (1LL << 32)) return GRIDGCN_ELIMIT;  // 32-bit row offsets
+        const size_t base = kernel_b_base(p, NSPLIT);
+        int n_slices;
+        size_t seq_bytes;
+        kernel_b_sequence(p, n_slices, seq_bytes);
+        size_t smem;
+        if (n_slices <= kMaxRing && base + seq_bytes + 1024 <= kSmemCap) {
+            p.ring_sticky = 1;  // every weight slice of a tile stays resident: loaded once per CTA
+            p.ring_slots = max(n_slices, 1);
+            smem = base + seq_bytes + 1024;
+        } else {
+            p.ring_sticky = 0;
+            p.ring_slots = 3;
+            while (base + (size_t)p.ring_slots * kSlotBytes + 1024 > kSmemCap) {
+                if (p.ring_slots > 2) p.ring_slots--;
+                else return GRIDGCN_ELIMIT;
+            }
+            smem = base + (size_t)p.ring_slots * kSlotBytes + 1024;
         }
-        p.ring_slots = slots;
         const int cpt = kTileRows / c.K;
         long long centers = (long long)c.B * c.O;
         long long tiles = (centers + cpt - 1) / cpt;
         if (tiles > 0x7fffffff) return GRIDGCN_ELIMIT;
-        size_t smem = kernel_b_smem(p, NSPLIT, slots);
-        int per_sm = (int)max((size_t)1, min((size_t)2, kSmemCap / smem));
+        // co-resident CTAs hide the lock-step latencies: limited by shared memory, TMEM columns (512 per SM)
+        // and threads
+        int per_sm = (int)min(min((size_t)3, kSmemCap / smem), (size_t)(512 / p.tmem_cols));  // 3: register limit (128 regs x 160 threads)
+        per_sm = max(per_sm, 1);
         int blocks = (int)min(tiles, (long long)sms * per_sm);
         edge_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
         return (int)cudaGetLastError();
@@ -786,24 +933,18 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
 
 int tc_packed_floats(const ConvParams &c) {
     TcParams p{};
-    long long n = build_tc_plan(c, p);
-    return n < 0 || n > 0x7fffffff ? -1 : (int)n;
+    long long n = build_tc_plan(c, p, nullptr);
+    return n < 0 || n > 0x7fffffff ? -1 : (int)max(n, 4LL);
 }
 
 int tc_pack(const ConvParams &c, float *packed, cudaStream_t st) {
     TcParams p{};
-    if (build_tc_plan(c, p) < 0) return GRIDGCN_ELIMIT;
-    auto run = [&](const TcStage &s, const float *W) {
+    PackList pl;
+    if (build_tc_plan(c, p, &pl) < 0) return GRIDGCN_ELIMIT;
+    for (int i = 0; i < pl.n; i++) {
+        const TcStage &s = pl.st[i];
         int total = s.Np * s.Kp;
-        pack_stage_kernel<<<(total + 255) / 256, 256, 0, st>>>(W, packed, s);
-    };
-    const int nf = c.n_feat;
-    for (int s = 0; s < p.na; s++) run(p.a[s], c.w[s]);
-    for (int s = 0; s < p.nfh; s++) run(p.fh[s], c.w[s]);
-    if (p.has_ff) run(p.ff, c.w[nf - 1]);
-    if (p.has_att) {
-        run(p.a0, c.w[nf]);
-        run(p.a1, c.w[nf + 1]);
+        pack_stage_kernel<<<(total + 255) / 256, 256, 0, st>>>(c.w[pl.widx[i]], packed, s);
     }
     return (int)cudaGetLastError();
 }
@@ -811,7 +952,7 @@ int tc_pack(const ConvParams &c, float *packed, cudaStream_t st) {
 int launch_gridconv_tc(const ConvParams &c, int precision, const float *packed, float *ftab,
                        cudaStream_t st) {
     TcParams p{};
-    if (build_tc_plan(c, p) < 0) return GRIDGCN_ELIMIT;
+    if (build_tc_plan(c, p, nullptr) < 0) return GRIDGCN_ELIMIT;
     if (!packed || (c.Cin > 0 && !ftab)) return GRIDGCN_EWORKSPACE;
     p.packed = packed;
     p.ftab = ftab;
