@@ -173,7 +173,7 @@ def main():
     # ------------------------------------------------------------------ this framework
     import torch
     import torch.distributed as dist
-    from gridgcn_b200 import synth
+    from gridgcn_b200 import synth, shard
     import gridgcn_b200 as gg
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: gridgcn_b200 has no CPU path")
@@ -186,7 +186,8 @@ def main():
     B = args.batch
     # rank r owns clouds [r*B, (r+1)*B): seeds are global cloud ids, so any N sees the same data
     pool = min(B, 32)  # distinct clouds generated per rank, tiled to B (host generation cost)
-    base, npts1 = synth.make_batch(pool, cfg.num_points, seed0=rank * B, voxels=cfg.voxels)
+    base, npts1 = synth.make_batch(pool, cfg.num_points, seed0=shard.cloud_seeds(B, rank)[0],
+                                   voxels=cfg.voxels)
     reps = (B + pool - 1) // pool
     data_h = torch.from_numpy(np.tile(base, (reps, 1, 1))[:B].copy()).pin_memory()
     npts_h = torch.full((B, 1), cfg.num_points, dtype=torch.int32).pin_memory()
@@ -237,10 +238,7 @@ def main():
     barrier()
     sampler.stop_flag = True
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e = shard.max_over_ranks([ms_total, ms_e2e], device=dev)  # MAX over ranks
     points_job = world * B * cfg.num_points
     value = points_job * args.steps / (ms_total * 1e-3)
     e2e_value = points_job * args.steps / (ms_e2e * 1e-3)

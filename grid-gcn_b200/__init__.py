@@ -10,8 +10,8 @@ from . import synth  # noqa: F401  host-side input generator, numpy only
 from . import _lib  # noqa: F401  ctypes binding (loads the library lazily)
 from .ops import Gridify, GridifyKNN, GridifyUp, contrib  # noqa: F401
 from .gridconv import GridConv, sub_g_update, fold_bn, init_layer, features_nco  # noqa: F401
-from . import stack  # noqa: F401
+from . import stack, shard  # noqa: F401
 from .build import build  # noqa: F401
 
 __all__ = ["Gridify", "GridifyKNN", "GridifyUp", "contrib", "GridConv", "sub_g_update", "fold_bn",
-           "init_layer", "features_nco", "stack", "synth", "build"]
+           "init_layer", "features_nco", "stack", "shard", "synth", "build"]
