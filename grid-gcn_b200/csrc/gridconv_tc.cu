@@ -422,9 +422,11 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
 //     tensor core, D^T[ch, edge]; epilogue thread = channel: relu(att) * feat (feat from TMEM for the
 //     first layer, gathered from kernel A's table otherwise), running max over each centre's K
 //     consecutive TMEM columns, pre-ReLU, centre mask, coalesced store.
+// FIRST selects the first-layer variant (features computed per edge) at compile time so that neither
+// variant carries the other's (predicated) instructions.
 // ------------------------------------------------------------------------------------------------
-template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 3)
+template <int NSPLIT, bool FIRST>
+__global__ void __launch_bounds__(kTcThreads, FIRST ? 2 : 3)
 edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
@@ -435,22 +437,27 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     const int K = c.K, C = c.Cout;
     constexpr uint32_t LBO = kTileRows * 16;  // images with 128 rows: panel = 2 KB
     constexpr int NIMG = NSPLIT == 3 ? 2 : 1;
+    const bool has_att = p.has_att != 0;
 
-    // ---- shared memory carve-up (mirrored by kernel_b_layout on the host) ----
+    // ---- shared memory carve-up (mirrored by kernel_b_base on the host) ----
     int kx = 0;  // feature-path image width (first layer only)
-    if (p.f0_cuda) kx = pad_to(p.f0_cout, 8);
-    for (int s = 0; s < p.nfh; s++) kx = max(kx, max(p.fh[s].Kp, pad_to(p.fh[s].Cout, 8)));
-    if (p.has_ff) kx = max(kx, p.ff.Kp);
-    const int kh = p.has_att ? p.a1.Kp : 0;
+    if (FIRST) {
+        if (p.f0_cuda) kx = pad_to(p.f0_cout, 8);
+        for (int s = 0; s < p.nfh; s++) kx = max(kx, max(p.fh[s].Kp, pad_to(p.fh[s].Cout, 8)));
+        kx = max(kx, p.ff.Kp);
+    }
+    const int kh = has_att ? p.a1.Kp : 0;
     uint8_t *xf_hi = smem, *xf_lo = xf_hi + (size_t)(kx / 4) * LBO;
     uint8_t *xa_hi = smem + (size_t)NIMG * (kx / 4) * LBO, *xa_lo = xa_hi + (size_t)(kh / 4) * LBO;
     uint8_t *wres = xa_hi + (size_t)NIMG * (kh / 4) * LBO;  // resident plain-stage operand images
     size_t wres_bytes = 0;
     for (int s = 0; s < p.nfh; s++) wres_bytes += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
-    float *wa0_s = reinterpret_cast<float *>(wres + wres_bytes);  // [a0_cout][12] fp32 + bias[a0_cout]
-    float *ba0_s = wa0_s + (p.has_att ? p.a0_cout * 12 : 0);
-    float *wf0_s = ba0_s + (p.has_att ? p.a0_cout : 0);          // [f0_cout][4] fp32 (w0 w1 w2 bias)
-    float *small_end = wf0_s + (p.f0_cuda ? p.f0_cout * 4 : 0);
+    // CUDA-core stage weights, zero padded so that the inner loops need no bounds checks:
+    //   wa0_s[kh][12]: 10 weights, bias in slot 10 (att[10] == 1), 0;   wf0_s[kf0][4]: w0 w1 w2 bias
+    float *wa0_s = reinterpret_cast<float *>(wres + wres_bytes);
+    const int kf0 = (FIRST && p.f0_cuda) ? pad_to(p.f0_cout, 8) : 0;
+    float *wf0_s = wa0_s + kh * 12;
+    float *small_end = wf0_s + kf0 * 4;
     Ring ring;
     ring.slots = smem + pad_to((int)(reinterpret_cast<uint8_t *>(small_end) - smem), 128);
     ring.nslots = p.ring_slots;
@@ -462,8 +469,8 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     SliceSeq prod;
     prod.n = 0;
     prod.chunk_major = 1;
-    if (p.has_ff) prod.st[prod.n++] = &p.ff;
-    if (p.has_att) prod.st[prod.n++] = &p.a1;
+    if (FIRST) prod.st[prod.n++] = &p.ff;
+    if (has_att) prod.st[prod.n++] = &p.a1;
     prod.reset();
     const int per_tile = prod.per_tile();
     const bool sticky = p.ring_sticky != 0;
@@ -501,18 +508,19 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             for (int i = tid; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
             off += (size_t)n4 * 16;
         }
-        if (p.has_att) {
-            for (int i = tid; i < p.a0_cout * 12; i += kTcThreads) {
-                const int j = i / 12, q = i % 12;
-                wa0_s[i] = q < p.a0_cin ? __ldg(p.a0_w + (size_t)j * p.a0_cin + q) : 0.f;
+        for (int i = tid; i < kh * 12; i += kTcThreads) {
+            const int j = i / 12, q = i % 12;
+            float v = 0.f;
+            if (j < p.a0_cout) {
+                if (q < p.a0_cin) v = __ldg(p.a0_w + (size_t)j * p.a0_cin + q);
+                else if (q == 10) v = __ldg(p.a0_b + j);
             }
-            for (int i = tid; i < p.a0_cout; i += kTcThreads) ba0_s[i] = __ldg(p.a0_b + i);
+            wa0_s[i] = v;
         }
-        if (p.f0_cuda)
-            for (int i = tid; i < p.f0_cout * 4; i += kTcThreads) {
-                const int j = i / 4, q = i % 4;
-                wf0_s[i] = q < 3 ? __ldg(p.f0_w + (size_t)j * 3 + q) : __ldg(p.f0_b + j);
-            }
+        for (int i = tid; i < kf0 * 4; i += kTcThreads) {
+            const int j = i / 4, q = i % 4;
+            wf0_s[i] = j < p.f0_cout ? (q < 3 ? __ldg(p.f0_w + (size_t)j * 3 + q) : __ldg(p.f0_b + j)) : 0.f;
+        }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -531,25 +539,29 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     const long long centers_total = (long long)c.B * c.O;
     const int row_w = 4 + c.Cin;
     const int out_w = 4 + C;
-    const uint32_t tm_f = tmem, tm_g = tmem + (p.has_ff ? 128 : 0);
+    const int attfdim = c.attfdim, Nprev = c.Nprev, O = c.O;
+    const uint32_t tm_f = tmem, tm_g = tmem + (FIRST ? 128 : 0);
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;  // this edge's row in an image
+    const int nchunk = pad_to(C, 128) / 128;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long c_base = (long long)tile * cpt;
         // ---- gather + geometry + tiny-K stages on the CUDA cores: thread = edge row ----
         if (warp < 4) {
-            const int r = tid, cl = r / K, slot = r % K;
+            const int cl = tid / K, slot = tid - cl * K;
             const long long center = c_base + cl;
             const bool valid = cl < cpt && center < centers_total;
             float att[12];
 #pragma unroll
             for (int i = 0; i < 12; i++) att[i] = 0.f;
+            att[10] = 1.f;  // multiplies the bias column of wa0_s
             float dx = 0.f, dy = 0.f, dz = 0.f;
-            int ridx = -1;
+            uint32_t roff = 0;
             if (valid) {
-                const int b = (int)(center / c.O);
+                const int b = (int)(center / O);
                 const int idx = __ldg(c.nebidx + center * K + slot);
-                const long long row = take_row(idx, b, c.Nprev, rows_total);
-                ridx = (int)row;
+                const long long row = take_row(idx, b, Nprev, rows_total);
+                roff = (uint32_t)row * (uint32_t)C;
                 const float *src = c.table + row * row_w;
                 float nx, ny, nz;
                 if ((row_w & 3) == 0) {
@@ -558,58 +570,57 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                 } else {
                     nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
                 }
-                att_vector(c.attfdim, __ldg(c.cent + center), nx, ny, nz, att, dx, dy, dz);
+                att_vector(attfdim, __ldg(c.cent + center), nx, ny, nz, att, dx, dy, dz);
             }
-            rowoff_s[r] = (uint32_t)(ridx < 0 ? 0 : ridx) * (uint32_t)C;
-            if (p.has_att) {  // attention stage 0: h = relu(W a + b), K <= 10, exact fp32
-                for (int j0 = 0; j0 < kh; j0 += 4) {
-                    float hi[4], lo[4];
+            if (!FIRST) rowoff_s[tid] = roff;
+            // attention stage 0: h = relu(W a + b), K <= 10, exact fp32 (bias folded in as w[10] * 1)
+            for (int g = 0; g < kh / 4; g++) {
+                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 48);
+                float hi[4], lo[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int j = j0 + i;
-                        float acc = 0.f;
-                        if (j < p.a0_cout) {
-                            const float4 w0 = *reinterpret_cast<const float4 *>(wa0_s + j * 12);
-                            const float4 w1 = *reinterpret_cast<const float4 *>(wa0_s + j * 12 + 4);
-                            const float4 w2 = *reinterpret_cast<const float4 *>(wa0_s + j * 12 + 8);
-                            acc = ba0_s[j];
-                            acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
-                            acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
-                            acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
-                            acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
-                            acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
-                            acc = fmaxf(acc, 0.f);
-                        }
-                        tc::split_tf32(acc, hi[i], lo[i]);
-                    }
-                    const uint32_t off = tc::kmajor_off(r, j0, LBO);
-                    *reinterpret_cast<float4 *>(xa_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    if (NSPLIT == 3)
-                        *reinterpret_cast<float4 *>(xa_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                for (int i = 0; i < 4; i++) {
+                    const float4 w0 = w4[i * 3], w1 = w4[i * 3 + 1], w2 = w4[i * 3 + 2];
+                    float acc = w2.z;  // bias (att[10] == 1)
+                    acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
+                    acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
+                    acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
+                    acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
+                    acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
+                    tc::split_tf32(fmaxf(acc, 0.f), hi[i], lo[i]);
                 }
+                const uint32_t off = row_off + (uint32_t)g * LBO;
+                *reinterpret_cast<float4 *>(xa_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (NSPLIT == 3)
+                    *reinterpret_cast<float4 *>(xa_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
-            if (c.Cin == 0) {  // first layer: features start from the geo vector (gcn_module_g_att.py:242-243)
-                const int kw = p.f0_cuda ? pad_to(p.f0_cout, 8) : (p.nfh > 0 ? p.fh[0].Kp : p.ff.Kp);
-                for (int j0 = 0; j0 < kw; j0 += 4) {
-                    float hi[4], lo[4];
+            if (FIRST) {  // features start from the geo vector (gcn_module_g_att.py:242-243)
+                if (kf0 > 0) {  // feature stage 0 (K = 3) on the CUDA cores
+                    for (int g = 0; g < kf0 / 4; g++) {
+                        const float4 *w4 = reinterpret_cast<const float4 *>(wf0_s + g * 16);
+                        float hi[4], lo[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int j = j0 + i;
-                        float v = 0.f;
-                        if (p.f0_cuda) {  // feature stage 0 (K = 3) on the CUDA cores
-                            if (j < p.f0_cout) {
-                                const float4 w = *reinterpret_cast<const float4 *>(wf0_s + j * 4);
-                                v = fmaxf(fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, w.w))), 0.f);
-                            }
-                        } else {
-                            v = j == 0 ? dx : (j == 1 ? dy : (j == 2 ? dz : 0.f));
+                        for (int i = 0; i < 4; i++) {
+                            const float4 w = w4[i];
+                            const float v = fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, w.w)));
+                            tc::split_tf32(fmaxf(v, 0.f), hi[i], lo[i]);
                         }
-                        tc::split_tf32(v, hi[i], lo[i]);
+                        const uint32_t off = row_off + (uint32_t)g * LBO;
+                        *reinterpret_cast<float4 *>(xf_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        if (NSPLIT == 3)
+                            *reinterpret_cast<float4 *>(xf_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    const uint32_t off = tc::kmajor_off(r, j0, LBO);
-                    *reinterpret_cast<float4 *>(xf_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    if (NSPLIT == 3)
-                        *reinterpret_cast<float4 *>(xf_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                } else {  // single-stage feature MLP: the tensor core reads the geo vector itself (K = 8)
+                    float hi[4], lo[4];
+                    tc::split_tf32(dx, hi[0], lo[0]);
+                    tc::split_tf32(dy, hi[1], lo[1]);
+                    tc::split_tf32(dz, hi[2], lo[2]);
+                    hi[3] = lo[3] = 0.f;
+                    *reinterpret_cast<float4 *>(xf_hi + row_off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4 *>(xf_hi + row_off + LBO) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (NSPLIT == 3) {
+                        *reinterpret_cast<float4 *>(xf_lo + row_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<float4 *>(xf_lo + row_off + LBO) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
             }
         }
@@ -619,44 +630,45 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
         tc::fence_after_sync();
 
         // ---- first layer: remaining hidden feature stages on the tensor core, D[edge, ch] ----
-        size_t woff = 0;
-        for (int s = 0; s < p.nfh; s++) {
-            const TcStage &st = p.fh[s];
-            if (warp == 4) {
-                if (lane == 0) {
-                    run_plain_stage<NSPLIT>(st, tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO,
-                                            tc::smem_u32(wres + woff), tmem);
-                    tc::mma_commit(bar_mma);
+        if (FIRST) {
+            size_t woff = 0;
+            for (int s = 0; s < p.nfh; s++) {
+                const TcStage &st = p.fh[s];
+                if (warp == 4) {
+                    if (lane == 0) {
+                        run_plain_stage<NSPLIT>(st, tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO,
+                                                tc::smem_u32(wres + woff), tmem);
+                        tc::mma_commit(bar_mma);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+                woff += (size_t)2 * st.Np * st.Kp * 4;
+                wait_bar(bar_mma, mma_phase);
+                mma_phase ^= 1;
+                tc::fence_after_sync();
+                if (warp < 4) {
+                    const int kp_next = s + 1 < p.nfh ? p.fh[s + 1].Kp : p.ff.Kp;
+                    plain_epilogue<NSPLIT>(st, tmem + ((uint32_t)(warp * 32) << 16), tid, xf_hi, xf_lo, LBO, kp_next);
+                }
+                tc::fence_async_smem();
+                tc::fence_before_sync();
+                __syncthreads();
+                tc::fence_after_sync();
             }
-            woff += (size_t)2 * st.Np * st.Kp * 4;
-            wait_bar(bar_mma, mma_phase);
-            mma_phase ^= 1;
-            tc::fence_after_sync();
-            if (warp < 4) {
-                const int kp_next = s + 1 < p.nfh ? p.fh[s + 1].Kp : p.ff.Kp;
-                plain_epilogue<NSPLIT>(st, tmem + ((uint32_t)(warp * 32) << 16), tid, xf_hi, xf_lo, LBO, kp_next);
-            }
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            __syncthreads();
-            tc::fence_after_sync();
         }
 
         // ---- transposed stages, one 128-channel chunk at a time ----
-        const int nchunk = pad_to(C, 128) / 128;
         for (int j = 0; j < nchunk; j++) {
             if (warp == 4) {
                 if (lane == 0) {
-                    if (p.has_ff) {
+                    if (FIRST) {
                         TcStage v = p.ff;
                         v.Np = 128;
                         v.w_off = p.ff.w_off + (long long)j * 2 * 128 * p.ff.Kp;
                         run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
                                                      tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO, 128, tm_f, 0);
                     }
-                    if (p.has_att) {
+                    if (has_att) {
                         TcStage v = p.a1;
                         v.Np = 128;
                         v.w_off = p.a1.w_off + (long long)j * 2 * 128 * p.a1.Kp;
@@ -667,39 +679,43 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                 }
                 __syncwarp();
             }
-            // ---- final epilogue: thread = channel (TMEM lane), 16 edge columns per batch ----
+            // ---- final epilogue: thread = channel (TMEM lane), 16 edge columns per batch.  Warps whose
+            //      32 channels all lie beyond C skip it entirely. ----
             const int ch = j * 128 + tid;
-            const bool chv = warp < 4 && ch < C;
-            // gathered feature of edge e for this channel: fbase[rowoff_s[e]] (invalid rows/channels are
+            const bool chv = ch < C;
+            const bool warp_on = warp < 4 && (j * 128 + warp * 32) < C;
+            // gathered feature of edge e for this channel: fbase[rowoff_s[e]] (invalid rows / channels are
             // clamped to a valid address; their values never reach the output)
-            const float *fbase = p.ftab + (chv ? ch : 0);
+            const float *fbase = FIRST ? nullptr : p.ftab + (chv ? ch : 0);
             float fg[16];
-            if (warp < 4 && !p.has_ff) {  // first batch of feature gathers issued under the MMAs
+            if (!FIRST && warp_on) {  // first batch of feature gathers issued under the MMAs
 #pragma unroll
                 for (int i = 0; i < 16; i++) fg[i] = __ldg(fbase + rowoff_s[i]);
             }
             wait_bar(bar_mma, mma_phase);
             mma_phase ^= 1;
             tc::fence_after_sync();
-            if (warp < 4) {
-                const float bf = (p.has_ff && chv) ? __ldg(p.ff.bias + ch) : 0.f;
-                const float ba = (p.has_att && chv) ? __ldg(p.a1.bias + ch) : 0.f;
+            if (warp_on) {
+                const float bf = (FIRST && chv) ? __ldg(p.ff.bias + ch) : 0.f;
+                const float ba = (has_att && chv) ? __ldg(p.a1.bias + ch) : 0.f;
                 const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+                const float pre_floor = c.pre_relu ? 0.f : -3.402823466e+38f;
+                float *out_ch = c.out + 4 + ch;
                 float m = -3.402823466e+38f;
                 int pos = 0, cl = 0;
                 for (int e0 = 0; e0 < kTileRows; e0 += 16) {
                     uint32_t gv[16], fv[16];
-                    if (p.has_att) tc::tmem_ld16(tm_g + lane_off + e0, gv);
-                    if (p.has_ff) tc::tmem_ld16(tm_f + lane_off + e0, fv);
+                    if (has_att) tc::tmem_ld16(tm_g + lane_off + e0, gv);
+                    if (FIRST) tc::tmem_ld16(tm_f + lane_off + e0, fv);
                     tc::tmem_ld_wait();
                     float pr[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        float f = p.has_ff ? fmaxf(__uint_as_float(fv[i]) + bf, 0.f) : fg[i];
-                        if (p.has_att) f *= fmaxf(__uint_as_float(gv[i]) + ba, 0.f);  // :167 att * feats
+                        float f = FIRST ? fmaxf(__uint_as_float(fv[i]) + bf, 0.f) : fg[i];
+                        if (has_att) f *= fmaxf(__uint_as_float(gv[i]) + ba, 0.f);  // :167 att * feats
                         pr[i] = f;
                     }
-                    if (!p.has_ff && e0 + 16 < kTileRows) {  // next batch of gathers in flight
+                    if (!FIRST && e0 + 16 < kTileRows) {  // next batch of gathers in flight
 #pragma unroll
                         for (int i = 0; i < 16; i++) fg[i] = __ldg(fbase + rowoff_s[e0 + 16 + i]);
                     }
@@ -711,10 +727,8 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                         pos += 16;
                         if (pos == K) {
                             const long long center = c_base + cl;
-                            if (chv && cl < cpt && center < centers_total) {
-                                const float y = c.pre_relu ? fmaxf(m, 0.f) : m;
-                                c.out[center * out_w + 4 + ch] = y * __ldg(c.centmsk + center);
-                            }
+                            if (chv && cl < cpt && center < centers_total)
+                                out_ch[center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
                             pos = 0;
                             cl++;
                             m = -3.402823466e+38f;
@@ -725,10 +739,8 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                             m = fmaxf(m, pr[i]);
                             if (++pos == K) {
                                 const long long center = c_base + cl;
-                                if (chv && cl < cpt && center < centers_total) {
-                                    const float y = c.pre_relu ? fmaxf(m, 0.f) : m;
-                                    c.out[center * out_w + 4 + ch] = y * __ldg(c.centmsk + center);
-                                }
+                                if (chv && cl < cpt && center < centers_total)
+                                    out_ch[center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
                                 pos = 0;
                                 cl++;
                                 m = -3.402823466e+38f;
@@ -838,8 +850,8 @@ static size_t kernel_b_base(const TcParams &p, int nsplit) {
     size_t nimg = nsplit == 3 ? 2 : 1;
     size_t bytes = nimg * (size_t)(kx / 4 + kh / 4) * kTileRows * 16;
     for (int s = 0; s < p.nfh; s++) bytes += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
-    if (p.has_att) bytes += (size_t)p.a0_cout * 13 * 4;
-    if (p.f0_cuda) bytes += (size_t)p.f0_cout * 4 * 4;
+    bytes += (size_t)kh * 12 * 4;                                   // wa0_s[kh][12]
+    if (p.f0_cuda) bytes += (size_t)pad_to(p.f0_cout, 8) * 4 * 4;     // wf0_s[kf0][4]
     return pad_to((int)bytes, 128);
 }
 
@@ -869,7 +881,10 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(point_mlp_tc_kernel<NSPLIT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(edge_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(edge_tc_kernel<NSPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kSmemCap);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(edge_tc_kernel<NSPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemCap);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
@@ -923,10 +938,13 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         if (tiles > 0x7fffffff) return GRIDGCN_ELIMIT;
         // co-resident CTAs hide the lock-step latencies: limited by shared memory, TMEM columns (512 per SM)
         // and threads
-        int per_sm = (int)min(min((size_t)3, kSmemCap / smem), (size_t)(512 / p.tmem_cols));  // 3: register limit (128 regs x 160 threads)
+        int per_sm = (int)min(min((size_t)(p.has_ff ? 2 : 3), kSmemCap / smem), (size_t)(512 / p.tmem_cols));  // 3: register limit (128 regs x 160 threads)
         per_sm = max(per_sm, 1);
         int blocks = (int)min(tiles, (long long)sms * per_sm);
-        edge_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
+        if (p.has_ff)
+            edge_tc_kernel<NSPLIT, true><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
+        else
+            edge_tc_kernel<NSPLIT, false><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
         return (int)cudaGetLastError();
     }
 }
