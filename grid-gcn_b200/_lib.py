@@ -41,6 +41,7 @@ SIGNATURES = {
     "gridgcn_knn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "gridgcn_ball_knn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "gridgcn_debug_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "gridgcn_debug_phase_buffer": (None, [_vp]),
     "gridgcn_gridconv_packed_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i]),
     "gridgcn_gridconv_pack": (_i, [ctypes.POINTER(MlpDesc), _i, _vp, _sz, _vp]),
     "gridgcn_gridconv_workspace_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i, _i, _i]),

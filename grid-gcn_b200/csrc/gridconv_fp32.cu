@@ -224,6 +224,7 @@ gridconv_fp32_kernel(ConvParams p, int num_tiles) {
 int launch_gridconv_tc(const ConvParams &p, int precision, const float *packed, float *ftab, cudaStream_t st);
 int tc_packed_floats(const ConvParams &c);
 int tc_pack(const ConvParams &c, float *packed, cudaStream_t st);
+void tc_set_phase_buffer(unsigned long long *buf);
 
 static int launch_gridconv_fp32(const ConvParams &p, cudaStream_t st) {
     ConvSmemLayout s = conv_smem_layout(p);
@@ -344,3 +345,8 @@ extern "C" int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const
     }
     return GRIDGCN_EINVAL;
 }
+
+// Debug: 8 x u64 device buffer that CTA 0 of the per-edge tensor-core kernel fills with the cycles it
+// spent in each phase (gather, sync, hidden MMA, hidden epilogue, sync, final MMA, final epilogue,
+// sync).  Pass NULL to switch the accounting off.  Not re-entrant; not part of the operator ABI.
+extern "C" void gridgcn_debug_phase_buffer(unsigned long long *dev_buf) { tc_set_phase_buffer(dev_buf); }

@@ -66,6 +66,7 @@ struct TcParams {
     TcStage a1;
     int ring_slots, ring_sticky;   // weight ring: number of slots; sticky = whole per-tile sequence resident
     int tmem_cols;
+    unsigned long long *dbg;       // optional phase-cycle counters (debug, see gridgcn_debug_phase_buffer)
 };
 
 __host__ __device__ inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
@@ -237,31 +238,33 @@ __device__ __forceinline__ void run_plain_stage(const TcStage &st, uint32_t x_hi
 }
 
 // TMEM epilogue of a plain stage, thread = row: x = relu(D + bias) -> hi/lo images [128 x Kp_next].
+// `bias_s`: the stage's bias in shared memory, zero padded to 128 (global bias loads on this path cost an
+// L2 round trip per batch when L1 is thrashed by the gathers).  Columns >= Cout come out as relu(0+0)=0
+// because the padded weight rows are zero.
 template <int NSPLIT>
-__device__ __forceinline__ void plain_epilogue(const TcStage &st, uint32_t tmem_lane_addr, int row,
+__device__ __forceinline__ void plain_epilogue(const TcStage &st, uint32_t tmem_lane_addr, uint32_t row_off,
                                                uint8_t *img_hi, uint8_t *img_lo, uint32_t lbo,
-                                               int kp_next) {
+                                               int kp_next, const float *bias_s) {
+    (void)st;
     for (int c0 = 0; c0 < kp_next; c0 += 16) {
         uint32_t v[16];
-        if (c0 < st.Np) {
-            tc::tmem_ld16(tmem_lane_addr + c0, v);
-            tc::tmem_ld_wait();
-        }
+        tc::tmem_ld16(tmem_lane_addr + c0, v);
+        tc::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int c = c0 + q * 4;
-            if (c >= kp_next) break;
-            float hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                float x = 0.f;
-                if (c + i < st.Cout) x = fmaxf(__uint_as_float(v[q * 4 + i]) + __ldg(st.bias + c + i), 0.f);
-                tc::split_tf32(x, hi[i], lo[i]);
+            if (c < kp_next) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c);
+                float hi[4], lo[4];
+                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 0]) + b4.x, 0.f), hi[0], lo[0]);
+                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 1]) + b4.y, 0.f), hi[1], lo[1]);
+                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 2]) + b4.z, 0.f), hi[2], lo[2]);
+                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 3]) + b4.w, 0.f), hi[3], lo[3]);
+                const uint32_t off = row_off + (uint32_t)(c >> 2) * lbo;
+                *reinterpret_cast<float4 *>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (NSPLIT == 3)
+                    *reinterpret_cast<float4 *>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
-            const uint32_t off = tc::kmajor_off(row, c, lbo);
-            *reinterpret_cast<float4 *>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            if (NSPLIT == 3)
-                *reinterpret_cast<float4 *>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
 }
@@ -457,7 +460,11 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     float *wa0_s = reinterpret_cast<float *>(wres + wres_bytes);
     const int kf0 = (FIRST && p.f0_cuda) ? pad_to(p.f0_cout, 8) : 0;
     float *wf0_s = wa0_s + kh * 12;
-    float *small_end = wf0_s + kf0 * 4;
+    // biases: hidden feature stages (128 floats each, zero padded), then ff and a1 (Cp floats each)
+    const int Cp = pad_to(C, 128);
+    float *bias_s = wf0_s + kf0 * 4;
+    float *bias_ff_s = bias_s + p.nfh * 128, *bias_a1_s = bias_ff_s + Cp;
+    float *small_end = bias_a1_s + Cp;
     Ring ring;
     ring.slots = smem + pad_to((int)(reinterpret_cast<uint8_t *>(small_end) - smem), 128);
     ring.nslots = p.ring_slots;
@@ -521,6 +528,14 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             const int j = i / 4, q = i % 4;
             wf0_s[i] = j < p.f0_cout ? (q < 3 ? __ldg(p.f0_w + (size_t)j * 3 + q) : __ldg(p.f0_b + j)) : 0.f;
         }
+        for (int i = tid; i < p.nfh * 128; i += kTcThreads) {
+            const int st = i >> 7, j = i & 127;
+            bias_s[i] = j < p.fh[st].Cout ? __ldg(p.fh[st].bias + j) : 0.f;
+        }
+        for (int i = tid; i < Cp; i += kTcThreads) {
+            bias_ff_s[i] = (FIRST && i < C) ? __ldg(p.ff.bias + i) : 0.f;
+            bias_a1_s[i] = (has_att && i < C) ? __ldg(p.a1.bias + i) : 0.f;
+        }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -544,33 +559,63 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;  // this edge's row in an image
     const int nchunk = pad_to(C, 128) / 128;
 
+    // optional per-phase cycle accounting of CTA 0 / thread 0 (debug)
+    long long tph = 0;
+    unsigned long long acc_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define GG_PHASE(i)                                   \
+    if (timing) {                                     \
+        const long long now_ = clock64();             \
+        acc_ph[i] += (unsigned long long)(now_ - tph); \
+        tph = now_;                                   \
+    }
+    // per-edge prefetch state (thread = edge row of the tile): the neighbour index of the NEXT tile is
+    // requested during this tile's gather phase, its table row and centre under this tile's MMAs.
+    const int my_cl = tid / K, my_slot = tid - my_cl * K;
+    bool pf_valid = false;
+    int pf_idx = 0;
+    long long pf_center = 0;
+    uint32_t pf_roff = 0;
+    float4 pf_head = make_float4(0.f, 0.f, 0.f, 0.f), pf_cent = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_row = [&]() {  // table row + centre of the edge whose index is in pf_idx
+        pf_roff = 0;
+        if (pf_valid) {
+            const int b = (int)(pf_center / O);
+            const long long row = take_row(pf_idx, b, Nprev, rows_total);
+            pf_roff = (uint32_t)row * (uint32_t)C;
+            const float *src = c.table + row * row_w;
+            if ((row_w & 3) == 0) {
+                pf_head = __ldg(reinterpret_cast<const float4 *>(src));
+            } else {
+                pf_head = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
+            }
+            pf_cent = __ldg(c.cent + pf_center);
+        }
+    };
+    if (warp < 4 && blockIdx.x < num_tiles) {
+        const long long center = (long long)blockIdx.x * cpt + my_cl;
+        pf_valid = my_cl < cpt && center < centers_total;
+        pf_center = center;
+        if (pf_valid) pf_idx = __ldg(c.nebidx + center * K + my_slot);
+        fetch_row();
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long c_base = (long long)tile * cpt;
+        if (timing) tph = clock64();
         // ---- gather + geometry + tiny-K stages on the CUDA cores: thread = edge row ----
         if (warp < 4) {
-            const int cl = tid / K, slot = tid - cl * K;
-            const long long center = c_base + cl;
-            const bool valid = cl < cpt && center < centers_total;
             float att[12];
 #pragma unroll
             for (int i = 0; i < 12; i++) att[i] = 0.f;
             att[10] = 1.f;  // multiplies the bias column of wa0_s
             float dx = 0.f, dy = 0.f, dz = 0.f;
-            uint32_t roff = 0;
-            if (valid) {
-                const int b = (int)(center / O);
-                const int idx = __ldg(c.nebidx + center * K + slot);
-                const long long row = take_row(idx, b, Nprev, rows_total);
-                roff = (uint32_t)row * (uint32_t)C;
-                const float *src = c.table + row * row_w;
-                float nx, ny, nz;
-                if ((row_w & 3) == 0) {
-                    const float4 h = __ldg(reinterpret_cast<const float4 *>(src));
-                    nx = h.x; ny = h.y; nz = h.z;
-                } else {
-                    nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
-                }
-                att_vector(attfdim, __ldg(c.cent + center), nx, ny, nz, att, dx, dy, dz);
+            const uint32_t roff = pf_roff;
+            if (pf_valid) att_vector(attfdim, pf_cent, pf_head.x, pf_head.y, pf_head.z, att, dx, dy, dz);
+            {   // request the next tile's neighbour index now; its row / centre are requested later
+                const long long ncenter = (long long)(tile + gridDim.x) * cpt + my_cl;
+                pf_valid = (tile + (int)gridDim.x) < num_tiles && my_cl < cpt && ncenter < centers_total;
+                pf_center = ncenter;
+                if (pf_valid) pf_idx = __ldg(c.nebidx + ncenter * K + my_slot);
             }
             if (!FIRST) rowoff_s[tid] = roff;
             // attention stage 0: h = relu(W a + b), K <= 10, exact fp32 (bias folded in as w[10] * 1)
@@ -624,10 +669,12 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                 }
             }
         }
+        GG_PHASE(0)  // gather + CUDA-core stages
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
+        GG_PHASE(1)  // sync after gather
 
         // ---- first layer: remaining hidden feature stages on the tensor core, D[edge, ch] ----
         if (FIRST) {
@@ -646,14 +693,18 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                 wait_bar(bar_mma, mma_phase);
                 mma_phase ^= 1;
                 tc::fence_after_sync();
+                GG_PHASE(2)  // hidden-stage MMA issue -> retired
                 if (warp < 4) {
                     const int kp_next = s + 1 < p.nfh ? p.fh[s + 1].Kp : p.ff.Kp;
-                    plain_epilogue<NSPLIT>(st, tmem + ((uint32_t)(warp * 32) << 16), tid, xf_hi, xf_lo, LBO, kp_next);
+                    plain_epilogue<NSPLIT>(st, tmem + ((uint32_t)(warp * 32) << 16), row_off, xf_hi, xf_lo, LBO, kp_next,
+                                           bias_s + s * 128);
                 }
+                GG_PHASE(3)  // hidden-stage epilogue
                 tc::fence_async_smem();
                 tc::fence_before_sync();
                 __syncthreads();
                 tc::fence_after_sync();
+                GG_PHASE(4)  // sync after hidden stage
             }
         }
 
@@ -679,45 +730,45 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                 }
                 __syncwarp();
             }
-            // ---- final epilogue: thread = channel (TMEM lane), 16 edge columns per batch.  Warps whose
-            //      32 channels all lie beyond C skip it entirely. ----
+            // ---- final epilogue: thread = channel (TMEM lane), 16 edge columns per batch, the TMEM loads (and
+            //      feature gathers) of batch k+1 in flight while batch k is reduced.  Warps whose 32 channels
+            //      all lie beyond C skip it entirely. ----
             const int ch = j * 128 + tid;
             const bool chv = ch < C;
             const bool warp_on = warp < 4 && (j * 128 + warp * 32) < C;
             // gathered feature of edge e for this channel: fbase[rowoff_s[e]] (invalid rows / channels are
             // clamped to a valid address; their values never reach the output)
             const float *fbase = FIRST ? nullptr : p.ftab + (chv ? ch : 0);
-            float fg[16];
-            if (!FIRST && warp_on) {  // first batch of feature gathers issued under the MMAs
+            uint32_t gA[16], fA[16], gB[16], fB[16];  // f*: TMEM bits (first layer) or gathered floats
+            auto gather16 = [&](uint32_t (&f)[16], int e0) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) fg[i] = __ldg(fbase + rowoff_s[i]);
-            }
+                for (int i = 0; i < 16; i++) f[i] = __float_as_uint(__ldg(fbase + rowoff_s[e0 + i]));
+            };
+            if (!FIRST && warp_on) gather16(fA, 0);  // first batch of feature gathers issued under the MMAs
+            if (j == 0 && warp < 4) fetch_row();      // next tile's table row + centre, also under the MMAs
             wait_bar(bar_mma, mma_phase);
             mma_phase ^= 1;
             tc::fence_after_sync();
+            GG_PHASE(5)  // transposed-stage MMAs -> retired
             if (warp_on) {
-                const float bf = (FIRST && chv) ? __ldg(p.ff.bias + ch) : 0.f;
-                const float ba = (has_att && chv) ? __ldg(p.a1.bias + ch) : 0.f;
+                const float bf = FIRST ? bias_ff_s[chv ? ch : 0] : 0.f;
+                const float ba = has_att ? bias_a1_s[chv ? ch : 0] : 0.f;
                 const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
                 const float pre_floor = c.pre_relu ? 0.f : -3.402823466e+38f;
                 float *out_ch = c.out + 4 + ch;
                 float m = -3.402823466e+38f;
                 int pos = 0, cl = 0;
-                for (int e0 = 0; e0 < kTileRows; e0 += 16) {
-                    uint32_t gv[16], fv[16];
-                    if (has_att) tc::tmem_ld16(tm_g + lane_off + e0, gv);
-                    if (FIRST) tc::tmem_ld16(tm_f + lane_off + e0, fv);
-                    tc::tmem_ld_wait();
+                auto issue = [&](uint32_t (&g)[16], uint32_t (&f)[16], int e0) {
+                    if (has_att) tc::tmem_ld16(tm_g + lane_off + e0, g);
+                    if (FIRST) tc::tmem_ld16(tm_f + lane_off + e0, f);
+                };
+                auto reduce16 = [&](const uint32_t (&g)[16], const uint32_t (&f)[16]) {
                     float pr[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        float f = FIRST ? fmaxf(__uint_as_float(fv[i]) + bf, 0.f) : fg[i];
-                        if (has_att) f *= fmaxf(__uint_as_float(gv[i]) + ba, 0.f);  // :167 att * feats
-                        pr[i] = f;
-                    }
-                    if (!FIRST && e0 + 16 < kTileRows) {  // next batch of gathers in flight
-#pragma unroll
-                        for (int i = 0; i < 16; i++) fg[i] = __ldg(fbase + rowoff_s[e0 + 16 + i]);
+                        float x = FIRST ? fmaxf(__uint_as_float(f[i]) + bf, 0.f) : __uint_as_float(f[i]);
+                        if (has_att) x *= fmaxf(__uint_as_float(g[i]) + ba, 0.f);  // :167 att * feats
+                        pr[i] = x;
                     }
                     if ((K & 15) == 0) {  // the 16 columns belong to one centre
                         float mm = pr[0];
@@ -747,11 +798,28 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                             }
                         }
                     }
+                };
+                issue(gA, fA, 0);
+                tc::tmem_ld_wait();
+#pragma unroll 1
+                for (int e0 = 0; e0 < kTileRows; e0 += 32) {
+                    issue(gB, fB, e0 + 16);
+                    if (!FIRST) gather16(fB, e0 + 16);
+                    reduce16(gA, fA);
+                    tc::tmem_ld_wait();
+                    if (e0 + 32 < kTileRows) {
+                        issue(gA, fA, e0 + 32);
+                        if (!FIRST) gather16(fA, e0 + 32);
+                    }
+                    reduce16(gB, fB);
+                    tc::tmem_ld_wait();
                 }
             }
+            GG_PHASE(6)  // final epilogue
             tc::fence_before_sync();
             __syncthreads();
             tc::fence_after_sync();
+            GG_PHASE(7)  // sync after final epilogue
         }
         // centre columns of the output rows
         if (warp < 4) {
@@ -763,6 +831,9 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             }
         }
     }
+    if (timing)
+        for (int i = 0; i < 8; i++) p.dbg[i] = acc_ph[i];
+#undef GG_PHASE
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
@@ -852,6 +923,7 @@ static size_t kernel_b_base(const TcParams &p, int nsplit) {
     for (int s = 0; s < p.nfh; s++) bytes += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
     bytes += (size_t)kh * 12 * 4;                                   // wa0_s[kh][12]
     if (p.f0_cuda) bytes += (size_t)pad_to(p.f0_cout, 8) * 4 * 4;     // wf0_s[kf0][4]
+    bytes += (size_t)(p.nfh * 128 + 2 * pad_to(p.c.Cout, 128)) * 4;    // biases
     return pad_to((int)bytes, 128);
 }
 
@@ -892,13 +964,19 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
     if (p.na > 0) {  // kernel A
         int chunks = 0;
         for (int s = 0; s < p.na; s++) chunks = max(chunks, p.a[s].Np / 128);
-        int TR = chunks * 128 > 256 ? 64 : 128, slots = 3;  // TMEM: chunks * TR columns <= 256
-        while (kernel_a_smem(p, TR, NSPLIT, slots) > kSmemCap) {
-            if (slots > 2) slots--;
-            else if (TR == 128) { TR = 64; slots = 3; }
-            else return GRIDGCN_ELIMIT;
+        // Rows per tile: the largest of 128/64/32 that fits chunks*TR <= 256 TMEM columns and leaves at
+        // least 2 ring slots (up to 6 when there is room).  Fewer, larger tiles win: every tile re-streams
+        // the layer's weights from L2 and that stream -- ~2-2.5 TB/s in aggregate when all SMs read the same
+        // slices -- is the bound for the wide layers (measured, r01).
+        int TR = 0, slots = 0;
+        for (int cand = 128; cand >= 32; cand >>= 1) {
+            if (chunks * cand > 256) continue;
+            size_t fixed = kernel_a_smem(p, cand, NSPLIT, 0);
+            if (fixed > kSmemCap) continue;
+            int fit = (int)min((size_t)6, (kSmemCap - fixed) / kSlotBytes);
+            if (fit >= 2) { TR = cand; slots = fit; break; }
         }
-        if (chunks * TR > 256) return GRIDGCN_ELIMIT;
+        if (TR == 0) return GRIDGCN_ELIMIT;
         p.a_rows = TR;
         p.ring_slots = slots;
         p.ring_sticky = 0;
@@ -925,11 +1003,9 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
             smem = base + seq_bytes + 1024;
         } else {
             p.ring_sticky = 0;
-            p.ring_slots = 3;
-            while (base + (size_t)p.ring_slots * kSlotBytes + 1024 > kSmemCap) {
-                if (p.ring_slots > 2) p.ring_slots--;
-                else return GRIDGCN_ELIMIT;
-            }
+            if (base + 1024 > kSmemCap) return GRIDGCN_ELIMIT;
+            p.ring_slots = (int)min((size_t)4, (kSmemCap - base - 1024) / kSlotBytes);
+            if (p.ring_slots < 2) return GRIDGCN_ELIMIT;
             smem = base + (size_t)p.ring_slots * kSlotBytes + 1024;
         }
         const int cpt = kTileRows / c.K;
@@ -967,6 +1043,9 @@ int tc_pack(const ConvParams &c, float *packed, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+static unsigned long long *g_phase_buf = nullptr;
+void tc_set_phase_buffer(unsigned long long *buf) { g_phase_buf = buf; }
+
 int launch_gridconv_tc(const ConvParams &c, int precision, const float *packed, float *ftab,
                        cudaStream_t st) {
     TcParams p{};
@@ -974,6 +1053,7 @@ int launch_gridconv_tc(const ConvParams &c, int precision, const float *packed, 
     if (!packed || (c.Cin > 0 && !ftab)) return GRIDGCN_EWORKSPACE;
     p.packed = packed;
     p.ftab = ftab;
+    p.dbg = g_phase_buf;
     p.nsplit = precision == GRIDGCN_PRECISION_TF32X3 ? 3 : 1;
     return p.nsplit == 3 ? launch_tc_t<3>(p, st) : launch_tc_t<1>(p, st);
 }

@@ -159,6 +159,9 @@ int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cen
 int gridgcn_debug_tc_gemm(const float *A, const float *B, float *D, int N, int K, int nsplit,
                           void *stream);
 
+/* Debug: see csrc/gridconv_fp32.cu.  8 x u64 device buffer of per-phase cycles, NULL = off. */
+void gridgcn_debug_phase_buffer(unsigned long long *dev_buf);
+
 #ifdef __cplusplus
 }
 #endif
