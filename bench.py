@@ -128,7 +128,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=96, help="clouds per GPU per step")
+    ap.add_argument("--batch", type=int, default=192, help="clouds per GPU per step")
     ap.add_argument("--K", type=int, default=64)
     ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify"])
     ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "tf32x3"),

@@ -99,6 +99,12 @@ static int gridify_impl(bool knn, const float *data, const int *npts, int B, int
     const float4 *d4 = reinterpret_cast<const float4 *>(data);
     float4 *c4 = reinterpret_cast<float4 *>(cent);
     const int *w = static_cast<const int *>(ws);
+    if (knn) {  // the sort key packs [voxel arrival order | point id] into 32 bits (grid_query.cuh)
+        int combos = 0, vbits = 1;
+        for (int l = 0; l < (ks + 1) / 2; l++) combos += (2 * l + 1) * (2 * l + 1) * (2 * l + 1);
+        while ((1 << vbits) < combos) vbits++;
+        if (N >= (1LL << (32 - vbits))) return GRIDGCN_ELIMIT;
+    }
     if (!knn) {
         gridify_query_kernel<<<blocks, kQueryWarps * 32, 0, st>>>(d4, g, w, L, centnum, nebidx,
                                                                    nebmsk, c4);

@@ -142,16 +142,21 @@ gridify_query_kernel(const float4 *__restrict__ data, GridParams g, const int *_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-level top-P collector: a (key, id) buffer of CAP entries per warp in shared memory; the
-// first `fill` entries are live.  flush() bitonic-sorts them ascending by key and keeps the first P.
-// Keys are unique (they embed the arrival sequence number or the id), so the result is the stable
-// order the reference's strict-< insertion produces (gridifyknn.cu:288-298).
+// Warp-level top-P collector: a buffer of CAP 64-bit keys per warp in shared memory; the first `fill`
+// entries are live.  flush() bitonic-sorts them ascending and keeps the first P.  A key is
+//     [ sort value : 32 | arrival order of the voxel : vbits | point id : 32 - vbits ]
+// so it is unique and self-contained (the id is read back from its low bits: one 8-byte exchange per
+// compare instead of key + payload).  Inside a voxel ids ascend in arrival order, so
+// (value, voxel order, id) orders exactly like (value, arrival sequence number): the stable order the
+// reference's strict-< insertion produces (gridifyknn.cu:288-298).
 // ------------------------------------------------------------------------------------------------
 template <int CAP>
 struct TopP {
     unsigned long long *keys;
-    int *ids;
     int fill;
+    unsigned idmask;  // (1 << idbits) - 1
+
+    __device__ __forceinline__ int id_of(int i) const { return (int)((unsigned)keys[i] & idmask); }
 
     __device__ __forceinline__ void sort(int lane) {
         int n = 2;
@@ -161,16 +166,13 @@ struct TopP {
         for (int k = 2; k <= n; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int p = lane; p < (n >> 1); p += 32) {
-                    int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                    int q = i | j;
-                    unsigned long long a = keys[i], c = keys[q];
-                    bool up = (i & k) == 0;
+                    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                    const int q = i | j;
+                    const unsigned long long a = keys[i], c = keys[q];
+                    const bool up = (i & k) == 0;
                     if ((a > c) == up) {
                         keys[i] = c;
                         keys[q] = a;
-                        int ia = ids[i];
-                        ids[i] = ids[q];
-                        ids[q] = ia;
                     }
                 }
                 __syncwarp();
@@ -183,11 +185,11 @@ struct TopP {
     }
 };
 
-// Append the candidates of up to 32 voxels (one per lane: segment start `s`, `amount` ids) in lane
-// order.  `make_key(id, seq)` builds the sort key; seq numbers continue from `seq0`.
+// Append the candidates of up to 32 voxels (one per lane: segment start `s`, `amount` ids, arrival order
+// `vorder` of the voxel) in lane order.  `make_key(id, vorder)` builds the 64-bit key.
 template <int CAP, class KeyFn>
 __device__ __forceinline__ void append_batch(TopP<CAP> &tp, const int *sorted, int s, int amount,
-                                             int P, int lane, int &seq0, KeyFn make_key) {
+                                             int P, int lane, int vorder, int &seen, KeyFn make_key) {
     int incl = warp_incl_scan(amount, lane);
     int pfx = incl - amount;
     const int batch_total = __shfl_sync(kFull, incl, 31);
@@ -202,25 +204,17 @@ __device__ __forceinline__ void append_batch(TopP<CAP> &tp, const int *sorted, i
         }
         if (can) {
             int at = tp.fill + pfx - base;
-            for (int j = 0; j < amount; j++) {
-                int id = sorted[s + j];
-                tp.keys[at + j] = make_key(id, seq0 + pfx + j);
-                tp.ids[at + j] = id;
-            }
+            for (int j = 0; j < amount; j++) tp.keys[at + j] = make_key(sorted[s + j], vorder);
             done = true;
         }
-        int appended = 0;
-        {
-            int mine = can ? amount : 0;
+        int mine = can ? amount : 0;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(kFull, mine, d);
-            appended = mine;
-        }
-        tp.fill += appended;
-        base += appended;
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(kFull, mine, d);
+        tp.fill += mine;
+        base += mine;
         __syncwarp();
     }
-    seq0 += batch_total;
+    seen += batch_total;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -229,15 +223,20 @@ __device__ __forceinline__ void append_batch(TopP<CAP> &tp, const int *sorted, i
 // centre in the shifted frame, stop after the first shell with cumulative candidates >= P.
 // ------------------------------------------------------------------------------------------------
 template <int CAP>
-__global__ void __launch_bounds__(kQueryWarps * 32)
+__global__ void __launch_bounds__(kQueryWarps * 32, 3)
 gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
                          const int *__restrict__ ws_base, WsLayout L,
                          const int *__restrict__ centnum, int *__restrict__ nebidx,
                          float *__restrict__ nebmsk, float4 *__restrict__ cent) {
     __shared__ unsigned long long s_keys[kQueryWarps][CAP];
-    __shared__ int s_ids[kQueryWarps][CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = g.P, O = g.O, ks = g.ks;
+    // key layout: the voxel arrival order needs vbits, the rest of the low word holds the point id
+    int total_combos = 0;
+    for (int l = 0; l < (ks + 1) / 2; l++) total_combos += (2 * l + 1) * (2 * l + 1) * (2 * l + 1);
+    int vbits = 1;
+    while ((1 << vbits) < total_combos) vbits++;
+    const int idbits = 32 - vbits;
     const int fma = (g.flags & GRIDGCN_FLAG_DIST_FMA) ? 1 : 0;
     const long long total_centers = (long long)g.B * O;
     for (long long ci = (long long)blockIdx.x * kQueryWarps + warp; ci < total_centers;
@@ -261,12 +260,12 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
         const float ux = (float)(((double)c0 + 0.5) * (double)g.voxel[0]);
         const float uy = (float)(((double)c1 + 0.5) * (double)g.voxel[1]);
         const float uz = (float)(((double)c2 + 0.5) * (double)g.voxel[2]);
-        TopP<CAP> tp{s_keys[warp], s_ids[warp], 0};
-        int seq = 0;
-        auto key_of = [&](int id, int sq) {
+        TopP<CAP> tp{s_keys[warp], 0, (1u << idbits) - 1u};
+        int seq = 0, vbase = 0;
+        auto key_of = [&](int id, int vorder) {
             float4 q = __ldg(pts + id);
             float dst = dist2(ux, uy, uz, q.x, q.y, q.z, fma);
-            return ((unsigned long long)__float_as_uint(dst) << 32) | (unsigned)sq;
+            return ((unsigned long long)__float_as_uint(dst) << 32) | ((unsigned)vorder << idbits) | (unsigned)id;
         };
         for (int layer = 0; layer < (ks + 1) / 2; layer++) {
             const int n1 = 2 * layer + 1, combos = n1 * n1 * n1;
@@ -278,9 +277,9 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
                         voxel_segment(t, g, d + c2, h + c1, w + c0, s, e);
                 }
                 int amount = min(P, e - s);
-                append_batch<CAP>(tp, t.sorted, s, amount, P, lane, seq, key_of);
-                // seq advanced by the batch total inside append_batch
+                append_batch<CAP>(tp, t.sorted, s, amount, P, lane, vbase + tt, seq, key_of);
             }
+            vbase += combos;
             // gridifyknn.cu:304-305: need_P -= amount_layer; stop once the cumulative number of
             // candidates (== seq) reaches P
             if (seq >= P) break;
@@ -288,12 +287,24 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
         tp.flush(P, lane);
         __syncwarp();
         const int found = tp.fill;  // >= 1: the centre voxel is never empty
-        const int pad = tp.ids[0];
-        for (int s = lane; s < P; s += 32) {
-            out_idx[s] = s < found ? tp.ids[s] : pad;  // :308-310, :317-321
-            out_msk[s] = 1.f;                          // :312 mask 1 on every slot
+        // unpack the ids in place (low word of every key) so that weight_sum can index them
+        int *ids = reinterpret_cast<int *>(tp.keys);
+        {
+            int v0 = lane < found ? tp.id_of(lane) : 0, v1 = lane + 32 < found ? tp.id_of(lane + 32) : 0;
+            int v2 = lane + 64 < found ? tp.id_of(lane + 64) : 0, v3 = lane + 96 < found ? tp.id_of(lane + 96) : 0;
+            __syncwarp();
+            if (lane < found) ids[lane] = v0;
+            if (lane + 32 < found) ids[lane + 32] = v1;
+            if (lane + 64 < found) ids[lane + 64] = v2;
+            if (lane + 96 < found) ids[lane + 96] = v3;
+            __syncwarp();
         }
-        float wsum = weight_sum(pts, tp.ids, found, lane);
+        const int pad = ids[0];
+        for (int s = lane; s < P; s += 32) {
+            out_idx[s] = s < found ? ids[s] : pad;  // :308-310, :317-321
+            out_msk[s] = 1.f;                       // :312 mask 1 on every slot
+        }
+        float wsum = weight_sum(pts, ids, found, lane);
         if (lane == 0) cent[ci] = center_row(t, o, g.loc, wsum);
         __syncwarp();
     }
@@ -312,7 +323,6 @@ gridify_up_query_kernel(const float4 *__restrict__ updata, const int *__restrict
                         GridParams g, const int *__restrict__ ws_base, WsLayout L,
                         int *__restrict__ nebidx, float *__restrict__ nebmsk) {
     __shared__ unsigned long long s_keys[kQueryWarps][CAP];
-    __shared__ int s_ids[kQueryWarps][CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = g.P, O = g.O, ks = g.ks, S = ks * ks * ks, r = (ks - 1) / 2;
     const long long total_rows = (long long)g.B * O;
@@ -327,7 +337,7 @@ gridify_up_query_kernel(const float4 *__restrict__ updata, const int *__restrict
             lin = voxel_of(p.x, p.y, p.z, g);
         }
         long long count = 0;
-        TopP<CAP> tp{s_keys[warp], s_ids[warp], 0};
+        TopP<CAP> tp{s_keys[warp], 0, 0xffffffffu};  // key = id
         if (lin >= 0) {
             const CloudTable t = cloud_table(ws_base, L, b);
             int c2, c1, c0;
@@ -344,15 +354,15 @@ gridify_up_query_kernel(const float4 *__restrict__ updata, const int *__restrict
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) lsum += __shfl_xor_sync(kFull, lsum, d);
                 count += lsum;
-                append_batch<CAP>(tp, t.sorted, s, min(P, len), P, lane, seq, key_of);
+                append_batch<CAP>(tp, t.sorted, s, min(P, len), P, lane, 0, seq, key_of);
             }
             tp.flush(P, lane);
             __syncwarp();
         }
         const int n = (int)min((long long)P, count);  // gridify_up.cu:212 j < countlimit
-        const int pad = n > 0 ? tp.ids[0] : 0;        // empty bucket: oracle definition, ids 0
+        const int pad = n > 0 ? tp.id_of(0) : 0;      // empty bucket: oracle definition, ids 0
         for (int s = lane; s < P; s += 32) {
-            out_idx[s] = s < n ? tp.ids[s] : pad;
+            out_idx[s] = s < n ? tp.id_of(s) : pad;
             out_msk[s] = s < n ? 1.f : 0.f;
         }
         __syncwarp();

@@ -269,8 +269,13 @@ def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod, precision):
     bit-exact at every layer, features within 1e-3."""
     from oracle import gridconv_oracle
     from gridgcn_b200 import stack
-    for cfg, B in ((stack.tiny(8), 3), (stack.cls1024_4layer(32), 2), (stack.seg8192_4layer(16), 1),
-                   (stack.seg8192_shipped(), 1)):
+    cases = [(stack.tiny(8), 3), (stack.cls1024_4layer(32), 2), (stack.seg8192_4layer(16), 1),
+             (stack.seg8192_shipped(), 1)]
+    if precision == "tf32x3":  # the product precision also covers the headline shape, the K sweep of
+        cases += [(stack.seg8192_4layer(64), 1),             # BASELINE config 5 and the config-4 shape
+                  (stack.seg8192_4layer(32, "gridify"), 1), (stack.seg8192_4layer(128), 1),
+                  (stack.seg81920_shipped(), 1)]
+    for cfg, B in cases:
         params = stack.init_params(cfg, seed=1)
         data, npts = synth.make_batch(B, cfg.num_points, seed0=200, voxels=cfg.voxels)
         enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision=precision)
