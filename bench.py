@@ -91,8 +91,9 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts):
-    """The reference algorithm's CPU port over a batch: oracle query + numpy GridConv per layer."""
+def cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts, pool=None):
+    """The reference algorithm's CPU port over a batch: oracle query (C, OpenMP over clouds) + numpy
+    GridConv per layer (one cloud per worker thread; numpy releases the GIL)."""
     q = oracle.gridify_knn if cfg.query == "gridifyknn" else oracle.gridify
     table, loc, num = data, data, npts
     for l, p in zip(cfg.layers, params):
@@ -100,26 +101,46 @@ def cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts):
                                           kernel_size=l.kernel_size, loc=cfg.loc,
                                           coord_shift=cfg.coord_shift, voxel_size=(l.voxel_size,) * 3,
                                           grid_size=(l.grid_size,) * 3)
-        table = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, p, pre_relu=cfg.pre_relu)
+        if pool is None:
+            table = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, p, pre_relu=cfg.pre_relu)
+        else:
+            def one(b, table=table, nebidx=nebidx, cent=cent, centmsk=centmsk, p=p):
+                return gridconv_oracle.gridconv_layer(table[b:b + 1], nebidx[b:b + 1], cent[b:b + 1],
+                                                      centmsk[b:b + 1], p, pre_relu=cfg.pre_relu)
+            table = np.concatenate(list(pool.map(one, range(len(data)))), axis=0)
         loc = cent
     return table
 
 
 def time_cpu(cfg, params, clouds, steps, warmup):
-    """Times the CPU port on `clouds` clouds per step with every host thread it can use."""
+    """Times the CPU port on `clouds` clouds per step with every host thread it can use: OpenMP over
+    clouds in the C oracle, a thread per cloud (BLAS pinned to 1 thread each) for the numpy GridConv."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle, gridconv_oracle
     from gridgcn_b200 import synth
     oracle.build()
     cores = os.cpu_count() or 1
-    oracle.set_threads(min(cores, oracle.max_threads(), max(clouds, 1)))
-    data, npts = synth.make_batch(clouds, cfg.num_points, seed0=0, voxels=cfg.voxels)
-    for _ in range(warmup):
-        cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return clouds * cfg.num_points / dt, dt, cores
+    workers = max(1, min(cores, clouds))
+    oracle.set_threads(min(oracle.max_threads(), workers))
+    data, npts = synth.make_batch(min(clouds, 8), cfg.num_points, seed0=0, voxels=cfg.voxels)
+    reps = (clouds + len(data) - 1) // len(data)
+    data = np.tile(data, (reps, 1, 1))[:clouds].copy()
+    npts = np.full((clouds, 1), cfg.num_points, np.int32)
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        for _ in range(warmup):
+            cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts, pool)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts, pool)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    if limiter is not None:
+        limiter.unregister() if hasattr(limiter, "unregister") else None
+    return clouds * cfg.num_points / dt, dt, workers
 
 
 def main():
@@ -133,8 +154,11 @@ def main():
     ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify"])
     ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "tf32x3"),
                     choices=["tf32x3", "tf32", "fp32"])
-    ap.add_argument("--cpu-clouds", type=int, default=4, help="clouds per CPU-baseline step")
+    ap.add_argument("--cpu-clouds", type=int, default=0,
+                    help="clouds per CPU-baseline step (default: one per host core, at most 64)")
     args = ap.parse_args()
+    if args.cpu_clouds <= 0:
+        args.cpu_clouds = max(1, min(64, os.cpu_count() or 1))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,9 +186,9 @@ def main():
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
-                                 "sample": "%d clouds of 8192 points per step (oracle C port, OpenMP over "
-                                           "clouds + numpy/BLAS GridConv); the reference has no CPU "
-                                           "Gridify (gridify.cc:30-39)" % args.cpu_clouds},
+                                 "sample": "%d clouds of 8192 points per step, %d steps (oracle C port: OpenMP over "
+                                           "clouds for the grid ops, one thread per cloud for the numpy GridConv); "
+                                           "the reference has no CPU Gridify (gridify.cc:30-39)" % (args.cpu_clouds, steps)},
                 "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -302,17 +326,29 @@ def main():
     q_bytes = B * gridify_bytes(cfg.num_points, l0.max_o_grid, l0.max_p_grid)
     q_gbs = q_bytes / (q_ms * 1e-3) / 1e9
 
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01_traffic.json),
+    # scaled to this run's batch; null when no capture exists for the kernel
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)["per_launch"]
+        for k, v in tj.items():
+            traffic[k] = (v["dram_read_bytes"] + v["dram_write_bytes"]) * B / v["clouds"]
+    except Exception:
+        pass
     tensor_peak = peaks["bf16_tflops_sustained"] if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"]
     roofline = {"kernel": "gridconv layer %d (%s)" % (dom, args.precision), "bound": "tensor",
                 "achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
-                "traffic": None, "ms_per_launch": conv_ms[dom], "layer_ms": conv_ms,
+                "traffic": traffic.get("edge_L%d" % dom), "ms_per_launch": conv_ms[dom], "layer_ms": conv_ms,
                 "algorithmic_tflops": tflops_alg,
                 "note": "achieved = flops the restructured layer executes (x1, split passes not counted) / "
                         "duration; algorithmic_tflops uses SURVEY s8d's per-edge formula 2*O*K*MAC",
                 "peak_source": peaks["_source"] + " dense bf16 cuBLAS (sustained); tf32 nominal peak is half of bf16"}
     roofline_hbm = {"kernel": "gridifyknn (build + query) N=8192 O=1024 P=%d" % l0.max_p_grid,
                     "bound": "hbm", "achieved": q_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": q_gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": q_ms,
+                    "frac": q_gbs / peaks["hbm_gbs"],
+                    "traffic": (traffic["knn_query"] + traffic.get("build", 0.0)) if "knn_query" in traffic else None,
+                    "ms_per_launch": q_ms,
                     "algorithmic_bytes": q_bytes, "peak_source": peaks["_source"]}
 
     cpu_val, cpu_dt, cores = time_cpu(cfg, params, args.cpu_clouds, 2, 1)
@@ -327,8 +363,8 @@ def main():
             "gpu_launches": args.steps * (len(cfg.layers) * 3 + (0 if args.precision == "fp32" else len(cfg.layers) - 1)),
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": {"value": cpu_val, "unit": "points/s", "cores": cores, "kind": "port",
-                             "sample": "%d clouds of 8192 points, 2 steps (oracle C port with OpenMP over "
-                                       "clouds + numpy/BLAS GridConv)" % args.cpu_clouds},
+                             "sample": "%d clouds of 8192 points, 2 steps (oracle C port: OpenMP over clouds for the grid "
+                                       "ops, one thread per cloud for the numpy GridConv)" % args.cpu_clouds},
             "breakdown_ms": {"query": query_ms, "gridconv": conv_ms,
                              "note": "each operator timed alone, L2 flushed before every call"},
             "clocks": sampler.summary()}

@@ -172,7 +172,9 @@ __device__ __forceinline__ void ring_request(Ring &ring, SliceSeq &prod, const f
 // Issue every MMA of one transposed stage (single thread).  D^T[128 ch of chunk j, ncols] (+)=
 // W_slice * Xop^T; x_hi/x_lo are the shared addresses of the B operand images ([ncols rows x Kp],
 // panel stride x_lbo); weight slices arrive through the ring in the packed order.
-template <int NSPLIT>
+// SWAP == true: the same slices serve as the B operand and the image as the A operand, i.e.
+// D[row, 128 ch of chunk j] (+)= X * W_slice^T (rows in TMEM lanes, channels in columns).
+template <int NSPLIT, bool SWAP = false>
 __device__ __forceinline__ void run_transposed_stage(const TcStage &st, Ring &ring, SliceSeq &prod,
                                                      const float *packed, long long total_slices,
                                                      bool sticky, uint32_t x_hi, uint32_t x_lo,
@@ -197,11 +199,17 @@ __device__ __forceinline__ void run_transposed_stage(const TcStage &st, Ring &ri
                 if (NSPLIT == 3) {
                     const uint64_t al = tc::make_sdesc(a_lo + ks * 2 * 2048, 2048);
                     const uint64_t bl = tc::make_sdesc(x_lo + xo, x_lbo);
-                    tc::mma_tf32(d, al, bh, idesc, acc);
-                    tc::mma_tf32(d, ah, bl, idesc, 1);
+                    if (SWAP) {
+                        tc::mma_tf32(d, bl, ah, idesc, acc);
+                        tc::mma_tf32(d, bh, al, idesc, 1);
+                    } else {
+                        tc::mma_tf32(d, al, bh, idesc, acc);
+                        tc::mma_tf32(d, ah, bl, idesc, 1);
+                    }
                     acc = 1;
                 }
-                tc::mma_tf32(d, ah, bh, idesc, acc);
+                if (SWAP) tc::mma_tf32(d, bh, ah, idesc, acc);
+                else tc::mma_tf32(d, ah, bh, idesc, acc);
                 acc = 1;
             }
             ring.consumed++;
@@ -410,6 +418,157 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     }
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel A, row-major variant (used when the widest stage input fits a [128 x K] hi/lo image, K <= 128):
+// D[row, ch] = X * W^T with the rows in the TMEM lanes.  The epilogue thread owns a ROW, so the next
+// stage's operand image is written with 16-byte vector stores and every one of the 128 epilogue threads
+// works whatever the stage width -- ~4x fewer instructions than the transposed kernel above, which
+// remains for the layers whose activations do not fit (K = 256).
+// ------------------------------------------------------------------------------------------------
+template <int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int TR = kTileRows;
+    constexpr uint32_t LBO = TR * 16;
+    int kmax = 0, npmax = 0;
+    for (int s = 0; s < p.na; s++) {
+        kmax = max(kmax, p.a[s].Kp);
+        npmax = max(npmax, p.a[s].Np);
+    }
+    const uint32_t x_img = (uint32_t)(kmax / 4) * LBO;
+    uint8_t *x_hi = smem, *x_lo = smem + x_img;
+    float *bias_s = reinterpret_cast<float *>(smem + (NSPLIT == 3 ? 2 : 1) * x_img);  // [na][npmax], zero padded
+    Ring ring;
+    ring.slots = reinterpret_cast<uint8_t *>(bias_s) + pad_to(p.na * npmax * 4, 128);
+    ring.nslots = p.ring_slots;
+    ring.full = bars;
+    ring.empty = bars + kMaxRing;
+    ring.issued = ring.consumed = 0;
+    for (int i = 0; i < kMaxRing; i++) ring.off[i] = (uint32_t)i * kSlotBytes;
+    uint64_t *bar_mma = bars + 2 * kMaxRing;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+    if (tid == 0) {
+        for (int i = 0; i < ring.nslots; i++) {
+            tc::mbar_init(&ring.full[i], 1);
+            tc::mbar_init(&ring.empty[i], 1);
+        }
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_init_fence();
+    }
+    for (int i = tid; i < p.na * npmax; i += kTcThreads) {
+        const int s = i / npmax, j = i % npmax;
+        bias_s[i] = j < p.a[s].Cout ? __ldg(p.a[s].bias + j) : 0.f;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    SliceSeq prod;
+    prod.n = p.na;
+    prod.chunk_major = 0;
+    for (int s = 0; s < p.na && s < 3; s++) prod.st[s] = &p.a[s];
+    prod.reset();
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_slices = (long long)my_tiles * prod.per_tile();
+    const bool sticky = prod.per_tile() <= ring.nslots;
+    if (sticky) ring.nslots = max(prod.per_tile(), 1);
+    if (warp == 4 && lane == 0) {
+        const long long pre = sticky ? prod.per_tile() : ring.nslots;
+        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+    }
+    uint32_t mma_phase = 0;
+    const long long rows_total = (long long)p.c.B * p.c.Nprev;
+    const int row_w = 4 + p.c.Cin;
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+    const int C = p.a[p.na - 1].Cout;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * TR;
+        // ---- X0 = table[row0 .. row0+128, 4:4+Cin] as hi/lo K-major images (coalesced 128-bit loads) ----
+        if (warp < 4) {
+            const int kp0 = p.a[0].Kp;
+            for (int e = tid; e < TR * (kp0 / 4); e += 128) {
+                const int r = e / (kp0 / 4), c = (e % (kp0 / 4)) * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (row0 + r < rows_total) {
+                    const float *src = p.c.table + (row0 + r) * row_w + 4 + c;
+                    if ((row_w & 3) == 0 && c + 3 < p.c.Cin) {
+                        float4 t4 = __ldg(reinterpret_cast<const float4 *>(src));
+                        v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+                    } else {
+                        for (int i = 0; i < 4; i++)
+                            if (c + i < p.c.Cin) v[i] = __ldg(src + i);
+                    }
+                }
+                float hi[4], lo[4];
+                for (int i = 0; i < 4; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+                const uint32_t off = tc::kmajor_off(r, c, LBO);
+                *reinterpret_cast<float4 *>(x_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (NSPLIT == 3) *reinterpret_cast<float4 *>(x_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        for (int s = 0; s < p.na; s++) {
+            const TcStage &st = p.a[s];
+            if (warp == 4) {
+                if (lane == 0) {
+                    run_transposed_stage<NSPLIT, true>(st, ring, prod, p.packed, total_slices, sticky,
+                                                       tc::smem_u32(x_hi), tc::smem_u32(x_lo), LBO, 128, tmem, 128);
+                    tc::mma_commit(bar_mma);
+                }
+                __syncwarp();
+            }
+            wait_bar(bar_mma, mma_phase);
+            mma_phase ^= 1;
+            tc::fence_after_sync();
+            if (warp < 4) {
+                const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+                if (s + 1 < p.na) {
+                    plain_epilogue<NSPLIT>(st, tl, row_off, x_hi, x_lo, LBO, p.a[s + 1].Kp, bias_s + s * npmax);
+                } else if (row0 + tid < rows_total) {  // last stage: F[row, :] = relu(D + b), 128-bit stores
+                    float *dst = p.ftab + (row0 + tid) * C;
+                    const float *bs = bias_s + s * npmax;
+                    for (int c0 = 0; c0 < C; c0 += 16) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(tl + c0, v);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int c = c0 + q * 4;
+                            if (c + 3 < C) {
+                                const float4 b4 = *reinterpret_cast<const float4 *>(bs + c);
+                                *reinterpret_cast<float4 *>(dst + c) =
+                                    make_float4(fmaxf(__uint_as_float(v[q * 4 + 0]) + b4.x, 0.f),
+                                                fmaxf(__uint_as_float(v[q * 4 + 1]) + b4.y, 0.f),
+                                                fmaxf(__uint_as_float(v[q * 4 + 2]) + b4.z, 0.f),
+                                                fmaxf(__uint_as_float(v[q * 4 + 3]) + b4.w, 0.f));
+                            } else {
+                                for (int i = 0; i < 4; i++)
+                                    if (c + i < C) dst[c + i] = fmaxf(__uint_as_float(v[q * 4 + i]) + bs[c + i], 0.f);
+                            }
+                        }
+                    }
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -953,6 +1112,9 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(point_mlp_tc_kernel<NSPLIT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
         if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(point_mlp_rows_tc_kernel<NSPLIT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+        if (e == cudaSuccess)
             e = cudaFuncSetAttribute(edge_tc_kernel<NSPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemCap);
         if (e == cudaSuccess)
@@ -962,32 +1124,57 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         attr_set = true;
     }
     if (p.na > 0) {  // kernel A
-        int chunks = 0;
-        for (int s = 0; s < p.na; s++) chunks = max(chunks, p.a[s].Np / 128);
-        // Rows per tile: the largest of 128/64/32 that fits chunks*TR <= 256 TMEM columns and leaves at
-        // least 2 ring slots (up to 6 when there is room).  Fewer, larger tiles win: every tile re-streams
-        // the layer's weights from L2 and that stream -- ~2-2.5 TB/s in aggregate when all SMs read the same
-        // slices -- is the bound for the wide layers (measured, r01).
-        int TR = 0, slots = 0;
-        for (int cand = 128; cand >= 32; cand >>= 1) {
-            if (chunks * cand > 256) continue;
-            size_t fixed = kernel_a_smem(p, cand, NSPLIT, 0);
-            if (fixed > kSmemCap) continue;
-            int fit = (int)min((size_t)6, (kSmemCap - fixed) / kSlotBytes);
-            if (fit >= 2) { TR = cand; slots = fit; break; }
+        int chunks = 0, kmax = 0, npmax = 0;
+        for (int s = 0; s < p.na; s++) {
+            chunks = max(chunks, p.a[s].Np / 128);
+            kmax = max(kmax, p.a[s].Kp);
+            npmax = max(npmax, p.a[s].Np);
         }
-        if (TR == 0) return GRIDGCN_ELIMIT;
-        p.a_rows = TR;
-        p.ring_slots = slots;
-        p.ring_sticky = 0;
         long long rows = (long long)c.B * c.Nprev;
-        long long tiles = (rows + TR - 1) / TR;
-        size_t smem = kernel_a_smem(p, TR, NSPLIT, slots);
-        int per_sm = (int)max((size_t)1, min((size_t)2, kSmemCap / smem));
-        int blocks = (int)min(tiles, (long long)sms * per_sm);
-        point_mlp_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
+        // Row-major variant when a [128 x kmax] hi/lo image plus >= 2 ring slots fit and C % 4 == 0
+        const size_t rows_fixed = (size_t)(NSPLIT == 3 ? 2 : 1) * (kmax / 4) * kTileRows * 16 +
+                                  pad_to(p.na * npmax * 4, 128) + 1024;
+        const bool rows_ok = rows_fixed + 2 * (size_t)kSlotBytes <= kSmemCap && npmax <= 512 &&
+                             (p.a[p.na - 1].Cout & 3) == 0;
+        if (rows_ok) {
+            p.a_rows = kTileRows;
+            p.ring_slots = (int)min((size_t)4, (kSmemCap - rows_fixed) / kSlotBytes);
+            p.ring_sticky = 0;
+            int saved_cols = p.tmem_cols;
+            p.tmem_cols = npmax <= 128 ? 128 : (npmax <= 256 ? 256 : 512);
+            long long tiles = (rows + kTileRows - 1) / kTileRows;
+            size_t smem = rows_fixed + (size_t)p.ring_slots * kSlotBytes;
+            int per_sm = (int)max((size_t)1, min(min((size_t)2, kSmemCap / smem), (size_t)(512 / p.tmem_cols)));
+            int blocks = (int)min(tiles, (long long)sms * per_sm);
+            point_mlp_rows_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles);
+            p.tmem_cols = saved_cols;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+        } else {
+            // Transposed variant.  Rows per tile: the largest of 128/64/32 that fits chunks*TR <= 256 TMEM
+            // columns and leaves at least 2 ring slots (up to 6 when there is room).  Fewer, larger tiles
+            // win: every tile re-streams the layer's weights from L2 and that stream -- ~2-2.5 TB/s in
+            // aggregate when all SMs read the same slices -- is the bound for the wide layers (measured, r01).
+            int TR = 0, slots = 0;
+            for (int cand = 128; cand >= 32; cand >>= 1) {
+                if (chunks * cand > 256) continue;
+                size_t fixed = kernel_a_smem(p, cand, NSPLIT, 0);
+                if (fixed > kSmemCap) continue;
+                int fit = (int)min((size_t)6, (kSmemCap - fixed) / kSlotBytes);
+                if (fit >= 2) { TR = cand; slots = fit; break; }
+            }
+            if (TR == 0) return GRIDGCN_ELIMIT;
+            p.a_rows = TR;
+            p.ring_slots = slots;
+            p.ring_sticky = 0;
+            long long tiles = (rows + TR - 1) / TR;
+            size_t smem = kernel_a_smem(p, TR, NSPLIT, slots);
+            int per_sm = (int)max((size_t)1, min((size_t)2, kSmemCap / smem));
+            int blocks = (int)min(tiles, (long long)sms * per_sm);
+            point_mlp_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     {  // kernel B
         if (c.K > kTileRows) return GRIDGCN_ELIMIT;
