@@ -173,7 +173,8 @@ def main():
                           "query=%s, synthetic surface clouds" % (args.K, args.query),
               "clouds_per_gpu": args.batch, "points_per_cloud": cfg.num_points, "K": args.K,
               "precision": args.precision, "parallelism": "batch-sharded clouds x%d, no collective" % world,
-              "l2": "flushed between timed steps (256 MiB write)"}
+              "l2": "value: L2 flushed (256 MiB write) between timed steps; e2e: inputs rewritten by H2D every step and "
+                    "the per-step working set (index + feature tables) exceeds the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference (CPU) arm
     if args.impl == "reference":
@@ -241,11 +242,46 @@ def main():
     def step_device():
         return enc(data_d, npts_d)
 
-    def step_e2e():
-        d = data_h.to(dev, non_blocking=True)
-        n = npts_h.to(dev, non_blocking=True)
-        out = enc(d, n)
-        out_h.copy_(out, non_blocking=True)
+    # End-to-end: every step copies its inputs from pinned host memory and reads its result back.  Copies
+    # run on their own stream, double buffered, so the H2D of step i+1 and the D2H of step i-1 overlap
+    # the compute of step i (all of it inside the timed region).
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    in_bufs = [(torch.empty_like(data_d), torch.empty_like(npts_d)) for _ in range(2)]
+    out_hs = [out_h, torch.empty_like(out_h).pin_memory()]
+
+    def run_e2e(steps):
+        comp = torch.cuda.current_stream(dev)
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        ev_comp = [torch.cuda.Event() for _ in range(2)]
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def h2d(i):
+            b = i & 1
+            with torch.cuda.stream(h2d_stream):
+                if i >= 2:
+                    h2d_stream.wait_event(ev_comp[b])  # step i-2 no longer reads in_bufs[b]
+                in_bufs[b][0].copy_(data_h, non_blocking=True)
+                in_bufs[b][1].copy_(npts_h, non_blocking=True)
+                ev_h2d[b].record(h2d_stream)
+
+        start.record(comp)
+        h2d_stream.wait_event(start)
+        d2h_stream.wait_event(start)
+        h2d(0)
+        for i in range(steps):
+            b = i & 1
+            if i + 1 < steps:
+                h2d(i + 1)  # next step's inputs travel while this step computes
+            comp.wait_event(ev_h2d[b])
+            out = enc(in_bufs[b][0], in_bufs[b][1])
+            ev_comp[b].record(comp)
+            out.record_stream(d2h_stream)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(ev_comp[b])
+                out_hs[b].copy_(out, non_blocking=True)
+        end.record(d2h_stream)
+        torch.cuda.synchronize()
+        return start.elapsed_time(end)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -255,10 +291,9 @@ def main():
         sampler.start()
     ms_total = timed(step_device, args.steps)
     barrier()
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     barrier()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = run_e2e(args.steps)
     barrier()
     sampler.stop_flag = True
 
