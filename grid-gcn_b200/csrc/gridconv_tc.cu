@@ -264,10 +264,10 @@ __device__ __forceinline__ void plain_epilogue(const TcStage &st, uint32_t tmem_
             if (c < kp_next) {
                 const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c);
                 float hi[4], lo[4];
-                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 0]) + b4.x, 0.f), hi[0], lo[0]);
-                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 1]) + b4.y, 0.f), hi[1], lo[1]);
-                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 2]) + b4.z, 0.f), hi[2], lo[2]);
-                tc::split_tf32(fmaxf(__uint_as_float(v[q * 4 + 3]) + b4.w, 0.f), hi[3], lo[3]);
+                tc::split_op<NSPLIT>(fmaxf(__uint_as_float(v[q * 4 + 0]) + b4.x, 0.f), hi[0], lo[0]);
+                tc::split_op<NSPLIT>(fmaxf(__uint_as_float(v[q * 4 + 1]) + b4.y, 0.f), hi[1], lo[1]);
+                tc::split_op<NSPLIT>(fmaxf(__uint_as_float(v[q * 4 + 2]) + b4.z, 0.f), hi[2], lo[2]);
+                tc::split_op<NSPLIT>(fmaxf(__uint_as_float(v[q * 4 + 3]) + b4.w, 0.f), hi[3], lo[3]);
                 const uint32_t off = row_off + (uint32_t)(c >> 2) * lbo;
                 *reinterpret_cast<float4 *>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 if (NSPLIT == 3)
@@ -354,7 +354,7 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
                     }
                 }
                 float hi[4], lo[4];
-                for (int i = 0; i < 4; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+                for (int i = 0; i < 4; i++) tc::split_op<NSPLIT>(v[i], hi[i], lo[i]);
                 const uint32_t off = tc::kmajor_off(r, c, x_lbo);
                 *reinterpret_cast<float4 *>(x_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 if (NSPLIT == 3) *reinterpret_cast<float4 *>(x_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -401,7 +401,7 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
                             for (int i = 0; i < 16; i++) {
                                 float x = ch < st.Cout ? fmaxf(__uint_as_float(v[i]) + bias, 0.f) : 0.f;
                                 float hi, lo;
-                                tc::split_tf32(x, hi, lo);
+                                tc::split_op<NSPLIT>(x, hi, lo);
                                 const uint32_t off = tc::kmajor_off(r0 + i, ch, x_lbo);
                                 *reinterpret_cast<float *>(x_hi + off) = hi;
                                 if (NSPLIT == 3) *reinterpret_cast<float *>(x_lo + off) = lo;
@@ -509,7 +509,7 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
                     }
                 }
                 float hi[4], lo[4];
-                for (int i = 0; i < 4; i++) tc::split_tf32(v[i], hi[i], lo[i]);
+                for (int i = 0; i < 4; i++) tc::split_op<NSPLIT>(v[i], hi[i], lo[i]);
                 const uint32_t off = tc::kmajor_off(r, c, LBO);
                 *reinterpret_cast<float4 *>(x_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 if (NSPLIT == 3) *reinterpret_cast<float4 *>(x_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -790,7 +790,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                     acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
                     acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
                     acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
-                    tc::split_tf32(fmaxf(acc, 0.f), hi[i], lo[i]);
+                    tc::split_op<NSPLIT>(fmaxf(acc, 0.f), hi[i], lo[i]);
                 }
                 const uint32_t off = row_off + (uint32_t)g * LBO;
                 *reinterpret_cast<float4 *>(xa_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -806,7 +806,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                         for (int i = 0; i < 4; i++) {
                             const float4 w = w4[i];
                             const float v = fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, w.w)));
-                            tc::split_tf32(fmaxf(v, 0.f), hi[i], lo[i]);
+                            tc::split_op<NSPLIT>(fmaxf(v, 0.f), hi[i], lo[i]);
                         }
                         const uint32_t off = row_off + (uint32_t)g * LBO;
                         *reinterpret_cast<float4 *>(xf_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -815,9 +815,9 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                     }
                 } else {  // single-stage feature MLP: the tensor core reads the geo vector itself (K = 8)
                     float hi[4], lo[4];
-                    tc::split_tf32(dx, hi[0], lo[0]);
-                    tc::split_tf32(dy, hi[1], lo[1]);
-                    tc::split_tf32(dz, hi[2], lo[2]);
+                    tc::split_op<NSPLIT>(dx, hi[0], lo[0]);
+                    tc::split_op<NSPLIT>(dy, hi[1], lo[1]);
+                    tc::split_op<NSPLIT>(dz, hi[2], lo[2]);
                     hi[3] = lo[3] = 0.f;
                     *reinterpret_cast<float4 *>(xf_hi + row_off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<float4 *>(xf_hi + row_off + LBO) = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -27,6 +27,7 @@ tc_gemm_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B
         int r = e / K, k = e % K;
         float hi, lo;
         tc::split_tf32(A[e], hi, lo);
+        if (nsplit == 0) hi = A[e];  // probe: unrounded fp32 bits
         uint32_t off = tc::kmajor_off(r, k, lbo_a);
         *reinterpret_cast<float *>(a_hi + off) = hi;
         *reinterpret_cast<float *>(a_lo + off) = lo;
@@ -35,6 +36,7 @@ tc_gemm_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B
         int r = e / K, k = e % K;
         float hi, lo;
         tc::split_tf32(B[e], hi, lo);
+        if (nsplit == 0) hi = B[e];
         uint32_t off = tc::kmajor_off(r, k, lbo_b);
         *reinterpret_cast<float *>(b_hi + off) = hi;
         *reinterpret_cast<float *>(b_lo + off) = lo;

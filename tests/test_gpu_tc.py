@@ -27,3 +27,24 @@ def test_tc_gemm_selftest(gg, cuda_dev, N, K, nsplit):
     tol = 2e-3 if nsplit == 1 else 1e-5  # tf32: 2^-11 per operand; split: fp32-class
     print("N=%d K=%d nsplit=%d err=%.3g" % (N, K, nsplit, err))
     assert err < tol, "N=%d K=%d nsplit=%d: max err / sqrt(K) = %.3g" % (N, K, nsplit, err)
+
+
+def test_tf32_operands_are_truncated(gg, cuda_dev):
+    """The 3-pass split (tc_common.cuh split_op) relies on tcgen05 kind::tf32 TRUNCATING the low 13
+    mantissa bits of fp32 operands.  nsplit == 0 feeds the self-test kernel raw fp32 bits."""
+    L = gg._lib.lib()
+    rng = np.random.default_rng(0)
+    N, K = 64, 8
+    A = rng.normal(size=(128, K)).astype(np.float32)
+    B = rng.normal(size=(N, K)).astype(np.float32)
+    a, b = torch.from_numpy(A).to(cuda_dev), torch.from_numpy(B).to(cuda_dev)
+    d = torch.zeros((128, N), dtype=torch.float32, device=cuda_dev)
+    gg._lib.check(L.gridgcn_debug_tc_gemm(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K, 0,
+                                          torch.cuda.current_stream(cuda_dev).cuda_stream), "tc_gemm")
+    torch.cuda.synchronize()
+    got = d.cpu().numpy().astype(np.float64)
+    trunc = lambda x: (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    want = trunc(A).astype(np.float64) @ trunc(B).astype(np.float64).T
+    exact = A.astype(np.float64) @ B.astype(np.float64).T
+    assert np.abs(got - want).max() < 1e-5
+    assert np.abs(got - exact).max() > 1e-4  # i.e. it really is tf32, not fp32
