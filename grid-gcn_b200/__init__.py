@@ -9,7 +9,8 @@ tensors are not on a CUDA device.
 from . import synth  # noqa: F401  host-side input generator, numpy only
 from . import _lib  # noqa: F401  ctypes binding (loads the library lazily)
 from .ops import Gridify, GridifyKNN, GridifyUp, contrib  # noqa: F401
-from .gridconv import GridConv, sub_g_update, fold_bn, init_layer, features_nco  # noqa: F401
+from .gridconv import (GridConv, GridConvUp, SegHead, sub_g_update, fold_bn, init_layer,  # noqa: F401
+                       init_up_layer, features_nco, rowmlp)
 from . import stack, shard  # noqa: F401
 from .build import build  # noqa: F401
 

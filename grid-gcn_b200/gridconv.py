@@ -179,3 +179,94 @@ def sub_g_update(centers_xyz, center_den, neighbors, has_feats, center_masks, ne
         center_masks = torch.ones((B, O), dtype=torch.float32, device=neighbors.device)
     conv = GridConv(layer, neighbors.device, pre_relu=pre_relu, precision=precision)
     return features_nco(conv(table, idx, cent, center_masks))
+
+
+def init_up_layer(rng, cd, cu, pt_mlp_lst, attfdim, center_dim, out_dim):
+    """Parameters of one decoder layer: neighbour features Cd -> pt_mlp, attention, centre branch on the
+    finer level's [cent | feat] rows (4+Cu -> center_dim), update MLP (center_dim[-1]+pt[-1] -> out_dim)."""
+    layer = init_layer(rng, cd, pt_mlp_lst, attfdim)
+    w, stages = 4 + cu, []
+    for c in center_dim:
+        stages.append(init_stage(rng, w, c))
+        w = c
+    layer["center"] = stages
+    w, stages = w + pt_mlp_lst[-1], []
+    for c in out_dim:
+        stages.append(init_stage(rng, w, c))
+        w = c
+    layer["update"] = stages
+    return layer
+
+
+def _folded(st, device, bn=True):
+    if bn:
+        w, b = fold_bn(st["weight"], st["bias"], st["gamma"], st["beta"], st["moving_mean"], st["moving_var"])
+    else:
+        w, b = np.asarray(st["weight"], np.float32).reshape(len(st["bias"]), -1), np.asarray(st["bias"], np.float32)
+    return torch.from_numpy(w).to(device).contiguous(), torch.from_numpy(b).to(device).contiguous()
+
+
+def rowmlp(in1, in2, w, b, *, relu_in=False, relu_out=True, row_scale=None, out=None, out_col=0, cent=None):
+    """out[..., out_col:out_col+Cout] = act(W act_in([in1 | in2]) + b) * row_scale   (C-ABI gridgcn_rowmlp_fwd).
+    in1 / in2: (..., C) views whose last dim is contiguous and whose rows are equally strided."""
+    L = _lib.lib()
+    rows = int(np.prod(in1.shape[:-1]))
+    c1, ld1 = in1.shape[-1], in1.stride(-2)
+    c2, ld2, p2 = 0, 0, None
+    if in2 is not None:
+        c2, ld2, p2 = in2.shape[-1], in2.stride(-2), in2.data_ptr()
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty(tuple(in1.shape[:-1]) + (out_col + cout,), dtype=torch.float32, device=in1.device)
+    ldo = out.stride(-2)
+    with torch.cuda.device(in1.device):
+        rc = L.gridgcn_rowmlp_fwd(in1.data_ptr(), ld1, c1, p2, ld2, c2, w.data_ptr(), b.data_ptr(), cout,
+                                  1 if relu_in else 0, 1 if relu_out else 0,
+                                  row_scale.data_ptr() if row_scale is not None else None,
+                                  out.data_ptr() + 4 * out_col, ldo,
+                                  cent.data_ptr() if cent is not None else None,
+                                  out.data_ptr() if cent is not None else None, rows,
+                                  torch.cuda.current_stream(in1.device).cuda_stream)
+    _lib.check(rc, "gridgcn_rowmlp_fwd")
+    return out
+
+
+class GridConvUp:
+    """One decoder GridConv layer (ggcn_models_g.py:191-231): aggregated neighbour features from the
+    fused GridConv kernels (no pre-ReLU / mask: they follow the concat), centre branch, concat, update MLP
+    and centre mask as row-MLP stages.  ``out = layer(f_last, nebidx, cent_up, f_this, centmsk)``."""
+
+    def __init__(self, layer, device, pre_relu=True, precision="tf32x3"):
+        self.device = torch.device(device)
+        self.core = GridConv(layer, device, pre_relu=False, precision=precision)
+        self.center = [_folded(st, self.device) for st in layer["center"]]
+        self.update = [_folded(st, self.device) for st in layer["update"]]
+        self.pre_relu = bool(pre_relu)
+        self.cout = int(layer["update"][-1]["weight"].shape[0]) if layer["update"] else None
+
+    def __call__(self, f_last, nebidx, cent_up, f_this, centmsk=None):
+        B, O, _ = nebidx.shape
+        ones = torch.ones((B, O), dtype=torch.float32, device=f_last.device)
+        agg = self.core(f_last, nebidx, cent_up, ones)[:, :, 4:]          # (B, O, C) strided view
+        cf = f_this
+        for w, b in self.center:
+            cf = rowmlp(cf, None, w, b)
+        x, x2 = cf, agg
+        for i, (w, b) in enumerate(self.update):
+            last = i + 1 == len(self.update)
+            x = rowmlp(x, x2, w, b, relu_in=self.pre_relu and i == 0, row_scale=centmsk if last else None,
+                       out_col=4 if last else 0, cent=cent_up.contiguous() if last else None)
+            x2 = None
+        return x
+
+
+class SegHead:
+    """get_seg_head up to the logits (ggcn_models_g.py:30-36, eval mode)."""
+
+    def __init__(self, head, device):
+        self.l1 = _folded(head[0], device)
+        self.l2 = _folded(head[1], device, bn=False)
+
+    def __call__(self, feats):
+        x = rowmlp(feats, None, *self.l1)
+        return rowmlp(x, None, *self.l2, relu_out=False)

@@ -125,3 +125,83 @@ class GridGcnEncoder:
                                   actual_centnum=num, table=table))
         self.trace = trace
         return table
+
+
+# ---------------------------------------------------------------------------------------------------
+# Encoder + decoder + head of the segmentation graph (get_symbol_seg_ggcn, ggcn_models_g.py:110-237)
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class UpCfg:
+    max_p_grid: int = 5                       # up_max_p_grid_lst
+    kernel_size: int = 3                      # up_kernel_size_lst
+    pt_mlp_lst: Sequence[int] = (128,)        # up_pt_ele_dim
+    center_dim: Sequence[int] = (128,)        # up_center_dim
+    out_dim: Sequence[int] = (128,)           # up_gcn_outDim
+    attfdim: int = 10                         # up_attfdim
+    neigh_fetch: str = "ballknn"              # up_neigh_fetch: True -> BallKNN; "gridifyup" -> GridifyUp
+
+
+def init_seg_params(cfg: StackCfg, up: UpCfg, seed=0, num_classes=21):
+    """Encoder layers, one decoder layer per encoder layer (reverse order) and the head."""
+    rng = np.random.default_rng(seed)
+    enc, cin = [], 0
+    for l in cfg.layers:
+        enc.append(gridconv.init_layer(rng, cin, list(l.pt_mlp_lst), cfg.attfdim))
+        cin = l.pt_mlp_lst[-1]
+    widths = [0] + [l.pt_mlp_lst[-1] for l in cfg.layers]  # feature width of every level (input level: 0)
+    dec, cd = [], widths[-1]
+    for i in range(len(cfg.layers)):
+        cu = widths[-i - 2]
+        dec.append(gridconv.init_up_layer(rng, cd, cu, list(up.pt_mlp_lst), up.attfdim, list(up.center_dim),
+                                          list(up.out_dim)))
+        cd = up.out_dim[-1]
+    head = [gridconv.init_stage(rng, cd, 128), gridconv.init_stage(rng, 128, num_classes)]
+    return dict(enc=enc, dec=dec, head=head)
+
+
+class GridGcnSeg:
+    """``logits = net(data, actual_numpoints)``: (B,N,4) -> (B,N,21).  Mirrors get_symbol_seg_ggcn: the
+    encoder loop (:152-187), then for every level in reverse the neighbour fetch
+    (BallKNN with radius = up_voxel * up_kernel * 1.7 / 2, :201-204, or GridifyUp, :206-210), the gather
+    from the coarser level's [cent | feat] table and sub_g_update with center_ori_feats (:212-231), and
+    the head (:233-236)."""
+
+    def __init__(self, cfg: StackCfg, up: UpCfg, params, device, precision="tf32x3"):
+        self.cfg, self.up = cfg, up
+        self.enc = GridGcnEncoder(cfg, params["enc"], device, precision=precision)
+        self.dec = [gridconv.GridConvUp(p, device, pre_relu=cfg.pre_relu, precision=precision)
+                    for p in params["dec"]]
+        self.head = gridconv.SegHead(params["head"], device)
+        self.trace = []
+
+    def __call__(self, data, actual_numpoints, keep_trace=False):
+        cfg, up = self.cfg, self.up
+        self.enc(data, actual_numpoints, keep_trace=True)
+        et = self.enc.trace
+        # level 0 = input points, level i+1 = encoder layer i
+        tables = [data] + [t["table"] for t in et]
+        cents = [data] + [t["cent"] for t in et]
+        nums = [actual_numpoints] + [t["actual_centnum"] for t in et]
+        masks = [None] + [t["centmsk"] for t in et]
+        f_last, trace = tables[-1], []
+        nl = len(cfg.layers)
+        for i, dec in enumerate(self.dec):
+            lvl_dn, lvl_up = nl - i, nl - i - 1
+            down, centers = cents[lvl_dn], cents[lvl_up]
+            l = cfg.layers[lvl_up]  # the up level's own grid: up_voxel_size_lst is the encoder ladder reversed
+            if up.neigh_fetch == "ballknn":
+                radius = l.voxel_size * up.kernel_size * 1.7 / 2
+                nebidx = ops.contrib.BallKNN(centers[:, :, :3].contiguous(), down[:, :, :3].contiguous(),
+                                             nums[lvl_dn], nums[lvl_up], k=up.max_p_grid, radius=radius)
+            else:
+                nebidx, _ = ops.GridifyUp(down, centers, nums[lvl_dn], nums[lvl_up],
+                                          max_p_grid=up.max_p_grid, max_o_grid=centers.shape[1],
+                                          kernel_size=up.kernel_size, coord_shift=cfg.coord_shift,
+                                          voxel_size=[l.voxel_size] * 3, grid_size=[l.grid_size] * 3)
+            mask = masks[lvl_up] if i != len(self.dec) - 1 else None  # ggcn_models_g.py:224
+            f_last = dec(f_last, nebidx, centers, tables[lvl_up], mask)
+            if keep_trace:
+                trace.append(dict(nebidx=nebidx, table=f_last))
+        logits = self.head(f_last[:, :, 4:])
+        self.trace = trace
+        return logits

@@ -154,6 +154,20 @@ int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cen
                          const gridgcn_mlp_t *mlp_host, int precision, const void *packed,
                          void *workspace, size_t workspace_bytes, float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Row MLP stage -- the per-centre 1x1 convolutions of the decoder half of sub_g_update           */
+/* (segmentation/models/gcn_module_g_att.py:267-285 centre branch + concat, :24-43 update_func,   */
+/* :284-285 centre mask) and of the segmentation head (ggcn_models_g.py:30-36), BN folded:        */
+/*   out[r, 0:cout] = act_out( W * act_in([in1[r, 0:c1] | in2[r, 0:c2]]) + b ) * row_scale[r]     */
+/* in1/in2/out are strided row views (ld = floats per row); in2 / row_scale may be NULL.  When     */
+/* `cent` (rows,4) is given its rows are copied to out_table[r*ld_out + 0..3] (the [cent | feat]  */
+/* table layout, ggcn_models_g.py:231).  Exact fp32 FMA on CUDA cores.                             */
+/* ------------------------------------------------------------------------------------------ */
+int gridgcn_rowmlp_fwd(const float *in1, int ld1, int c1, const float *in2, int ld2, int c2,
+                       const float *weight, const float *bias, int cout, int relu_in, int relu_out,
+                       const float *row_scale, float *out, int ld_out, const float *cent,
+                       float *out_table, long long rows, void *stream);
+
 /* Self-test of the tcgen05 primitives (not an operator): D[128,N] = A[128,K] * B[N,K]^T on one CTA,
  * kind::tf32, nsplit 1 (plain) or 3 (error-compensated).  N % 16 == 0, N <= 256, K % 8 == 0. */
 int gridgcn_debug_tc_gemm(const float *A, const float *B, float *D, int N, int K, int nsplit,

@@ -82,3 +82,55 @@ def gridconv_layer(table, nebidx, cent, centmsk, layer, pre_relu=True):
         agg = np.maximum(agg, F(0))
     agg = (agg * np.asarray(centmsk, F)[:, None, :]).astype(F)
     return np.concatenate([cent, agg.transpose(0, 2, 1)], axis=2).astype(F)
+
+
+def _conv1d_bn_relu(x, st, relu=True, bn=True):
+    """x: (B, Cin, O) -> (B, Cout, O); Convolution(kernel 1) -> BatchNorm eval -> relu
+    (utils/ops.py:141-147, mlp1d_c :236-242)."""
+    y = np.einsum("oc,bcn->bon", st["weight"], x, optimize=True).astype(F)
+    y = (y + st["bias"][None, :, None]).astype(F)
+    if bn:
+        inv = (F(1.0) / np.sqrt(st["moving_var"] + F(BN_EPS))).astype(F)
+        y = ((y - st["moving_mean"][None, :, None]) * inv[None, :, None]).astype(F)
+        y = (y * st["gamma"][None, :, None] + st["beta"][None, :, None]).astype(F)
+    return np.maximum(y, F(0)) if relu else y
+
+
+def gridconv_up_layer(f_last, nebidx, cent_up, f_this, centmsk, layer, pre_relu=True):
+    """One DECODER GridConv layer (segmentation/models/ggcn_models_g.py:191-231 + sub_g_update with
+    center_ori_feats, gcn_module_g_att.py:267-285).
+
+    f_last  (B, Nd, 4+Cd)  coarser level's [cent | feat] rows (gathered through nebidx, BallKNN/GridifyUp)
+    nebidx  (B, O, K)      cent_up (B, O, 4)  centres of the finer level
+    f_this  (B, O, 4+Cu)   finer level's own [cent | feat] rows (`center_ori_feats`)
+    centmsk (B, O) or None
+    layer: dict(feat=[stage], att=[stage, stage], center=[stage], update=[stage], attfdim, cin=Cd)
+    -> (B, O, 4+Cout) = concat(cent_up, feats)  (ggcn_models_g.py:231)"""
+    f_last = np.asarray(f_last, F)
+    cent_up = np.asarray(cent_up, F)
+    B, O, K = nebidx.shape
+    ones = np.ones((B, O), F)
+    # aggregated neighbour features: the encoder block without pre-ReLU / mask (they come after the concat)
+    agg = gridconv_layer(f_last, nebidx, cent_up, ones, layer, pre_relu=False)[..., 4:]   # (B, O, C)
+    agg = agg.transpose(0, 2, 1)                                                          # (B, C, O)
+    center_ori = np.asarray(f_this, F).transpose(0, 2, 1)                                 # (B, 4+Cu, O)
+    center_feats = center_ori
+    for st in layer["center"]:                                  # mlp1d_c(center_ori_feats, center_dim) :269
+        center_feats = _conv1d_bn_relu(center_feats, st)
+    x = np.concatenate([center_feats, agg], axis=1)             # up_center_inte == "concat" :281-282
+    if pre_relu:
+        x = np.maximum(x, F(0))                                 # update_func :31-32
+    for st in layer["update"]:                                  # mlp1d_c(outDim) :33-36
+        x = _conv1d_bn_relu(x, st)
+    if centmsk is not None:
+        x = (x * np.asarray(centmsk, F)[:, None, :]).astype(F)  # :284-285
+    return np.concatenate([cent_up, x.transpose(0, 2, 1)], axis=2).astype(F)
+
+
+def seg_head(feats, head):
+    """get_seg_head (ggcn_models_g.py:30-36) in eval mode up to the logits: conv1d 128 + BN + relu,
+    dropout = identity, conv1d 21 without BN / relu.  feats (B, O, C) -> logits (B, O, 21)."""
+    x = np.asarray(feats, F).transpose(0, 2, 1)
+    x = _conv1d_bn_relu(x, head[0])
+    x = _conv1d_bn_relu(x, head[1], relu=False, bn=False)
+    return x.transpose(0, 2, 1).astype(F)

@@ -350,3 +350,70 @@ def test_gridconv_plain_tf32_is_close(gg, cuda_dev, oracle_mod):
     print("rel err:", errs)
     assert errs["tf32x3"] <= 1e-3 and errs["tf32"] <= 1e-2
     assert errs["tf32x3"] < errs["tf32"]
+
+
+def _rand_up_case(rng, B, Nd, O, K, cd, cu):
+    f_last = rng.uniform(-1, 1, size=(B, Nd, 4 + cd)).astype(np.float32)
+    f_this = rng.uniform(-1, 1, size=(B, O, 4 + cu)).astype(np.float32)
+    nebidx = rng.integers(0, Nd, size=(B, O, K)).astype(np.int32)
+    nebidx[:, ::3, -1] = -1  # BallKNN misses
+    cent = f_this[:, :, :4].copy()
+    msk = (rng.uniform(size=(B, O)) > 0.2).astype(np.float32)
+    return f_last, nebidx, cent, f_this, msk
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_decoder_layer_matches_oracle(gg, cuda_dev, precision):
+    """sub_g_update with center_ori_feats (decoder half, gcn_module_g_att.py:267-285)."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import gridconv
+    rng = np.random.default_rng(11)
+    for (B, Nd, O, K, cd, cu) in ((2, 24, 256, 5, 256, 128), (1, 256, 1024, 5, 128, 64), (2, 64, 300, 5, 32, 0)):
+        f_last, nebidx, cent, f_this, msk = _rand_up_case(rng, B, Nd, O, K, cd, cu)
+        layer = gridconv.init_up_layer(np.random.default_rng(3), cd, cu, [128], 10, [128], [128])
+        for mask in (msk, None):
+            want = gridconv_oracle.gridconv_up_layer(f_last, nebidx, cent, f_this, mask, layer)
+            up = gg.GridConvUp(layer, cuda_dev, precision=precision)
+            got = up(_t(f_last, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(f_this, cuda_dev),
+                     _t(mask, cuda_dev) if mask is not None else None).cpu().numpy()
+            assert np.array_equal(got[..., :4], want[..., :4])
+            assert _rel_err(got[..., 4:], want[..., 4:]) <= 1e-3, (B, Nd, O, cd, cu, mask is None)
+
+
+def test_seg_graph_encoder_decoder_head(gg, cuda_dev, oracle_mod):
+    """BASELINE config 3: the shipped ScanNet-8192 graph, encoder + decoder + head, against the oracle
+    chain: BallKNN indices bit-exact at every decoder level, logits within 1e-3."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import stack
+    cfg, up = stack.seg8192_shipped(), stack.UpCfg()
+    params = stack.init_seg_params(cfg, up, seed=2)
+    B = 2
+    data, npts = synth.make_batch(B, cfg.num_points, seed0=400, voxels=cfg.voxels)
+    net = stack.GridGcnSeg(cfg, up, params, cuda_dev)
+    logits = net(_t(data, cuda_dev), _t(npts, cuda_dev), keep_trace=True).cpu().numpy()
+    # oracle chain
+    tables, cents, nums, masks = [data], [data], [npts], [None]
+    table, loc, num = data, data, npts
+    for l, p in zip(cfg.layers, params["enc"]):
+        nebidx, _, cent, centmsk, num = oracle_mod.gridify(
+            loc, num, max_p_grid=l.max_p_grid, max_o_grid=l.max_o_grid, kernel_size=l.kernel_size,
+            loc=cfg.loc, coord_shift=cfg.coord_shift, voxel_size=(l.voxel_size,) * 3,
+            grid_size=(l.grid_size,) * 3)
+        table = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, p)
+        tables.append(table); cents.append(cent); nums.append(num); masks.append(centmsk)
+        loc = cent
+    f_last, nl = tables[-1], len(cfg.layers)
+    for i, p in enumerate(params["dec"]):
+        dn, upl = nl - i, nl - i - 1
+        l = cfg.layers[upl]
+        radius = l.voxel_size * up.kernel_size * 1.7 / 2
+        nebidx = oracle_mod.ball_knn(cents[upl][:, :, :3], cents[dn][:, :, :3], nums[dn], nums[upl],
+                                     k=up.max_p_grid, radius=radius)
+        assert np.array_equal(net.trace[i]["nebidx"].cpu().numpy(), nebidx), "decoder level %d indices" % i
+        mask = masks[upl] if i != nl - 1 else None
+        f_last = gridconv_oracle.gridconv_up_layer(f_last, nebidx, cents[upl], tables[upl], mask, p)
+        err = _rel_err(net.trace[i]["table"].cpu().numpy()[..., 4:], f_last[..., 4:])
+        assert err <= 1e-3, "decoder level %d: rel err %.3g" % (i, err)
+    want = gridconv_oracle.seg_head(f_last[..., 4:], params["head"])
+    assert logits.shape == (B, cfg.num_points, 21)
+    assert _rel_err(logits, want) <= 1e-3
