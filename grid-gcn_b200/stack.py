@@ -205,3 +205,58 @@ class GridGcnSeg:
         logits = self.head(f_last[:, :, 4:])
         self.trace = trace
         return logits
+
+
+# ---------------------------------------------------------------------------------------------------
+# Reference-compatible configuration: the keys of segmentation/configs/configs.yaml
+# ---------------------------------------------------------------------------------------------------
+def from_reference_config(conf, query="gridify"):
+    """Builds (StackCfg, UpCfg) from a dict with the reference's YAML keys
+    (segmentation/configs/configs.yaml:54-111): voxel_size_lst, grid_size_lst, max_p_grid_lst,
+    max_o_grid_lst, kernel_size_lst, stride_lst, pt_ele_dim, lidar_coord, loc_within, attfdim, relu,
+    num_points, up_max_p_grid_lst, up_kernel_size_lst, up_pt_ele_dim, up_center_dim, up_gcn_outDim,
+    up_attfdim, up_neigh_fetch.  Only what the fused kernels implement is accepted (cubic voxels/grids,
+    aggtype gcn, max pooling, localfdim 0, no context MLP, empty gcn_outDim, concat centre integration)."""
+    def cubic(v):
+        v = list(v)
+        if len(set(v)) != 1:
+            raise NotImplementedError("anisotropic voxel / grid sizes are not supported by StackCfg: %r" % (v,))
+        return v[0]
+    for key, ok in (("aggtype", ("gcn",)), ("agg", ("max_pooling", "max")), ("up_aggtype", ("gcn",)),
+                    ("up_agg", ("max_pooling", "max")), ("up_center_inte", ("concat",))):
+        if conf.get(key, ok[0]) not in ok:
+            raise NotImplementedError("%s=%r is not supported" % (key, conf.get(key)))
+    if conf.get("localfdim", 0) != 0 or conf.get("cntxt_mlp_lst") or conf.get("att_full"):
+        raise NotImplementedError("localfdim / cntxt_mlp_lst / att_full variants are not supported")
+    if any(len(d) for d in conf.get("gcn_outDim", [])):
+        raise NotImplementedError("encoder gcn_outDim MLPs are not supported")
+    n = len(conf["max_o_grid_lst"])
+    layers = [LayerCfg(float(cubic(conf["voxel_size_lst"][i])), int(cubic(conf["grid_size_lst"][i])),
+                       int(conf["max_o_grid_lst"][i]), int(conf["max_p_grid_lst"][i]),
+                       int(conf["kernel_size_lst"][i]), list(conf["pt_ele_dim"][i]),
+                       int(conf.get("stride_lst", [1] * n)[i])) for i in range(n)]
+    cfg = StackCfg(str(conf.get("save_model_prefix", "reference_config")), int(conf["num_points"]), layers,
+                   coord_shift=tuple(float(x) for x in conf.get("lidar_coord", (1.0, 1.0, 1.0))),
+                   loc=1 if conf.get("loc_within", True) else 0, attfdim=int(conf.get("attfdim", 10)),
+                   pre_relu=bool(conf.get("relu", True)), query=query)
+    up = None
+    if conf.get("up_max_p_grid_lst"):
+        def same(key):
+            v = conf[key]
+            if any(list(x) != list(v[0]) for x in v) if isinstance(v[0], (list, tuple)) else len(set(v)) != 1:
+                raise NotImplementedError("%s must be the same on every decoder level" % key)
+            return v[0]
+        up = UpCfg(max_p_grid=int(same("up_max_p_grid_lst")), kernel_size=int(same("up_kernel_size_lst")),
+                   pt_mlp_lst=tuple(same("up_pt_ele_dim")), center_dim=tuple(same("up_center_dim")),
+                   out_dim=tuple(same("up_gcn_outDim")), attfdim=int(conf.get("up_attfdim", 10)),
+                   neigh_fetch="ballknn" if conf.get("up_neigh_fetch", True) else "gridifyup")
+    return cfg, up
+
+
+def load_reference_yaml(path, query="gridify"):
+    """Reads a YAML file written for the reference (the ACTIVE, un-commented block) and returns
+    (StackCfg, UpCfg)."""
+    import yaml
+    with open(path) as f:
+        conf = yaml.safe_load(f)
+    return from_reference_config(conf, query)

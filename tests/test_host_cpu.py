@@ -57,3 +57,26 @@ def test_synthetic_clouds():
     assert frac.min() > 5e-5 and frac.max() < 1 - 5e-5  # away from voxel faces
     again, _ = synth.make_batch(3, 1024, seed0=0)
     assert np.array_equal(data, again)
+
+
+def test_reference_yaml_keys_are_understood():
+    import os
+    import pytest
+    here = os.path.dirname(os.path.abspath(__file__))
+    cfg, up = stack.load_reference_yaml(os.path.join(here, "golden", "seg8192_reference_keys.yaml"))
+    ship = stack.seg8192_shipped()
+    assert [(l.voxel_size, l.grid_size, l.max_o_grid, l.max_p_grid, l.kernel_size, list(l.pt_mlp_lst))
+            for l in cfg.layers] == \
+           [(l.voxel_size, l.grid_size, l.max_o_grid, l.max_p_grid, l.kernel_size, list(l.pt_mlp_lst))
+            for l in ship.layers]
+    assert cfg.num_points == 8192 and cfg.loc == 1 and cfg.attfdim == 10 and cfg.pre_relu
+    assert (up.max_p_grid, up.kernel_size, up.neigh_fetch) == (5, 3, "ballknn")
+    assert tuple(up.pt_mlp_lst) == (128,) and tuple(up.center_dim) == (128,) and tuple(up.out_dim) == (128,)
+    ref = "/root/reference/segmentation/configs/configs.yaml"
+    if os.path.exists(ref):  # the reference's own file (build container only)
+        rcfg, rup = stack.load_reference_yaml(ref)
+        assert [l.max_o_grid for l in rcfg.layers] == [1024, 256, 24] and rup.max_p_grid == 5
+    with pytest.raises(NotImplementedError):
+        stack.from_reference_config(dict(max_o_grid_lst=[8], voxel_size_lst=[[0.1, 0.2, 0.1]],
+                                         grid_size_lst=[[4, 4, 4]], max_p_grid_lst=[4], kernel_size_lst=[3],
+                                         pt_ele_dim=[[8]], num_points=16))
