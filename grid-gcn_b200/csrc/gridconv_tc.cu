@@ -6,24 +6,33 @@
 //
 //  * Feature MLP hoisting.  For layers with input features (has_feats, localfdim == 0) the feature
 //    MLP of verts_pair_func (:135) is a function of the gathered neighbour ROW only, so
-//    MLP(gather(table)) == gather(MLP(table)): kernel A (`point_mlp_tc_kernel`) applies it once per
-//    source point (B*Nprev rows) instead of once per edge (B*O*K rows, 16x more at K=64), writing a
-//    transformed table F.  The per-edge work that remains is what really depends on the
+//    MLP(gather(table)) == gather(MLP(table)): kernel A applies it once per source point (B*Nprev
+//    rows) instead of once per edge (B*O*K rows, 16x more at K=64), writing a transformed table F.
+//    Kernel A has two variants: `point_mlp_rows_tc_kernel` (D[row, ch], epilogue thread = row, used
+//    when a [128 x K] hi/lo activation image fits, K <= 128) and `point_mlp_tc_kernel` (D^T[ch, row],
+//    64-row tiles, for K = 256).  The per-edge work that remains is what really depends on the
 //    (centre, neighbour) pair: the attention MLP, the product and the max pool.
-//  * Kernel B (`edge_tc_kernel`), one persistent CTA per SM slot, tiles of 128 edges:
-//      gather neighbour xyz (128-bit loads) -> geo / att_vec in registers -> K-major fp32 operand
-//      images in shared memory -> hidden stages as D[edge, ch] (thread = edge row in the TMEM
-//      epilogue) -> last attention stage (and, for the first layer, last feature stage) TRANSPOSED,
-//      D^T[ch, edge] = W * H^T, so that the max over a centre's K edges is a run of TMEM columns in
-//      ONE thread's registers: no shuffles, no shared-memory transpose -> relu(att) * feat, max,
-//      pre-ReLU, centre mask -> one coalesced [cent | feats] row per centre.
-//  * fp32 parity on tf32 tensor cores: TF32X3 splits every operand into hi + lo tf32 parts and
-//    issues lo*hi, hi*lo, hi*hi into the same TMEM accumulator (error ~2^-21, fp32-class); TF32
-//    issues hi*hi only.
+//  * Kernel B (`edge_tc_kernel<NSPLIT, FIRST>`), persistent CTAs, tiles of 128 edges:
+//      gather phase (thread = edge; index / row / centre prefetched a tile ahead): neighbour xyz with
+//      one 128-bit load -> geo / att_vec in registers -> the tiny-K stages on the CUDA cores in exact
+//      fp32 (attention stage 0, K <= 10; first-layer feature stage 0, K = 3: a tensor-core round trip
+//      would cost more than the 11 FMAs) -> hi/lo K-major operand images in shared memory;
+//      first layer only: the remaining hidden feature stage on the tensor core, D[edge, ch];
+//      last attention stage (and first-layer last feature stage) TRANSPOSED, D^T[ch, edge] = W * H^T:
+//      the K edges of a centre are K consecutive TMEM columns of ONE lane, so the max pool is a run
+//      of FMNMX in one thread's registers -- no shuffles, no shared-memory transpose -- and thread =
+//      channel makes the output store coalesced; relu(att) * feat (feat from TMEM for the first layer,
+//      gathered from F otherwise), pre-ReLU, centre mask, one [cent | feats] row per centre.
+//  * fp32 parity on tf32 tensor cores: TF32X3 splits every operand into hi + lo and issues lo*hi,
+//    hi*lo, hi*hi into the same TMEM accumulator (error ~2^-21, fp32-class).  Activations use the
+//    measured truncation of the low 13 mantissa bits by the tensor core (hi = raw bits, lo = v -
+//    trunc(v): 2 instructions; tc_common.cuh split_op, pinned by tests/test_gpu_tc.py); weights are
+//    packed once with round-to-nearest parts.  TF32 issues hi*hi only (speed option, held to 1e-2).
 //
 // Synchronisation is deliberately lock-step (one __syncthreads per phase, one mbarrier for "MMAs of
-// this stage retired", full/empty mbarriers on the weight ring); overlap comes from co-resident
-// CTAs.  Every mbarrier wait is bounded and traps instead of hanging.
+// this stage retired", full/empty mbarriers on the weight ring); overlap comes from 2-3 co-resident
+// CTAs per SM (TMEM: 256 columns for the first layer, 128 otherwise).  Every mbarrier wait is bounded
+// and traps instead of hanging.  `gridgcn_debug_phase_buffer` exposes per-phase cycle counters.
 #include "gridconv_common.cuh"
 #include "tc_common.cuh"
 

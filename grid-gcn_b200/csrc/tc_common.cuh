@@ -156,7 +156,7 @@ __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
 }
 
 // Cheaper split for the 3-pass mode, relying on the MEASURED behaviour of tcgen05 kind::tf32 on sm_100a:
-// the tensor core TRUNCATES the low 13 mantissa bits of an fp32 operand (tools_tf32_probe.py: max
+// the tensor core TRUNCATES the low 13 mantissa bits of an fp32 operand (tools/tf32_probe.py: max
 // |D - trunc-model| = 9e-7 vs 1.4e-2 for a round-to-nearest model; tests/test_gpu_tc.py pins it).
 // So hi is the raw value (the hardware reads trunc(v)) and lo = v - trunc(v), exact in fp32; the hardware
 // truncates lo to its top 11 bits, leaving |v - hi_eff - lo_eff| <= 2^-21 |v|.  2 instructions instead of 5.

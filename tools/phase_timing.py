@@ -1,6 +1,6 @@
 """Debug helper: per-phase cycle breakdown of the per-edge tensor-core kernel (CTA 0), per layer."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import gridgcn_b200 as gg
 from gridgcn_b200 import stack, synth

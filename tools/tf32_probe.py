@@ -1,6 +1,6 @@
 """Probe: how does tcgen05 kind::tf32 treat the low 13 mantissa bits of fp32 operands?"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import gridgcn_b200 as gg
 dev = torch.device("cuda:0")
