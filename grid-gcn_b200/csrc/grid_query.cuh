@@ -150,71 +150,148 @@ gridify_query_kernel(const float4 *__restrict__ data, GridParams g, const int *_
 // (value, voxel order, id) orders exactly like (value, arrival sequence number): the stable order the
 // reference's strict-< insertion produces (gridifyknn.cu:288-298).
 // ------------------------------------------------------------------------------------------------
-template <int CAP>
-struct TopP {
-    unsigned long long *keys;
-    int fill;
-    unsigned idmask;  // (1 << idbits) - 1
-
-    __device__ __forceinline__ int id_of(int i) const { return (int)((unsigned)keys[i] & idmask); }
-
-    __device__ __forceinline__ void sort(int lane) {
-        int n = 2;
-        while (n < fill) n <<= 1;
-        for (int i = fill + lane; i < n; i += 32) keys[i] = ~0ull;
-        __syncwarp();
-        for (int k = 2; k <= n; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int p = lane; p < (n >> 1); p += 32) {
+// Fully unrolled bitonic networks over shared memory (one warp, 64-bit keys).
+template <int N, bool DESC>
+__device__ __forceinline__ void bitonic_sort(unsigned long long *keys, int lane) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int p0 = 0; p0 < (N >> 1); p0 += 32) {
+                const int p = p0 + lane;
+                if ((N >> 1) >= 32 || p < (N >> 1)) {
                     const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
                     const int q = i | j;
                     const unsigned long long a = keys[i], c = keys[q];
-                    const bool up = (i & k) == 0;
-                    if ((a > c) == up) {
+                    const bool asc = ((i & k) == 0) != DESC;
+                    if ((a > c) == asc) {
                         keys[i] = c;
                         keys[q] = a;
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
         }
     }
+}
+// The last log2(N) stages only: sorts a bitonic sequence ascending.
+template <int N>
+__device__ __forceinline__ void bitonic_merge(unsigned long long *keys, int lane) {
+#pragma unroll
+    for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int p0 = 0; p0 < (N >> 1); p0 += 32) {
+            const int p = p0 + lane;
+            if ((N >> 1) >= 32 || p < (N >> 1)) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                const int q = i | j;
+                const unsigned long long a = keys[i], c = keys[q];
+                if (a > c) {
+                    keys[i] = c;
+                    keys[q] = a;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+template <bool DESC>
+__device__ __forceinline__ void bitonic_sort_n(unsigned long long *keys, int n, int lane) {
+    switch (n) {
+        case 2: bitonic_sort<2, DESC>(keys, lane); break;
+        case 4: bitonic_sort<4, DESC>(keys, lane); break;
+        case 8: bitonic_sort<8, DESC>(keys, lane); break;
+        case 16: bitonic_sort<16, DESC>(keys, lane); break;
+        case 32: bitonic_sort<32, DESC>(keys, lane); break;
+        case 64: bitonic_sort<64, DESC>(keys, lane); break;
+        case 128: bitonic_sort<128, DESC>(keys, lane); break;
+        case 256: bitonic_sort<256, DESC>(keys, lane); break;
+        default: break;  // n <= 1
+    }
+}
+
+template <int CAP>
+struct TopP {
+    unsigned long long *keys;
+    int fill;         // after a flush: keys[0, fill) are the best min(P, seen) keys, ascending
+    unsigned idmask;  // (1 << idbits) - 1
+    int tail;         // candidates appended since the last flush
+    bool merged;      // a flush has happened: the tail grows downwards from keys[CAP - 1]
+
+    __device__ __forceinline__ int id_of(int i) const { return (int)((unsigned)keys[i] & idmask); }
+    __device__ __forceinline__ int room() const { return CAP - fill - tail; }
+    __device__ __forceinline__ int slot(int f) const { return merged ? CAP - 1 - f : f; }
+
+    // Sort what has been collected and keep the best P.  First flush: plain ascending sort of the
+    // (power-of-two padded) buffer.  Later flushes: the kept prefix is already sorted, so only the
+    // new tail is sorted (descending, at the top end of the buffer), the gap is padded with +inf --
+    // ascending prefix, +inf plateau, descending tail is a bitonic sequence -- and one log2(CAP)
+    // merge pass finishes the job.
     __device__ __forceinline__ void flush(int P, int lane) {
-        if (fill > 1) sort(lane);
-        fill = min(fill, P);
+        if (!merged) {
+            int n = 1;
+            while (n < tail) n <<= 1;
+            for (int i = tail + lane; i < n; i += 32) keys[i] = ~0ull;
+            __syncwarp();
+            bitonic_sort_n<false>(keys, n, lane);
+            fill = min(tail, P);
+        } else if (tail > 0) {
+            int m = 1;
+            while (m < tail) m <<= 1;
+            if (m <= CAP - fill) {
+                for (int i = fill + lane; i < CAP - tail; i += 32) keys[i] = ~0ull;
+                __syncwarp();
+                bitonic_sort_n<true>(keys + (CAP - m), m, lane);
+                bitonic_merge<CAP>(keys, lane);
+            } else {
+                for (int i = fill + lane; i < CAP - tail; i += 32) keys[i] = ~0ull;
+                __syncwarp();
+                bitonic_sort<CAP, false>(keys, lane);
+            }
+            fill = min(fill + tail, P);
+        }
+        tail = 0;
+        merged = true;
     }
 };
 
 // Append the candidates of up to 32 voxels (one per lane: segment start `s`, `amount` ids, arrival order
-// `vorder` of the voxel) in lane order.  `make_key(id, vorder)` builds the 64-bit key.
+// `vorder` of the voxel).  The candidates of the batch are numbered flat, 0 .. total-1, and dealt to the
+// lanes round-robin -- every lane does the same amount of work whatever the voxel populations are; a
+// candidate finds its voxel by a 5-step binary search over the lanes' inclusive prefix (shuffles).
+// When the buffer fills it is flushed (sorted, best P kept) and filling continues.
 template <int CAP, class KeyFn>
 __device__ __forceinline__ void append_batch(TopP<CAP> &tp, const int *sorted, int s, int amount,
                                              int P, int lane, int vorder, int &seen, KeyFn make_key) {
-    int incl = warp_incl_scan(amount, lane);
-    int pfx = incl - amount;
-    const int batch_total = __shfl_sync(kFull, incl, 31);
-    int base = 0;
-    bool done = amount == 0;
-    while (__any_sync(kFull, !done)) {
-        int room = CAP - tp.fill;
-        bool can = !done && (pfx - base + amount <= room);
-        if (!__any_sync(kFull, can)) {  // CAP >= 2P guarantees progress after a flush
-            tp.flush(P, lane);
-            continue;
-        }
-        if (can) {
-            int at = tp.fill + pfx - base;
-            for (int j = 0; j < amount; j++) tp.keys[at + j] = make_key(sorted[s + j], vorder);
-            done = true;
-        }
-        int mine = can ? amount : 0;
+    const int incl = warp_incl_scan(amount, lane);
+    const int total = __shfl_sync(kFull, incl, 31);
+    int done = 0;
+    while (done < total) {  // warp-uniform
+        if (tp.room() == 0) tp.flush(P, lane);  // CAP >= 2P: a flush always frees at least P slots
+        const int take = min(tp.room(), total - done);
+        for (int f0 = 0; f0 < take; f0 += 32) {
+            const int f = done + f0 + lane;
+            const bool act = f0 + lane < take;
+            int v = 0;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(kFull, mine, d);
-        tp.fill += mine;
-        base += mine;
+            for (int st = 16; st > 0; st >>= 1) {
+                const int t = __shfl_sync(kFull, incl, v + st - 1);
+                if (t <= f) v += st;
+            }
+            v = min(v, 31);
+            const int v_incl = __shfl_sync(kFull, incl, v), v_amount = __shfl_sync(kFull, amount, v);
+            const int v_s = __shfl_sync(kFull, s, v), v_order = __shfl_sync(kFull, vorder, v);
+            if (act) {
+                const int j = f - (v_incl - v_amount);
+                tp.keys[tp.slot(tp.tail + f0 + lane)] = make_key(sorted[v_s + j], v_order);
+            }
+        }
+        tp.tail += take;
+        done += take;
         __syncwarp();
     }
-    seen += batch_total;
+    seen += total;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -260,14 +337,29 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
         const float ux = (float)(((double)c0 + 0.5) * (double)g.voxel[0]);
         const float uy = (float)(((double)c1 + 0.5) * (double)g.voxel[1]);
         const float uz = (float)(((double)c2 + 0.5) * (double)g.voxel[2]);
-        TopP<CAP> tp{s_keys[warp], 0, (1u << idbits) - 1u};
+        TopP<CAP> tp{s_keys[warp], 0, (1u << idbits) - 1u, 0, false};
         int seq = 0, vbase = 0;
         auto key_of = [&](int id, int vorder) {
             float4 q = __ldg(pts + id);
             float dst = dist2(ux, uy, uz, q.x, q.y, q.z, fma);
             return ((unsigned long long)__float_as_uint(dst) << 32) | ((unsigned)vorder << idbits) | (unsigned)id;
         };
-        for (int layer = 0; layer < (ks + 1) / 2; layer++) {
+        int first_layer = 0;
+        if (ks >= 3) {
+            // shells 0 and 1 in one pass over the 27 voxels around the centre (constant divisors, one
+            // table lookup per lane).  The centre voxel is shell 0 (arrival order 0); the other 26 are
+            // shell 1 in loop order (arrival order 1 + tt) and only count when shell 0 alone holds
+            // fewer than P candidates (gridifyknn.cu:304-305).
+            int s = 0, e = 0;
+            if (lane < 27)
+                voxel_segment(t, g, lane % 3 - 1 + c2, (lane / 3) % 3 - 1 + c1, lane / 9 - 1 + c0, s, e);
+            int amount = min(P, e - s);
+            if (__shfl_sync(kFull, amount, 13) >= P && lane != 13) amount = 0;
+            append_batch<CAP>(tp, t.sorted, s, amount, P, lane, lane == 13 ? 0 : 1 + lane, seq, key_of);
+            vbase = 28;
+            first_layer = 2;
+        }
+        for (int layer = first_layer; layer < (ks + 1) / 2 && seq < P; layer++) {
             const int n1 = 2 * layer + 1, combos = n1 * n1 * n1;
             for (int t0 = 0; t0 < combos; t0 += 32) {
                 int tt = t0 + lane, s = 0, e = 0;
@@ -281,8 +373,7 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
             }
             vbase += combos;
             // gridifyknn.cu:304-305: need_P -= amount_layer; stop once the cumulative number of
-            // candidates (== seq) reaches P
-            if (seq >= P) break;
+            // candidates (== seq) reaches P (the loop condition)
         }
         tp.flush(P, lane);
         __syncwarp();
@@ -337,7 +428,7 @@ gridify_up_query_kernel(const float4 *__restrict__ updata, const int *__restrict
             lin = voxel_of(p.x, p.y, p.z, g);
         }
         long long count = 0;
-        TopP<CAP> tp{s_keys[warp], 0, 0xffffffffu};  // key = id
+        TopP<CAP> tp{s_keys[warp], 0, 0xffffffffu, 0, false};  // key = id
         if (lin >= 0) {
             const CloudTable t = cloud_table(ws_base, L, b);
             int c2, c1, c0;
