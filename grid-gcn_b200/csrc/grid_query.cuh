@@ -57,12 +57,11 @@ __device__ __forceinline__ float weight_sum(const float4 *pts, const int *row, i
         s += iw;
         a += iw < 0 ? -(long long)iw : iw;
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        s += __shfl_xor_sync(kFull, s, d);
-        a += __shfl_xor_sync(kFull, a, d);
-    }
-    if (a < (1LL << 24)) return (float)s;
+    // warp totals with two REDUX instructions: clamp the per-lane |.| sums to 2^24 (32 lanes: < 2^30); if
+    // the clamped total is below 2^24 no lane was clamped, the total is exact and the signed sum fits
+    const unsigned at = __reduce_add_sync(kFull, (unsigned)min(a, 1LL << 24));
+    const int st = __reduce_add_sync(kFull, (int)s);
+    if (at < (1u << 24)) return (float)st;
     float f = 0.f;
     if (lane == 0)
         for (int i = 0; i < n; i++) f = __fadd_rn(f, (float)(int)__ldg(&pts[row[i]].w));
