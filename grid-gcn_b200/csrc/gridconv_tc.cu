@@ -1007,6 +1007,382 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kernel B', compact first-layer variant (Cout <= 64, K | 64, 3-pass mode): same math as
+// edge_tc_kernel<3, true>, re-laid-out so that THREE CTAs fit on an SM (the first layer is latency bound:
+// more resident tiles is what speeds it up; profiles/README.md).
+//   * M = 64 MMAs: the 64 feature channels F and the 64 attention channels G share ONE 128-column TMEM
+//     tile.  A cta_group::1 M=64 accumulator occupies lanes 32q..32q+15 of every quadrant q (row 16q+i ->
+//     lane 32q+i); issued with lane offset 16 it occupies lanes 32q+16..32q+31 (tools/m64_probe.cu).  F goes
+//     to the low half-warps, G to the high ones: lane l and lane l^16 hold the same channel, the product
+//     needs one SHFL, and all four epilogue warps are busy (the 128-row variant idles two).
+//   * TMEM: 128 columns (F|G) + a second allocation for the hidden-stage accumulators (32): 160 <= 512/3.
+//   * shared memory: the attention operand image aliases the lo half of the feature image (attention stage 1
+//     is issued first and has retired before the feature path writes its lo parts), and the last-stage weight
+//     images keep only their 64 live rows: ~66 KB per CTA instead of ~108 KB.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_raw(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+struct First64Layout {  // byte offsets inside dynamic shared memory (host and device agree through this)
+    int kx, kh, kf0;
+    uint32_t xf_lo, wres, wff_hi, wff_lo, wa1_hi, wa1_lo, wa0, wf0, bias, total;
+};
+__host__ __device__ inline First64Layout first64_layout(const TcParams &p) {
+    First64Layout L;
+    int kx = pad_to(p.f0_cout, 8);
+    for (int s = 0; s < p.nfh; s++) kx = max(kx, max(p.fh[s].Kp, pad_to(p.fh[s].Cout, 8)));
+    kx = max(kx, p.ff.Kp);
+    L.kx = kx;
+    L.kh = p.a1.Kp;
+    L.kf0 = pad_to(p.f0_cout, 8);
+    L.xf_lo = (uint32_t)(kx / 4) * 2048u;
+    L.wres = 2u * L.xf_lo;
+    uint32_t o = L.wres;
+    for (int s = 0; s < p.nfh; s++) o += 2u * p.fh[s].Np * p.fh[s].Kp * 4u;
+    L.wff_hi = o;
+    L.wff_lo = L.wff_hi + (uint32_t)(p.ff.Kp / 4) * 1024u;
+    L.wa1_hi = L.wff_lo + (uint32_t)(p.ff.Kp / 4) * 1024u;
+    L.wa1_lo = L.wa1_hi + (uint32_t)(L.kh / 4) * 1024u;
+    L.wa0 = L.wa1_lo + (uint32_t)(L.kh / 4) * 1024u;
+    L.wf0 = L.wa0 + (uint32_t)L.kh * 12u * 4u;
+    L.bias = L.wf0 + (uint32_t)L.kf0 * 4u * 4u;
+    L.total = L.bias + (uint32_t)p.nfh * 128u * 4u;
+    return L;
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 3)
+edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, int hid_cols) {
+    static_assert(NSPLIT == 3, "compact first-layer kernel: 3-pass mode only");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_mma_s;
+    __shared__ uint32_t tmem_base_s[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const ConvParams &c = p.c;
+    const int K = c.K, C = c.Cout;
+    constexpr uint32_t LBO = kTileRows * 16;  // 128-row images: panel = 2 KB
+    constexpr uint32_t WLBO = 64 * 16;        // 64-row weight images: panel = 1 KB
+    const First64Layout L = first64_layout(p);
+    const int kh = L.kh, kf0 = L.kf0;
+    uint8_t *xf_hi = smem, *xf_lo = smem + L.xf_lo;
+    uint8_t *xa_hi = xf_lo, *xa_lo = xa_hi + (size_t)(kh / 4) * LBO;  // alias (2 * kh <= kx, host-checked)
+    uint8_t *wres = smem + L.wres;
+    float *wa0_s = reinterpret_cast<float *>(smem + L.wa0);
+    float *wf0_s = reinterpret_cast<float *>(smem + L.wf0);
+    float *bias_s = reinterpret_cast<float *>(smem + L.bias);
+    uint64_t *bar_mma = &bar_mma_s;
+
+    if (warp == 0) {
+        tmem_alloc_raw(&tmem_base_s[0], 128);
+        tmem_alloc_raw(&tmem_base_s[1], (uint32_t)hid_cols);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_init_fence();
+    }
+    {   // resident operands
+        size_t off = 0;
+        for (int s = 0; s < p.nfh; s++) {
+            const TcStage &st = p.fh[s];
+            const int n4 = 2 * st.Np * st.Kp / 4;
+            const float4 *src = reinterpret_cast<const float4 *>(p.packed + st.w_off);
+            float4 *dst = reinterpret_cast<float4 *>(wres + off);
+            for (int i = tid; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
+            off += (size_t)n4 * 16;
+        }
+        // rows 0..63 of every [128 x 4] panel of the packed transposed-stage images (chunk 0)
+        auto load_compact = [&](const TcStage &st, uint32_t dst_hi, uint32_t dst_lo) {
+            const int per_img = (st.Kp / 4) * 256;
+            for (int i = tid; i < 2 * per_img; i += kTcThreads) {
+                const int img = i / per_img, r = i % per_img, P = r >> 8, w = r & 255;
+                const int t = P / (kSliceK / 4), pp = P % (kSliceK / 4);
+                const int kw = min(kSliceK, st.Kp - t * kSliceK);
+                const float *src = p.packed + st.w_off + (size_t)t * 2 * 128 * kSliceK + (img ? 128 * kw : 0) +
+                                   pp * 512 + w;
+                reinterpret_cast<float *>(smem + (img ? dst_lo : dst_hi))[r] = __ldg(src);
+            }
+        };
+        load_compact(p.ff, L.wff_hi, L.wff_lo);
+        load_compact(p.a1, L.wa1_hi, L.wa1_lo);
+        for (int i = tid; i < kh * 12; i += kTcThreads) {
+            const int j = i / 12, q = i % 12;
+            float v = 0.f;
+            if (j < p.a0_cout) {
+                if (q < p.a0_cin) v = __ldg(p.a0_w + (size_t)j * p.a0_cin + q);
+                else if (q == 10) v = __ldg(p.a0_b + j);
+            }
+            wa0_s[i] = v;
+        }
+        for (int i = tid; i < kf0 * 4; i += kTcThreads) {
+            const int j = i / 4, q = i % 4;
+            wf0_s[i] = j < p.f0_cout ? (q < 3 ? __ldg(p.f0_w + (size_t)j * 3 + q) : __ldg(p.f0_b + j)) : 0.f;
+        }
+        for (int i = tid; i < p.nfh * 128; i += kTcThreads) {
+            const int st = i >> 7, j = i & 127;
+            bias_s[i] = j < p.fh[st].Cout ? __ldg(p.fh[st].bias + j) : 0.f;
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_fg = tmem_base_s[0], tmem_h = tmem_base_s[1];
+
+    uint32_t mma_phase = 0;
+    const long long rows_total = (long long)c.B * c.Nprev;
+    const long long centers_total = (long long)c.B * c.O;
+    const int row_w = 4 + c.Cin;
+    const int out_w = 4 + C;
+    const int attfdim = c.attfdim, Nprev = c.Nprev, O = c.O;
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+    // final epilogue role of this thread: TMEM lane = 32*warp + lane; low half-warp: feature channel, high: attention
+    const bool is_g = lane >= 16;
+    const int ch = 16 * (warp & 3) + (lane & 15);
+    const bool chv = warp < 4 && ch < C;
+    const float bias_fg = chv ? __ldg((is_g ? p.a1.bias : p.ff.bias) + ch) : 0.f;
+    const float pre_floor = c.pre_relu ? 0.f : -3.402823466e+38f;
+
+    const int my_cl = tid / K, my_slot = tid - my_cl * K;
+    bool pf_valid = false;
+    int pf_idx = 0;
+    long long pf_center = 0;
+    float4 pf_head = make_float4(0.f, 0.f, 0.f, 0.f), pf_cent = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_row = [&]() {
+        if (pf_valid) {
+            const int b = (int)(pf_center / O);
+            const long long row = take_row(pf_idx, b, Nprev, rows_total);
+            const float *src = c.table + row * row_w;
+            if ((row_w & 3) == 0) pf_head = __ldg(reinterpret_cast<const float4 *>(src));
+            else pf_head = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
+            pf_cent = __ldg(c.cent + pf_center);
+        }
+    };
+    if (warp < 4 && blockIdx.x < num_tiles) {
+        const long long center = (long long)blockIdx.x * cpt + my_cl;
+        pf_valid = my_cl < cpt && center < centers_total;
+        pf_center = center;
+        if (pf_valid) pf_idx = __ldg(c.nebidx + center * K + my_slot);
+        fetch_row();
+    }
+    const uint32_t idesc64 = tc::make_idesc_tf32(64, kTileRows);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long c_base = (long long)tile * cpt;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        // ---- gather + attention stage 0 (thread = edge row) ----
+        if (warp < 4) {
+            float att[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) att[i] = 0.f;
+            att[10] = 1.f;
+            if (pf_valid) att_vector(attfdim, pf_cent, pf_head.x, pf_head.y, pf_head.z, att, dx, dy, dz);
+            {
+                const long long ncenter = (long long)(tile + gridDim.x) * cpt + my_cl;
+                pf_valid = (tile + (int)gridDim.x) < num_tiles && my_cl < cpt && ncenter < centers_total;
+                pf_center = ncenter;
+                if (pf_valid) pf_idx = __ldg(c.nebidx + ncenter * K + my_slot);
+            }
+            for (int g = 0; g < kh / 4; g++) {
+                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 48);
+                float hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 w0 = w4[i * 3], w1 = w4[i * 3 + 1], w2 = w4[i * 3 + 2];
+                    float acc = w2.z;
+                    acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
+                    acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
+                    acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
+                    acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
+                    acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
+                    tc::split_op<NSPLIT>(fmaxf(acc, 0.f), hi[i], lo[i]);
+                }
+                const uint32_t off = row_off + (uint32_t)g * LBO;
+                *reinterpret_cast<float4 *>(xa_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(xa_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        // ---- attention stage 1 -> G (lanes 32q+16..31), issued now, needed only by the final epilogue ----
+        if (warp == 4) {
+            if (lane == 0) {
+                const uint32_t d = tmem_fg + (16u << 16);
+                uint32_t acc = 0;
+                for (int ks = 0; ks < kh / 8; ks++) {
+                    const uint64_t ah = tc::make_sdesc(tc::smem_u32(smem + L.wa1_hi) + ks * 2 * WLBO, WLBO);
+                    const uint64_t al = tc::make_sdesc(tc::smem_u32(smem + L.wa1_lo) + ks * 2 * WLBO, WLBO);
+                    const uint64_t bh = tc::make_sdesc(tc::smem_u32(xa_hi) + ks * 2 * LBO, LBO);
+                    const uint64_t bl = tc::make_sdesc(tc::smem_u32(xa_lo) + ks * 2 * LBO, LBO);
+                    tc::mma_tf32(d, al, bh, idesc64, acc);
+                    tc::mma_tf32(d, ah, bl, idesc64, 1);
+                    tc::mma_tf32(d, ah, bh, idesc64, 1);
+                    acc = 1;
+                }
+                tc::mma_commit(bar_mma);
+            }
+            __syncwarp();
+        }
+        // ---- feature stage 0 (K = 3) on the CUDA cores: hi parts while the attention MMAs run, lo parts
+        //      (whose image the attention operand aliases) once they have retired ----
+        if (warp < 4) {
+            for (int g = 0; g < kf0 / 4; g++) {
+                const float4 *w4 = reinterpret_cast<const float4 *>(wf0_s + g * 16);
+                float v[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 w = w4[i];
+                    v[i] = fmaxf(fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, w.w))), 0.f);
+                }
+                *reinterpret_cast<float4 *>(xf_hi + row_off + (uint32_t)g * LBO) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        wait_bar(bar_mma, mma_phase);
+        mma_phase ^= 1;
+        tc::fence_after_sync();
+        if (warp < 4) {
+            for (int g = 0; g < kf0 / 4; g++) {
+                const float4 *w4 = reinterpret_cast<const float4 *>(wf0_s + g * 16);
+                float lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 w = w4[i];
+                    float hi;
+                    tc::split_op<NSPLIT>(fmaxf(fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, w.w))), 0.f), hi, lo[i]);
+                }
+                *reinterpret_cast<float4 *>(xf_lo + row_off + (uint32_t)g * LBO) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        // ---- hidden feature stages on the tensor core, D[edge, ch] in the second TMEM allocation ----
+        {
+            size_t woff = 0;
+            for (int s = 0; s < p.nfh; s++) {
+                const TcStage &st = p.fh[s];
+                if (warp == 4) {
+                    if (lane == 0) {
+                        run_plain_stage<NSPLIT>(st, tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO,
+                                                tc::smem_u32(wres + woff), tmem_h);
+                        tc::mma_commit(bar_mma);
+                    }
+                    __syncwarp();
+                }
+                woff += (size_t)2 * st.Np * st.Kp * 4;
+                wait_bar(bar_mma, mma_phase);
+                mma_phase ^= 1;
+                tc::fence_after_sync();
+                if (warp < 4) {
+                    const int kp_next = s + 1 < p.nfh ? p.fh[s + 1].Kp : p.ff.Kp;
+                    plain_epilogue<NSPLIT>(st, tmem_h + ((uint32_t)(warp * 32) << 16), row_off, xf_hi, xf_lo, LBO,
+                                           kp_next, bias_s + s * 128);
+                }
+                tc::fence_async_smem();
+                tc::fence_before_sync();
+                __syncthreads();
+                tc::fence_after_sync();
+            }
+        }
+        // ---- last feature stage -> F (lanes 32q..32q+15) ----
+        if (warp == 4) {
+            if (lane == 0) {
+                uint32_t acc = 0;
+                for (int ks = 0; ks < p.ff.Kp / 8; ks++) {
+                    const uint64_t ah = tc::make_sdesc(tc::smem_u32(smem + L.wff_hi) + ks * 2 * WLBO, WLBO);
+                    const uint64_t al = tc::make_sdesc(tc::smem_u32(smem + L.wff_lo) + ks * 2 * WLBO, WLBO);
+                    const uint64_t bh = tc::make_sdesc(tc::smem_u32(xf_hi) + ks * 2 * LBO, LBO);
+                    const uint64_t bl = tc::make_sdesc(tc::smem_u32(xf_lo) + ks * 2 * LBO, LBO);
+                    tc::mma_tf32(tmem_fg, al, bh, idesc64, acc);
+                    tc::mma_tf32(tmem_fg, ah, bl, idesc64, 1);
+                    tc::mma_tf32(tmem_fg, ah, bh, idesc64, 1);
+                    acc = 1;
+                }
+                tc::mma_commit(bar_mma);
+            }
+            __syncwarp();
+        }
+        if (warp < 4) fetch_row();  // next tile's table row + centre, under the MMAs
+        wait_bar(bar_mma, mma_phase);
+        mma_phase ^= 1;
+        tc::fence_after_sync();
+        // ---- final epilogue: lane pair (l, l^16) = (feature, attention) of one channel.  The low half-warp
+        //      reduces columns [0, 64), the high one columns [64, 128): each sends the other the half it does
+        //      not reduce, so one shuffle serves two columns.  K | 64: no centre straddles column 64. ----
+        if (warp < 4) {
+            const uint32_t taddr = tmem_fg + ((uint32_t)(warp * 32) << 16);
+            float *out_ch = c.out + 4 + ch;
+            float m = -3.402823466e+38f;
+            int pos = 0, cl = is_g ? (cpt >> 1) : 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                uint32_t a[16], b[16];
+                tc::tmem_ld16(taddr + c0, a);
+                tc::tmem_ld16(taddr + 64 + c0, b);
+                tc::tmem_ld_wait();
+                float pr[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float xa = fmaxf(__uint_as_float(a[i]) + bias_fg, 0.f);
+                    const float xb = fmaxf(__uint_as_float(b[i]) + bias_fg, 0.f);
+                    const float got = __shfl_xor_sync(0xffffffffu, is_g ? xa : xb, 16);
+                    pr[i] = (is_g ? xb : xa) * got;  // :167 att * feats
+                }
+                if ((K & 15) == 0) {
+                    float mm = pr[0];
+#pragma unroll
+                    for (int i = 1; i < 16; i++) mm = fmaxf(mm, pr[i]);
+                    m = fmaxf(m, mm);
+                    pos += 16;
+                    if (pos == K) {
+                        const long long center = c_base + cl;
+                        if (chv && center < centers_total)
+                            out_ch[center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
+                        pos = 0;
+                        cl++;
+                        m = -3.402823466e+38f;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        m = fmaxf(m, pr[i]);
+                        if (++pos == K) {
+                            const long long center = c_base + cl;
+                            if (chv && center < centers_total)
+                                out_ch[center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
+                            pos = 0;
+                            cl++;
+                            m = -3.402823466e+38f;
+                        }
+                    }
+                }
+            }
+            for (int i = tid; i < cpt * 4; i += 128) {  // centre columns of the output rows
+                const long long center = c_base + i / 4;
+                if (center < centers_total)
+                    c.out[center * out_w + (i & 3)] = __ldg(reinterpret_cast<const float *>(c.cent + center) + (i & 3));
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc::tmem_dealloc(tmem_fg, 128);
+        tc::tmem_dealloc(tmem_h, (uint32_t)hid_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side: stage tables, packing, launches.
 // ------------------------------------------------------------------------------------------------
 static void make_stage(TcStage &s, int transposed, int cin, int cout, const float *bias, long long &off) {
@@ -1110,6 +1486,16 @@ static void kernel_b_sequence(const TcParams &p, int &n_slices, size_t &seq_byte
 
 constexpr size_t kSmemCap = 224 * 1024;  // dynamic part; static barriers/index cache use < 3 KB of the 227 KB
 
+static void launch_first64(const TcParams &p, int blocks, size_t smem, cudaStream_t st, int tiles, int cpt,
+                           int hid) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(edge_first64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+        attr_set = true;
+    }
+    edge_first64_kernel<3><<<blocks, kTcThreads, smem, st>>>(p, tiles, cpt, hid);
+}
+
 template <int NSPLIT>
 static int launch_tc_t(TcParams &p, cudaStream_t st) {
     const ConvParams &c = p.c;
@@ -1188,6 +1574,25 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
     {  // kernel B
         if (c.K > kTileRows) return GRIDGCN_ELIMIT;
         if ((long long)c.B * c.Nprev * c.Cout >= (1LL << 32)) return GRIDGCN_ELIMIT;  // 32-bit row offsets
+        if (NSPLIT == 3 && p.has_ff && p.has_att && p.f0_cuda && p.dbg == nullptr && c.Cout <= 64 &&
+            64 % c.K == 0) {
+            // compact first-layer variant: three CTAs per SM (see edge_first64_kernel)
+            const First64Layout L = first64_layout(p);
+            int hid = 32;
+            for (int s = 0; s < p.nfh; s++)
+                while (hid < p.fh[s].Np) hid <<= 1;
+            const size_t smem = L.total + 128;
+            const int per_sm = (int)min(min((size_t)3, kSmemCap / smem), (size_t)(512 / (128 + hid)));
+            if (2 * L.kh <= L.kx && p.ff.Np == 128 && p.a1.Np == 128 && per_sm >= 3) {
+                const int cpt = kTileRows / c.K;
+                const long long centers = (long long)c.B * c.O;
+                const long long tiles = (centers + cpt - 1) / cpt;
+                if (tiles > 0x7fffffff) return GRIDGCN_ELIMIT;
+                const int blocks = (int)min(tiles, (long long)sms * per_sm);
+                launch_first64(p, blocks, smem, st, (int)tiles, cpt, hid);
+                return (int)cudaGetLastError();
+            }
+        }
         const size_t base = kernel_b_base(p, NSPLIT);
         int n_slices;
         size_t seq_bytes;
