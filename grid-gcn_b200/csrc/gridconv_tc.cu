@@ -1383,6 +1383,273 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kernel B'', wide-layer variant (layers >= 1 whose operand image + weights leave room for ONE CTA per SM):
+// the same tile pipeline as edge_tc_kernel<NSPLIT, false> with EIGHT worker warps.  With one resident CTA
+// the four-warp version leaves the SM latency bound (issue slots ~20 % busy); here two threads share an
+// edge row in the gather phase (each computes half of the attention stage-0 channels) and two warps share
+// a TMEM lane quadrant in the epilogue (columns [0,64) / [64,128); K | 64 so no centre straddles the
+// split).  Shared-memory layout and ring protocol are those of edge_tc_kernel (kernel_b_base).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWideThreads = 288;  // warps 0-7: workers; warp 8: TMA + MMA issue
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kWideThreads, 1)
+edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t rowoff_s[kTileRows];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, half = (tid >> 7) & 1;  // workers: edge row of the tile, which half of the work
+    const ConvParams &c = p.c;
+    const int K = c.K, C = c.Cout;
+    constexpr uint32_t LBO = kTileRows * 16;
+    constexpr int NIMG = NSPLIT == 3 ? 2 : 1;
+    const int kh = p.a1.Kp;
+    uint8_t *xa_hi = smem, *xa_lo = xa_hi + (size_t)(kh / 4) * LBO;
+    float *wa0_s = reinterpret_cast<float *>(smem + (size_t)NIMG * (kh / 4) * LBO);
+    const int Cp = pad_to(C, 128);
+    float *bias_a1_s = wa0_s + kh * 12 + Cp;  // kernel_b_base: [wa0 | bias_ff (unused) | bias_a1]
+    float *small_end = bias_a1_s + Cp;
+    Ring ring;
+    ring.slots = smem + pad_to((int)(reinterpret_cast<uint8_t *>(small_end) - smem), 128);
+    ring.nslots = p.ring_slots;
+    ring.full = bars;
+    ring.empty = bars + kMaxRing;
+    ring.issued = ring.consumed = 0;
+    uint64_t *bar_mma = bars + 2 * kMaxRing;
+
+    SliceSeq prod;
+    prod.n = 0;
+    prod.chunk_major = 1;
+    prod.st[prod.n++] = &p.a1;
+    prod.reset();
+    const int per_tile = prod.per_tile();
+    const bool sticky = p.ring_sticky != 0;
+    if (sticky) {
+        SliceSeq tmp = prod;
+        uint32_t o = 0;
+        for (int i = 0; i < per_tile && i < kMaxRing; i++) {
+            long long off;
+            uint32_t bytes;
+            tmp.next(off, bytes);
+            ring.off[i] = o;
+            o += bytes;
+        }
+    } else {
+        for (int i = 0; i < kMaxRing; i++) ring.off[i] = (uint32_t)i * kSlotBytes;
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) {
+        for (int i = 0; i < ring.nslots; i++) {
+            tc::mbar_init(&ring.full[i], 1);
+            tc::mbar_init(&ring.empty[i], 1);
+        }
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_init_fence();
+    }
+    for (int i = tid; i < kh * 12; i += kWideThreads) {
+        const int j = i / 12, q = i % 12;
+        float v = 0.f;
+        if (j < p.a0_cout) {
+            if (q < p.a0_cin) v = __ldg(p.a0_w + (size_t)j * p.a0_cin + q);
+            else if (q == 10) v = __ldg(p.a0_b + j);
+        }
+        wa0_s[i] = v;
+    }
+    for (int i = tid; i < Cp; i += kWideThreads) bias_a1_s[i] = i < C ? __ldg(p.a1.bias + i) : 0.f;
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_slices = (long long)my_tiles * per_tile;
+    if (warp == 8 && lane == 0) {
+        const long long pre = sticky ? per_tile : ring.nslots;
+        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+    }
+    uint32_t mma_phase = 0;
+    const long long rows_total = (long long)c.B * c.Nprev;
+    const long long centers_total = (long long)c.B * c.O;
+    const int row_w = 4 + c.Cin;
+    const int out_w = 4 + C;
+    const int attfdim = c.attfdim, Nprev = c.Nprev, O = c.O;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+    const int nchunk = Cp / 128;
+    const float pre_floor = c.pre_relu ? 0.f : -3.402823466e+38f;
+
+    const int my_cl = row / K, my_slot = row - my_cl * K;
+    bool pf_valid = false;
+    int pf_idx = 0;
+    long long pf_center = 0;
+    uint32_t pf_roff = 0;
+    float4 pf_head = make_float4(0.f, 0.f, 0.f, 0.f), pf_cent = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_row = [&]() {
+        pf_roff = 0;
+        if (pf_valid) {
+            const int b = (int)(pf_center / O);
+            const long long r = take_row(pf_idx, b, Nprev, rows_total);
+            pf_roff = (uint32_t)r * (uint32_t)C;
+            const float *src = c.table + r * row_w;
+            if ((row_w & 3) == 0) pf_head = __ldg(reinterpret_cast<const float4 *>(src));
+            else pf_head = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
+            pf_cent = __ldg(c.cent + pf_center);
+        }
+    };
+    if (warp < 8 && blockIdx.x < num_tiles) {
+        const long long center = (long long)blockIdx.x * cpt + my_cl;
+        pf_valid = my_cl < cpt && center < centers_total;
+        pf_center = center;
+        if (pf_valid) pf_idx = __ldg(c.nebidx + center * K + my_slot);
+        fetch_row();
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long c_base = (long long)tile * cpt;
+        // ---- gather + attention stage 0: two threads per edge row, each half of the channel groups ----
+        if (warp < 8) {
+            float att[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) att[i] = 0.f;
+            att[10] = 1.f;
+            float dx, dy, dz;
+            const uint32_t roff = pf_roff;
+            if (pf_valid) att_vector(attfdim, pf_cent, pf_head.x, pf_head.y, pf_head.z, att, dx, dy, dz);
+            {
+                const long long ncenter = (long long)(tile + gridDim.x) * cpt + my_cl;
+                pf_valid = (tile + (int)gridDim.x) < num_tiles && my_cl < cpt && ncenter < centers_total;
+                pf_center = ncenter;
+                if (pf_valid) pf_idx = __ldg(c.nebidx + ncenter * K + my_slot);
+            }
+            if (half == 0) rowoff_s[row] = roff;
+            const int gh = kh / 8;  // groups of 4 channels per half
+            for (int g = half * gh; g < (half + 1) * gh; g++) {
+                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 48);
+                float hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 w0 = w4[i * 3], w1 = w4[i * 3 + 1], w2 = w4[i * 3 + 2];
+                    float acc = w2.z;
+                    acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
+                    acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
+                    acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
+                    acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
+                    acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
+                    tc::split_op<NSPLIT>(fmaxf(acc, 0.f), hi[i], lo[i]);
+                }
+                const uint32_t off = row_off + (uint32_t)g * LBO;
+                *reinterpret_cast<float4 *>(xa_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (NSPLIT == 3)
+                    *reinterpret_cast<float4 *>(xa_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+
+        for (int j = 0; j < nchunk; j++) {
+            if (warp == 8) {
+                if (lane == 0) {
+                    TcStage v = p.a1;
+                    v.Np = 128;
+                    v.w_off = p.a1.w_off + (long long)j * 2 * 128 * p.a1.Kp;
+                    run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
+                                                 tc::smem_u32(xa_hi), tc::smem_u32(xa_lo), LBO, 128, tmem, 0);
+                    tc::mma_commit(bar_mma);
+                }
+                __syncwarp();
+            }
+            // ---- epilogue: thread = channel (TMEM lane of quadrant warp & 3), columns [64 * half, +64) ----
+            const int ch = j * 128 + (warp & 3) * 32 + lane;
+            const bool chv = ch < C;
+            const bool warp_on = warp < 8 && (j * 128 + (warp & 3) * 32) < C;
+            const int col0 = 64 * half;
+            const float *fbase = p.ftab + (chv ? ch : 0);
+            uint32_t gA[16], fA[16], gB[16], fB[16];
+            auto gather16 = [&](uint32_t (&f)[16], int e0) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) f[i] = __float_as_uint(__ldg(fbase + rowoff_s[e0 + i]));
+            };
+            if (warp_on) gather16(fA, col0);
+            if (j == 0 && warp < 8) fetch_row();
+            wait_bar(bar_mma, mma_phase);
+            mma_phase ^= 1;
+            tc::fence_after_sync();
+            if (warp_on) {
+                const float ba = bias_a1_s[chv ? ch : 0];
+                const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+                float *out_ch = c.out + 4 + ch;
+                float m = -3.402823466e+38f;
+                int pos = 0, cl = col0 / K;
+                auto reduce16 = [&](const uint32_t (&g)[16], const uint32_t (&f)[16]) {
+                    float pr[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        pr[i] = __uint_as_float(f[i]) * fmaxf(__uint_as_float(g[i]) + ba, 0.f);  // :167 att * feats
+                    if ((K & 15) == 0) {
+                        float mm = pr[0];
+#pragma unroll
+                        for (int i = 1; i < 16; i++) mm = fmaxf(mm, pr[i]);
+                        m = fmaxf(m, mm);
+                        pos += 16;
+                        if (pos == K) {
+                            const long long center = c_base + cl;
+                            if (chv && cl < cpt && center < centers_total)
+                                out_ch[center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
+                            pos = 0;
+                            cl++;
+                            m = -3.402823466e+38f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            m = fmaxf(m, pr[i]);
+                            if (++pos == K) {
+                                const long long center = c_base + cl;
+                                if (chv && cl < cpt && center < centers_total)
+                                    out_ch[center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
+                                pos = 0;
+                                cl++;
+                                m = -3.402823466e+38f;
+                            }
+                        }
+                    }
+                };
+                tc::tmem_ld16(lane_addr + col0, gA);
+                tc::tmem_ld_wait();
+#pragma unroll 1
+                for (int e0 = col0; e0 < col0 + 64; e0 += 32) {
+                    tc::tmem_ld16(lane_addr + e0 + 16, gB);
+                    gather16(fB, e0 + 16);
+                    reduce16(gA, fA);
+                    tc::tmem_ld_wait();
+                    if (e0 + 32 < col0 + 64) {
+                        tc::tmem_ld16(lane_addr + e0 + 32, gA);
+                        gather16(fA, e0 + 32);
+                    }
+                    reduce16(gB, fB);
+                    tc::tmem_ld_wait();
+                }
+            }
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+        }
+        if (warp < 8) {
+            for (int i = tid; i < cpt * 4; i += 256) {
+                const long long center = c_base + i / 4;
+                if (center < centers_total)
+                    c.out[center * out_w + (i & 3)] = __ldg(reinterpret_cast<const float *>(c.cent + center) + (i & 3));
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side: stage tables, packing, launches.
 // ------------------------------------------------------------------------------------------------
 static void make_stage(TcStage &s, int transposed, int cin, int cout, const float *bias, long long &off) {
@@ -1515,6 +1782,9 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(edge_tc_kernel<NSPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemCap);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(edge_wide_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kSmemCap);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -1620,6 +1890,8 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         int blocks = (int)min(tiles, (long long)sms * per_sm);
         if (p.has_ff)
             edge_tc_kernel<NSPLIT, true><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
+        else if (per_sm == 1 && p.has_att && p.dbg == nullptr && 64 % c.K == 0 && (p.a1.Kp & 7) == 0)
+            edge_wide_kernel<NSPLIT><<<blocks, kWideThreads, smem, st>>>(p, (int)tiles, cpt);  // 8 worker warps
         else
             edge_tc_kernel<NSPLIT, false><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
         return (int)cudaGetLastError();

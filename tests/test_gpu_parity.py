@@ -164,6 +164,14 @@ CONV_CASES = [
     ("K128", 1, 512, 16, 128, 32, [32, 64]),
     ("K5_decoder_like", 2, 128, 100, 5, 32, [128]),
     ("K16_single_stage", 2, 256, 40, 16, 8, [24]),
+    # first-layer shapes of the compact (M=64, three CTAs per SM) kernel: K | 64, Cout <= 64, ragged centre counts
+    ("l0_K32_C40", 2, 512, 50, 32, 0, [32, 32, 40]),
+    ("l0_K16_C64", 2, 512, 77, 16, 0, [32, 64]),
+    ("l0_K4_C24", 1, 128, 30, 4, 0, [8, 16, 24]),
+    ("l0_K64_C64_narrow_f0", 1, 1024, 33, 64, 0, [16, 32, 64]),
+    # first-layer shapes that must take the general kernel (Cout > 64, K not a divisor of 64)
+    ("l0_C96", 1, 512, 40, 32, 0, [32, 96]),
+    ("l0_K24", 1, 512, 40, 24, 0, [32, 32, 64]),
 ]
 
 
