@@ -43,6 +43,7 @@ constexpr int kTileRows = 128;
 constexpr int kSliceK = 32;         // k extent of one streamed weight slice
 constexpr int kSlotBytes = 2 * 128 * kSliceK * 4;  // hi + lo images of a [128 x 32] slice
 constexpr int kMaxRing = 8;
+constexpr int kRowsThreads = 288;    // row-major kernel A: warps 0-7 workers (two per TMEM lane quadrant), warp 8 TMA + MMA
 
 struct TcStage {
     int transposed;  // 0: D[row, ch], weights resident in smem as the B operand; 1: D^T[ch, row], weights streamed as A
@@ -261,9 +262,10 @@ __device__ __forceinline__ void run_plain_stage(const TcStage &st, uint32_t x_hi
 template <int NSPLIT>
 __device__ __forceinline__ void plain_epilogue(const TcStage &st, uint32_t tmem_lane_addr, uint32_t row_off,
                                                uint8_t *img_hi, uint8_t *img_lo, uint32_t lbo,
-                                               int kp_next, const float *bias_s) {
+                                               int kp_next, const float *bias_s, int c_begin = 0,
+                                               int c_end = 1 << 30) {
     (void)st;
-    for (int c0 = 0; c0 < kp_next; c0 += 16) {
+    for (int c0 = c_begin; c0 < min(kp_next, c_end); c0 += 16) {
         uint32_t v[16];
         tc::tmem_ld16(tmem_lane_addr + c0, v);
         tc::tmem_ld_wait();
@@ -291,7 +293,7 @@ __device__ __forceinline__ void plain_epilogue(const TcStage &st, uint32_t tmem_
 // Every stage transposed: D^T[ch, row]; thread = channel in the epilogue.
 // ------------------------------------------------------------------------------------------------
 template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kRowsThreads, 1)
 point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
@@ -336,7 +338,7 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     const long long total_slices = (long long)my_tiles * prod.per_tile();
     const bool sticky = prod.per_tile() <= ring.nslots;  // whole sequence fits: load once, keep
     if (sticky) ring.nslots = max(prod.per_tile(), 1);
-    if (warp == 4 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         const long long pre = sticky ? prod.per_tile() : ring.nslots;
         for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
     }
@@ -347,9 +349,9 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * TR;
         // ---- load X0 = table[row0 .. row0+TR, 4:4+Cin] as hi/lo K-major images ----
-        if (warp < 4) {
+        if (warp < 8) {
             const int kp0 = p.a[0].Kp;
-            for (int e = tid; e < TR * (kp0 / 4); e += 128) {
+            for (int e = tid; e < TR * (kp0 / 4); e += 256) {
                 const int r = e / (kp0 / 4), c = (e % (kp0 / 4)) * 4;
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
                 if (row0 + r < rows_total) {
@@ -375,7 +377,7 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
         tc::fence_after_sync();
         for (int s = 0; s < p.na; s++) {
             const TcStage &st = p.a[s];
-            if (warp == 4) {
+            if (warp == 8) {
                 if (lane == 0) {
                     run_transposed_stage<NSPLIT>(st, ring, prod, p.packed, total_slices, sticky,
                                                  tc::smem_u32(x_hi), tc::smem_u32(x_lo), x_lbo, TR, tmem, TR);
@@ -386,14 +388,14 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
             wait_bar(bar_mma, mma_phase);
             mma_phase ^= 1;
             tc::fence_after_sync();
-            if (warp < 4) {
+            if (warp < 8) {
                 const bool last = s + 1 == p.na;
                 const int kp_next = last ? 0 : p.a[s + 1].Kp;
                 for (int j = 0; j < st.Np / 128; j++) {
-                    const int ch = j * 128 + tid;
+                    const int ch = j * 128 + (tid & 127);
                     const float bias = ch < st.Cout ? __ldg(st.bias + ch) : 0.f;
-                    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + j * TR;
-                    for (int r0 = 0; r0 < TR; r0 += 16) {
+                    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + j * TR;
+                    for (int r0 = (warp >> 2) * (TR / 2); r0 < ((warp >> 2) + 1) * (TR / 2); r0 += 16) {  // two warps per lane quadrant: half of the rows each
                         uint32_t v[16];
                         tc::tmem_ld16(taddr + r0, v);
                         tc::tmem_ld_wait();
@@ -437,12 +439,13 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
 // remains for the layers whose activations do not fit (K = 256).
 // ------------------------------------------------------------------------------------------------
 template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kRowsThreads, 1)
 point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, half = (tid >> 7) & 1;  // workers: tile row, which half of the columns
     constexpr int TR = kTileRows;
     constexpr uint32_t LBO = TR * 16;
     int kmax = 0, npmax = 0;
@@ -471,7 +474,7 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
         tc::mbar_init(bar_mma, 1);
         tc::mbar_init_fence();
     }
-    for (int i = tid; i < p.na * npmax; i += kTcThreads) {
+    for (int i = tid; i < p.na * npmax; i += kRowsThreads) {
         const int s = i / npmax, j = i % npmax;
         bias_s[i] = j < p.a[s].Cout ? __ldg(p.a[s].bias + j) : 0.f;
     }
@@ -489,22 +492,22 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     const long long total_slices = (long long)my_tiles * prod.per_tile();
     const bool sticky = prod.per_tile() <= ring.nslots;
     if (sticky) ring.nslots = max(prod.per_tile(), 1);
-    if (warp == 4 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         const long long pre = sticky ? prod.per_tile() : ring.nslots;
         for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
     }
     uint32_t mma_phase = 0;
     const long long rows_total = (long long)p.c.B * p.c.Nprev;
     const int row_w = 4 + p.c.Cin;
-    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     const int C = p.a[p.na - 1].Cout;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * TR;
         // ---- X0 = table[row0 .. row0+128, 4:4+Cin] as hi/lo K-major images (coalesced 128-bit loads) ----
-        if (warp < 4) {
+        if (warp < 8) {
             const int kp0 = p.a[0].Kp;
-            for (int e = tid; e < TR * (kp0 / 4); e += 128) {
+            for (int e = tid; e < TR * (kp0 / 4); e += 256) {
                 const int r = e / (kp0 / 4), c = (e % (kp0 / 4)) * 4;
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
                 if (row0 + r < rows_total) {
@@ -530,7 +533,7 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
         tc::fence_after_sync();
         for (int s = 0; s < p.na; s++) {
             const TcStage &st = p.a[s];
-            if (warp == 4) {
+            if (warp == 8) {
                 if (lane == 0) {
                     run_transposed_stage<NSPLIT, true>(st, ring, prod, p.packed, total_slices, sticky,
                                                        tc::smem_u32(x_hi), tc::smem_u32(x_lo), LBO, 128, tmem, 128);
@@ -541,14 +544,17 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
             wait_bar(bar_mma, mma_phase);
             mma_phase ^= 1;
             tc::fence_after_sync();
-            if (warp < 4) {
-                const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+            if (warp < 8) {  // two threads per row: columns [0, mid) and [mid, width), mid a multiple of 16
+                const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
                 if (s + 1 < p.na) {
-                    plain_epilogue<NSPLIT>(st, tl, row_off, x_hi, x_lo, LBO, p.a[s + 1].Kp, bias_s + s * npmax);
-                } else if (row0 + tid < rows_total) {  // last stage: F[row, :] = relu(D + b), 128-bit stores
-                    float *dst = p.ftab + (row0 + tid) * C;
+                    const int kpn = p.a[s + 1].Kp, mid = ((kpn + 31) / 32) * 16;
+                    plain_epilogue<NSPLIT>(st, tl, row_off, x_hi, x_lo, LBO, kpn, bias_s + s * npmax,
+                                           half ? mid : 0, half ? kpn : mid);
+                } else if (row0 + row < rows_total) {  // last stage: F[row, :] = relu(D + b), 128-bit stores
+                    float *dst = p.ftab + (row0 + row) * C;
                     const float *bs = bias_s + s * npmax;
-                    for (int c0 = 0; c0 < C; c0 += 16) {
+                    const int mid = ((C + 31) / 32) * 16;
+                    for (int c0 = half ? mid : 0; c0 < (half ? C : min(mid, C)); c0 += 16) {
                         uint32_t v[16];
                         tc::tmem_ld16(tl + c0, v);
                         tc::tmem_ld_wait();
@@ -1811,7 +1817,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
             size_t smem = rows_fixed + (size_t)p.ring_slots * kSlotBytes;
             int per_sm = (int)max((size_t)1, min(min((size_t)2, kSmemCap / smem), (size_t)(512 / p.tmem_cols)));
             int blocks = (int)min(tiles, (long long)sms * per_sm);
-            point_mlp_rows_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles);
+            point_mlp_rows_tc_kernel<NSPLIT><<<blocks, kRowsThreads, smem, st>>>(p, (int)tiles);
             p.tmem_cols = saved_cols;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
@@ -1836,7 +1842,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
             size_t smem = kernel_a_smem(p, TR, NSPLIT, slots);
             int per_sm = (int)max((size_t)1, min((size_t)2, kSmemCap / smem));
             int blocks = (int)min(tiles, (long long)sms * per_sm);
-            point_mlp_tc_kernel<NSPLIT><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles);
+            point_mlp_tc_kernel<NSPLIT><<<blocks, kRowsThreads, smem, st>>>(p, (int)tiles);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
         }
