@@ -120,16 +120,33 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
     }
 }
 
+constexpr int kMaxSeq = 128;  // slices per tile (3 stages x <= 4 chunks x <= 8 slices)
+
+// Weight ring.  All bookkeeping is done by ONE thread (the MMA issuer) and sits on its critical path between
+// two MMA batches, so it is kept to 32-bit counters with wrap-around increments (no divisions) and a per-tile
+// slice table precomputed in shared memory (r01: the 64-bit modulo / SliceSeq::next version cost ~1.5 us per
+// slice, more than the copy and the MMAs together).
 struct Ring {
     uint8_t *slots;
     uint32_t off[kMaxRing];  // byte offset of every slot (exact-fit in sticky mode, 32 KB apart otherwise)
     uint64_t *full, *empty;
     int nslots;
-    long long issued;     // producer: slices requested so far (whole kernel)
-    long long consumed;   // consumer: slices whose MMAs were issued so far
+    const float *packed;
+    const uint32_t *seq_off, *seq_bytes;  // per-tile slice sequence: float offset into packed, bytes
+    int per_tile;
+    uint32_t remaining;            // producer: slices still to request (whole kernel)
+    int p_slot, p_seq;             // producer cursors: ring slot, position in the per-tile sequence
+    uint32_t p_round;              // producer: times the slot cursor has wrapped
+    int c_slot;                    // consumer cursor
+    uint32_t c_round, c_count;     // consumer: wraps; slices consumed, saturating at 2
+    __device__ void reset() {
+        remaining = 0;
+        p_slot = p_seq = c_slot = 0;
+        p_round = c_round = c_count = 0;
+    }
 };
 
-// ---- slice sequence bookkeeping ------------------------------------------------------------------
+// ---- slice sequence (setup only: the hot path reads the table built from it) ------------------------
 struct SliceSeq {
     const TcStage *st[3];
     int n;            // number of transposed stages per tile
@@ -164,19 +181,42 @@ struct SliceSeq {
     }
 };
 
+// Producer set-up (the issuing thread only): build the slice table, then prefetch the first slices.
+__device__ __forceinline__ void ring_request(Ring &ring, bool wait_empty);
+__device__ __forceinline__ void ring_start(Ring &ring, SliceSeq seq, uint32_t *seq_off, uint32_t *seq_bytes,
+                                           const float *packed, int per_tile, long long total_slices,
+                                           bool sticky) {
+    seq.reset();
+    for (int i = 0; i < per_tile && i < kMaxSeq; i++) {
+        long long off;
+        uint32_t bytes;
+        seq.next(off, bytes);
+        seq_off[i] = (uint32_t)off;
+        seq_bytes[i] = bytes;
+    }
+    ring.packed = packed;
+    ring.seq_off = seq_off;
+    ring.seq_bytes = seq_bytes;
+    ring.per_tile = per_tile;
+    const long long pre = min((long long)(sticky ? per_tile : ring.nslots), total_slices);
+    ring.remaining = (uint32_t)(sticky ? pre : total_slices);
+    for (long long i = 0; i < pre; i++) ring_request(ring, false);
+}
+
 // Single-thread producer step: request the next slice of the CTA's sequence into the ring.
-__device__ __forceinline__ void ring_request(Ring &ring, SliceSeq &prod, const float *packed,
-                                             long long total_slices, bool wait_empty) {
-    if (ring.issued >= total_slices) return;
-    const int slot = (int)(ring.issued % ring.nslots);
-    if (wait_empty && ring.issued >= ring.nslots)
-        wait_bar(&ring.empty[slot], (uint32_t)(((ring.issued / ring.nslots) - 1) & 1));
-    long long off;
-    uint32_t bytes;
-    prod.next(off, bytes);
+__device__ __forceinline__ void ring_request(Ring &ring, bool wait_empty) {
+    if (ring.remaining == 0) return;
+    const int slot = ring.p_slot;
+    if (wait_empty && ring.p_round > 0) wait_bar(&ring.empty[slot], (ring.p_round - 1) & 1u);
+    const uint32_t bytes = ring.seq_bytes[ring.p_seq];
     tc::mbar_expect_tx(&ring.full[slot], bytes);
-    tc::bulk_g2s(ring.slots + ring.off[slot], packed + off, bytes, &ring.full[slot]);
-    ring.issued++;
+    tc::bulk_g2s(ring.slots + ring.off[slot], ring.packed + ring.seq_off[ring.p_seq], bytes, &ring.full[slot]);
+    if (++ring.p_seq == ring.per_tile) ring.p_seq = 0;
+    if (++ring.p_slot == ring.nslots) {
+        ring.p_slot = 0;
+        ring.p_round++;
+    }
+    ring.remaining--;
 }
 
 // Issue every MMA of one transposed stage (single thread).  D^T[128 ch of chunk j, ncols] (+)=
@@ -185,21 +225,18 @@ __device__ __forceinline__ void ring_request(Ring &ring, SliceSeq &prod, const f
 // SWAP == true: the same slices serve as the B operand and the image as the A operand, i.e.
 // D[row, 128 ch of chunk j] (+)= X * W_slice^T (rows in TMEM lanes, channels in columns).
 template <int NSPLIT, bool SWAP = false>
-__device__ __forceinline__ void run_transposed_stage(const TcStage &st, Ring &ring, SliceSeq &prod,
-                                                     const float *packed, long long total_slices,
-                                                     bool sticky, uint32_t x_hi, uint32_t x_lo,
-                                                     uint32_t x_lbo, int ncols, uint32_t tmem_base,
-                                                     int col_stride) {
+__device__ __forceinline__ void run_transposed_stage(int Kp, int nchunk, Ring &ring, bool sticky,
+                                                     uint32_t x_hi, uint32_t x_lo, uint32_t x_lbo, int ncols,
+                                                     uint32_t tmem_base, int col_stride) {
     const uint32_t idesc = tc::make_idesc_tf32(128, ncols);
-    const int nchunk = st.Np / 128, nslice = (st.Kp + kSliceK - 1) / kSliceK;
+    const int nslice = (Kp + kSliceK - 1) / kSliceK;
     for (int j = 0; j < nchunk; j++) {
         const uint32_t d = tmem_base + j * col_stride;
         uint32_t acc = 0;
         for (int t = 0; t < nslice; t++) {
-            const int kw = min(kSliceK, st.Kp - t * kSliceK);
-            const int slot = (int)(ring.consumed % ring.nslots);
-            if (!sticky || ring.consumed < ring.nslots)
-                wait_bar(&ring.full[slot], (uint32_t)((ring.consumed / ring.nslots) & 1));
+            const int kw = min(kSliceK, Kp - t * kSliceK);
+            const int slot = ring.c_slot;
+            if (!sticky || ring.c_round == 0) wait_bar(&ring.full[slot], ring.c_round & 1u);
             const uint32_t a_hi = tc::smem_u32(ring.slots + ring.off[slot]);
             const uint32_t a_lo = a_hi + 128 * kw * 4;
             for (int ks = 0; ks < kw / 8; ks++) {
@@ -222,12 +259,16 @@ __device__ __forceinline__ void run_transposed_stage(const TcStage &st, Ring &ri
                 else tc::mma_tf32(d, ah, bh, idesc, acc);
                 acc = 1;
             }
-            ring.consumed++;
+            if (++ring.c_slot == ring.nslots) {
+                ring.c_slot = 0;
+                ring.c_round++;
+            }
+            if (ring.c_count < 2) ring.c_count++;
             if (!sticky) {
                 tc::mma_commit(&ring.empty[slot]);
                 // Keep the ring full, one slice behind: the slot recycled here belongs to the slice
                 // BEFORE the one just issued, so waiting for it to drain never idles the tensor pipe.
-                if (ring.consumed >= 2) ring_request(ring, prod, packed, total_slices, true);
+                if (ring.c_count >= 2) ring_request(ring, true);
             }
         }
     }
@@ -297,6 +338,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
 point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t seq_off_s[kMaxSeq], seq_bytes_s[kMaxSeq];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int TR = p.a_rows;
@@ -310,7 +352,7 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     ring.nslots = p.ring_slots;
     ring.full = bars;
     ring.empty = bars + kMaxRing;
-    ring.issued = ring.consumed = 0;
+    ring.reset();
     for (int i = 0; i < kMaxRing; i++) ring.off[i] = (uint32_t)i * kSlotBytes;
     uint64_t *bar_mma = bars + 2 * kMaxRing;
 
@@ -339,8 +381,7 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     const bool sticky = prod.per_tile() <= ring.nslots;  // whole sequence fits: load once, keep
     if (sticky) ring.nslots = max(prod.per_tile(), 1);
     if (warp == 8 && lane == 0) {
-        const long long pre = sticky ? prod.per_tile() : ring.nslots;
-        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+        ring_start(ring, prod, seq_off_s, seq_bytes_s, p.packed, prod.per_tile(), total_slices, sticky);
     }
     uint32_t mma_phase = 0;
     const long long rows_total = (long long)p.c.B * p.c.Nprev;
@@ -379,8 +420,8 @@ point_mlp_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
             const TcStage &st = p.a[s];
             if (warp == 8) {
                 if (lane == 0) {
-                    run_transposed_stage<NSPLIT>(st, ring, prod, p.packed, total_slices, sticky,
-                                                 tc::smem_u32(x_hi), tc::smem_u32(x_lo), x_lbo, TR, tmem, TR);
+                    run_transposed_stage<NSPLIT>(st.Kp, st.Np / 128, ring, sticky, tc::smem_u32(x_hi),
+                                                 tc::smem_u32(x_lo), x_lbo, TR, tmem, TR);
                     tc::mma_commit(bar_mma);
                 }
                 __syncwarp();
@@ -443,6 +484,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
 point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t seq_off_s[kMaxSeq], seq_bytes_s[kMaxSeq];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & 127, half = (tid >> 7) & 1;  // workers: tile row, which half of the columns
@@ -461,7 +503,7 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     ring.nslots = p.ring_slots;
     ring.full = bars;
     ring.empty = bars + kMaxRing;
-    ring.issued = ring.consumed = 0;
+    ring.reset();
     for (int i = 0; i < kMaxRing; i++) ring.off[i] = (uint32_t)i * kSlotBytes;
     uint64_t *bar_mma = bars + 2 * kMaxRing;
 
@@ -493,8 +535,7 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
     const bool sticky = prod.per_tile() <= ring.nslots;
     if (sticky) ring.nslots = max(prod.per_tile(), 1);
     if (warp == 8 && lane == 0) {
-        const long long pre = sticky ? prod.per_tile() : ring.nslots;
-        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+        ring_start(ring, prod, seq_off_s, seq_bytes_s, p.packed, prod.per_tile(), total_slices, sticky);
     }
     uint32_t mma_phase = 0;
     const long long rows_total = (long long)p.c.B * p.c.Nprev;
@@ -535,8 +576,8 @@ point_mlp_rows_tc_kernel(const __grid_constant__ TcParams p, int num_tiles) {
             const TcStage &st = p.a[s];
             if (warp == 8) {
                 if (lane == 0) {
-                    run_transposed_stage<NSPLIT, true>(st, ring, prod, p.packed, total_slices, sticky,
-                                                       tc::smem_u32(x_hi), tc::smem_u32(x_lo), LBO, 128, tmem, 128);
+                    run_transposed_stage<NSPLIT, true>(st.Kp, st.Np / 128, ring, sticky, tc::smem_u32(x_hi),
+                                                       tc::smem_u32(x_lo), LBO, 128, tmem, 128);
                     tc::mma_commit(bar_mma);
                 }
                 __syncwarp();
@@ -607,6 +648,7 @@ __global__ void __launch_bounds__(kTcThreads, FIRST ? 2 : 3)
 edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t seq_off_s[kMaxSeq], seq_bytes_s[kMaxSeq];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t rowoff_s[kTileRows];  // element offset of every edge's source row in ftab
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -644,7 +686,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     ring.nslots = p.ring_slots;
     ring.full = bars;
     ring.empty = bars + kMaxRing;
-    ring.issued = ring.consumed = 0;
+    ring.reset();
     uint64_t *bar_mma = bars + 2 * kMaxRing;
 
     SliceSeq prod;
@@ -720,8 +762,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long total_slices = (long long)my_tiles * per_tile;
     if (warp == 4 && lane == 0) {
-        const long long pre = sticky ? per_tile : ring.nslots;
-        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+        ring_start(ring, prod, seq_off_s, seq_bytes_s, p.packed, per_tile, total_slices, sticky);
     }
     uint32_t mma_phase = 0;
     const long long rows_total = (long long)c.B * c.Nprev;
@@ -887,18 +928,12 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             if (warp == 4) {
                 if (lane == 0) {
                     if (FIRST) {
-                        TcStage v = p.ff;
-                        v.Np = 128;
-                        v.w_off = p.ff.w_off + (long long)j * 2 * 128 * p.ff.Kp;
-                        run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
-                                                     tc::smem_u32(xf_hi), tc::smem_u32(xf_lo), LBO, 128, tm_f, 0);
+                        run_transposed_stage<NSPLIT>(p.ff.Kp, 1, ring, sticky, tc::smem_u32(xf_hi),
+                                                     tc::smem_u32(xf_lo), LBO, 128, tm_f, 0);
                     }
                     if (has_att) {
-                        TcStage v = p.a1;
-                        v.Np = 128;
-                        v.w_off = p.a1.w_off + (long long)j * 2 * 128 * p.a1.Kp;
-                        run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
-                                                     tc::smem_u32(xa_hi), tc::smem_u32(xa_lo), LBO, 128, tm_g, 0);
+                        run_transposed_stage<NSPLIT>(p.a1.Kp, 1, ring, sticky, tc::smem_u32(xa_hi),
+                                                     tc::smem_u32(xa_lo), LBO, 128, tm_g, 0);
                     }
                     tc::mma_commit(bar_mma);
                 }
@@ -1403,6 +1438,7 @@ __global__ void __launch_bounds__(kWideThreads, 1)
 edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2 * kMaxRing + 1];
+    __shared__ uint32_t seq_off_s[kMaxSeq], seq_bytes_s[kMaxSeq];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t rowoff_s[kTileRows];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1422,7 +1458,7 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     ring.nslots = p.ring_slots;
     ring.full = bars;
     ring.empty = bars + kMaxRing;
-    ring.issued = ring.consumed = 0;
+    ring.reset();
     uint64_t *bar_mma = bars + 2 * kMaxRing;
 
     SliceSeq prod;
@@ -1473,8 +1509,7 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long total_slices = (long long)my_tiles * per_tile;
     if (warp == 8 && lane == 0) {
-        const long long pre = sticky ? per_tile : ring.nslots;
-        for (long long i = 0; i < pre; i++) ring_request(ring, prod, p.packed, sticky ? pre : total_slices, false);
+        ring_start(ring, prod, seq_off_s, seq_bytes_s, p.packed, per_tile, total_slices, sticky);
     }
     uint32_t mma_phase = 0;
     const long long rows_total = (long long)c.B * c.Nprev;
@@ -1558,11 +1593,8 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
         for (int j = 0; j < nchunk; j++) {
             if (warp == 8) {
                 if (lane == 0) {
-                    TcStage v = p.a1;
-                    v.Np = 128;
-                    v.w_off = p.a1.w_off + (long long)j * 2 * 128 * p.a1.Kp;
-                    run_transposed_stage<NSPLIT>(v, ring, prod, p.packed, total_slices, sticky,
-                                                 tc::smem_u32(xa_hi), tc::smem_u32(xa_lo), LBO, 128, tmem, 0);
+                    run_transposed_stage<NSPLIT>(p.a1.Kp, 1, ring, sticky, tc::smem_u32(xa_hi),
+                                                 tc::smem_u32(xa_lo), LBO, 128, tmem, 0);
                     tc::mma_commit(bar_mma);
                 }
                 __syncwarp();
