@@ -8,11 +8,11 @@ tensors are not on a CUDA device.
 """
 from . import synth  # noqa: F401  host-side input generator, numpy only
 from . import _lib  # noqa: F401  ctypes binding (loads the library lazily)
-from .ops import Gridify, GridifyKNN, GridifyUp, contrib  # noqa: F401
+from .ops import Gridify, GridifyKNN, GridifyUp, Gridify_occaware, GridifyOccaware, contrib  # noqa: F401
 from .gridconv import (GridConv, GridConvUp, SegHead, sub_g_update, fold_bn, init_layer,  # noqa: F401
                        init_up_layer, features_nco, rowmlp)
 from . import stack, shard  # noqa: F401
 from .build import build  # noqa: F401
 
-__all__ = ["Gridify", "GridifyKNN", "GridifyUp", "contrib", "GridConv", "sub_g_update", "fold_bn",
+__all__ = ["Gridify", "GridifyKNN", "GridifyUp", "Gridify_occaware", "GridifyOccaware", "contrib", "GridConv", "sub_g_update", "fold_bn",
            "init_layer", "features_nco", "stack", "shard", "synth", "build"]

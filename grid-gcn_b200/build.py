@@ -41,6 +41,21 @@ def _stale():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def _deps(path, seen=None):
+    """The file and every quoted #include reachable from it (so that an edit recompiles only the
+    objects that see it)."""
+    import re
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as f:
+        for inc in re.findall(r'^\s*#include\s+"([^"]+)"', f.read(), flags=re.M):
+            _deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ and link libgridgcn_b200.so.  Returns the library path."""
     if not force and not _stale():
@@ -52,9 +67,12 @@ def build(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and \
+                all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in _deps(src)):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:

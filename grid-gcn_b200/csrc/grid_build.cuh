@@ -158,8 +158,10 @@ grid_build_kernel(const float4 *__restrict__ data, const int *__restrict__ npts_
         cent_acc[cid] = make_float4(ax, ay, az, aw);
     }
     // P9: centre mask and count (gridify.cu:179, :222-224)
-    for (int o = tid; o < O; o += THREADS) centmsk[(size_t)b * O + o] = o < ncent ? 1.0f : 0.0f;
-    if (tid == 0) centnum[b] = ncent;
+    // (Gridify_occaware passes null: its sampling kernel writes both after choosing the centres)
+    if (centmsk != nullptr)
+        for (int o = tid; o < O; o += THREADS) centmsk[(size_t)b * O + o] = o < ncent ? 1.0f : 0.0f;
+    if (centnum != nullptr && tid == 0) centnum[b] = ncent;
 }
 
 }  // namespace gg

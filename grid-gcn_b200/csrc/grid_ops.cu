@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "grid_build.cuh"
 #include "grid_query.cuh"
+#include "grid_cas.cuh"
 #include "knn.cuh"
 
 namespace gg {
@@ -76,25 +77,10 @@ static int query_grid_blocks(long long rows) {
     return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
-static int gridify_impl(bool knn, const float *data, const int *npts, int B, int N, int O, int P,
-                        int ks, int loc, const float *shift, const float *voxel, const int *grid,
-                        int flags, int *nebidx, float *nebmsk, float *cent, float *centmsk,
-                        int *centnum, void *ws, size_t ws_bytes, void *stream) {
-    GridParams g{};
-    int rc = check_grid_args(B, N, O, P, ks, shift, voxel, grid, g);
-    if (rc) return rc;
-    if (!data || !npts || !nebidx || !nebmsk || !cent || !centmsk || !centnum) return GRIDGCN_EINVAL;
-    g.loc = loc;
-    g.flags = flags;
-    if (B == 0) return 0;
-    if (!ws || ws_bytes < gridgcn_gridify_workspace_bytes(B, N, O, grid)) return GRIDGCN_EWORKSPACE;
-    if ((reinterpret_cast<uintptr_t>(ws) & 15) || (reinterpret_cast<uintptr_t>(data) & 15) ||
-        (reinterpret_cast<uintptr_t>(cent) & 15))
-        return GRIDGCN_EINVAL;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    WsLayout L = make_layout(N, O, g.G);
-    cudaError_t e = launch_build(data, npts, g, static_cast<int *>(ws), L, centmsk, centnum, 1, st);
-    if (e != cudaSuccess) return (int)e;
+static int launch_gridify_query(bool knn, const float *data, const GridParams &g, const void *ws,
+                                const WsLayout &L, int *nebidx, float *nebmsk, float *cent,
+                                const int *centnum, cudaStream_t st) {
+    const int B = g.B, N = g.N, O = g.O, P = g.P, ks = g.ks;
     const int blocks = query_grid_blocks((long long)B * O);
     const float4 *d4 = reinterpret_cast<const float4 *>(data);
     float4 *c4 = reinterpret_cast<float4 *>(cent);
@@ -119,6 +105,95 @@ static int gridify_impl(bool knn, const float *data, const int *npts, int B, int
                                                                             nebidx, nebmsk, c4);
     }
     return (int)cudaGetLastError();
+}
+
+static int gridify_impl(bool knn, const float *data, const int *npts, int B, int N, int O, int P,
+                        int ks, int loc, const float *shift, const float *voxel, const int *grid,
+                        int flags, int *nebidx, float *nebmsk, float *cent, float *centmsk,
+                        int *centnum, void *ws, size_t ws_bytes, void *stream) {
+    GridParams g{};
+    int rc = check_grid_args(B, N, O, P, ks, shift, voxel, grid, g);
+    if (rc) return rc;
+    if (!data || !npts || !nebidx || !nebmsk || !cent || !centmsk || !centnum) return GRIDGCN_EINVAL;
+    g.loc = loc;
+    g.flags = flags;
+    if (B == 0) return 0;
+    if (!ws || ws_bytes < gridgcn_gridify_workspace_bytes(B, N, O, grid)) return GRIDGCN_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) || (reinterpret_cast<uintptr_t>(data) & 15) ||
+        (reinterpret_cast<uintptr_t>(cent) & 15))
+        return GRIDGCN_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WsLayout L = make_layout(N, O, g.G);
+    cudaError_t e = launch_build(data, npts, g, static_cast<int *>(ws), L, centmsk, centnum, 1, st);
+    if (e != cudaSuccess) return (int)e;
+    return launch_gridify_query(knn, data, g, ws, L, nebidx, nebmsk, cent, centnum, st);
+}
+
+// Gridify_occaware: build (every occupied voxel numbered by first occurrence, with its barycentre)
+// -> coverage-aware sampling of max_o of them (grid_cas.cuh) -> the Gridify / GridifyKNN query on the
+// selected centres.  Workspace = the build layout sized for min(N, G) "centres" + the CAS extras.
+struct CasPlan {
+    WsLayout L;        // build layout (cent_lin / cent_acc hold every occupied voxel)
+    WsLayout Lq;       // same memory, centre arrays redirected to the sampled ones (query kernel)
+    CasLayout C;
+    bool cover_in_smem, bitmap_in_smem;
+    size_t smem;
+};
+
+static CasPlan make_cas_plan(int N, int O, int G) {
+    CasPlan p;
+    const int V = N < G ? N : G, W = (G + 31) / 32;
+    p.L = make_layout(N, V < 1 ? 1 : V, G);
+    long long off = p.L.stride;
+    p.C.cent_lin_out = (int)off;  off += round4(O);
+    p.C.cent_acc_out = (int)off;  off += round4(4LL * O);
+    p.cover_in_smem = cas_smem_bytes(G, W, O, true, false) <= kBuildSmemLimit;
+    p.bitmap_in_smem = cas_smem_bytes(G, W, O, p.cover_in_smem, true) <= kBuildSmemLimit;
+    p.C.cover = (int)off;
+    if (!p.cover_in_smem) off += round4((G + 1) / 2);
+    p.L.stride = off;
+    p.Lq = p.L;
+    p.Lq.cent_lin = p.C.cent_lin_out;
+    p.Lq.cent_acc = p.C.cent_acc_out;
+    p.smem = cas_smem_bytes(G, W, O, p.cover_in_smem, p.bitmap_in_smem);
+    return p;
+}
+
+static int gridify_occaware_impl(const float *data, const int *npts, int B, int N, int O, int P,
+                                 int ks, int loc, const float *shift, const float *voxel,
+                                 const int *grid, int flags, unsigned long long seed, int *nebidx,
+                                 float *nebmsk, float *cent, float *centmsk, int *centnum, void *ws,
+                                 size_t ws_bytes, void *stream) {
+    GridParams g{};
+    int rc = check_grid_args(B, N, O, P, ks, shift, voxel, grid, g);
+    if (rc) return rc;
+    if (!data || !npts || !nebidx || !nebmsk || !cent || !centmsk || !centnum) return GRIDGCN_EINVAL;
+    if (O > 8192) return GRIDGCN_ELIMIT;  // slot tables live in shared memory
+    g.loc = loc;
+    g.flags = flags;
+    if (B == 0) return 0;
+    if (!ws || ws_bytes < gridgcn_gridify_occaware_workspace_bytes(B, N, O, grid))
+        return GRIDGCN_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) || (reinterpret_cast<uintptr_t>(data) & 15) ||
+        (reinterpret_cast<uintptr_t>(cent) & 15))
+        return GRIDGCN_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const CasPlan p = make_cas_plan(N, O, g.G);
+    GridParams gb = g;  // build: every occupied voxel is a candidate centre
+    gb.O = N < g.G ? N : g.G;
+    if (gb.O < 1) gb.O = 1;
+    cudaError_t e = launch_build(data, npts, gb, static_cast<int *>(ws), p.L, nullptr, nullptr, 1, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(cas_sampling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kBuildSmemLimit);
+    if (e != cudaSuccess) return (int)e;
+    cas_sampling_kernel<<<B, kCasThreads, p.smem, st>>>(g, static_cast<int *>(ws), p.L, p.C, seed,
+                                                        centmsk, centnum, p.cover_in_smem ? 1 : 0,
+                                                        p.bitmap_in_smem ? 1 : 0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    return launch_gridify_query((flags & GRIDGCN_FLAG_KNN_QUERY) != 0, data, g, ws, p.Lq, nebidx,
+                                nebmsk, cent, centnum, st);
 }
 
 }  // namespace gg
@@ -173,6 +248,28 @@ int gridgcn_gridify_knn_fwd(const float *data, const int *actual_numpoints, int 
     return gridify_impl(true, data, actual_numpoints, B, N, max_o_grid, max_p_grid, kernel_size,
                         loc, coord_shift, voxel_size, grid_size, flags, nebidx, nebidxmsk, cent,
                         centmsk, actual_centnum, workspace, workspace_bytes, stream);
+}
+
+size_t gridgcn_gridify_occaware_workspace_bytes(int B, int N, int max_o_grid,
+                                                const int grid_size[3]) {
+    if (B <= 0 || N < 0 || max_o_grid < 1 || !grid_size) return 0;
+    long long G = (long long)grid_size[0] * grid_size[1] * grid_size[2];
+    if (G < 1 || G > kMaxGridVoxels) return 0;
+    return (size_t)make_cas_plan(N, max_o_grid, (int)G).L.stride * 4 * (size_t)B;
+}
+
+int gridgcn_gridify_occaware_fwd(const float *data, const int *actual_numpoints, int B, int N,
+                                 int max_o_grid, int max_p_grid, int kernel_size, int stride,
+                                 int loc, const float coord_shift[3], const float voxel_size[3],
+                                 const int grid_size[3], int flags, unsigned long long seed,
+                                 int *nebidx, float *nebidxmsk, float *cent, float *centmsk,
+                                 int *actual_centnum, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
+    (void)stride;
+    return gridify_occaware_impl(data, actual_numpoints, B, N, max_o_grid, max_p_grid, kernel_size,
+                                 loc, coord_shift, voxel_size, grid_size, flags, seed, nebidx,
+                                 nebidxmsk, cent, centmsk, actual_centnum, workspace,
+                                 workspace_bytes, stream);
 }
 
 int gridgcn_gridify_up_fwd(const float *downdata, const float *updata,

@@ -36,7 +36,7 @@ def _check_cuda(name, t, dtype, ndim):
 
 
 def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_size, stride, loc,
-             coord_shift, voxel_size, grid_size, flags):
+             coord_shift, voxel_size, grid_size, flags, seed=None):
     L = _lib.lib()
     data = _check_cuda("data", data, torch.float32, 3)
     actual_numpoints = _check_cuda("actualnum", actual_numpoints, torch.int32, 2)
@@ -48,7 +48,10 @@ def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_siz
     O, P = int(max_o_grid), int(max_p_grid)
     dev = data.device
     grid = _lib.triple_i(grid_size)
-    ws_bytes = L.gridgcn_gridify_workspace_bytes(B, N, O, grid) if B > 0 else 0
+    ws_fn = L.gridgcn_gridify_workspace_bytes if seed is None else L.gridgcn_gridify_occaware_workspace_bytes
+    ws_bytes = ws_fn(B, N, O, grid) if B > 0 else 0
+    if B > 0 and ws_bytes == 0:
+        raise _lib.GridGcnError("%s: unsupported sizes (max_o_grid >= 1, grid volume <= 262144)" % fn_name)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     nebidx = torch.empty((B, O, P), dtype=torch.int32, device=dev)
     nebidxmsk = torch.empty((B, O, P), dtype=torch.float32, device=dev)
@@ -61,7 +64,7 @@ def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_siz
         rc = getattr(L, fn_name)(
             data.data_ptr(), actual_numpoints.data_ptr(), B, N, O, P, int(kernel_size), int(stride),
             int(loc), _lib.triple_f(coord_shift), _lib.triple_f(voxel_size), grid, int(flags),
-            nebidx.data_ptr(), nebidxmsk.data_ptr(), cent.data_ptr(), centmsk.data_ptr(),
+            *(() if seed is None else (int(seed) & 0xFFFFFFFFFFFFFFFF,)), nebidx.data_ptr(), nebidxmsk.data_ptr(), cent.data_ptr(), centmsk.data_ptr(),
             actual_centnum.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(dev))
     _lib.check(rc, fn_name)
     return nebidx, nebidxmsk, cent, centmsk, actual_centnum
@@ -85,6 +88,22 @@ def GridifyKNN(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_siz
     return _gridify("gridgcn_gridify_knn_fwd", data, actual_numpoints, max_p_grid, max_o_grid,
                     kernel_size, stride, loc, coord_shift, voxel_size, grid_size,
                     1 if dist_fma else 0)
+
+
+def Gridify_occaware(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_size=0, stride=0,
+                     loc=0, coord_shift=(), voxel_size=(), grid_size=(), seed=0, knn_query=False,
+                     dist_fma=False):
+    """Gridify with Coverage-Aware Sampling of the centre voxels (paper s3.2).  The reference
+    registers this operator from gridifyop/additional.so but ships its kernels only as cubins
+    (SURVEY.md F3); same inputs, attributes and five outputs as Gridify.  ``seed`` replaces the
+    reference's wall-clock seed (challenger i draws from XORWOW(seed + i)); ``knn_query`` (extension)
+    runs the GridifyKNN query on the sampled centres.  Parity unpinned, see DESIGN.md."""
+    flags = (2 if knn_query else 0) | (1 if dist_fma else 0)
+    return _gridify("gridgcn_gridify_occaware_fwd", data, actual_numpoints, max_p_grid, max_o_grid,
+                    kernel_size, stride, loc, coord_shift, voxel_size, grid_size, flags, seed=seed)
+
+
+GridifyOccaware = Gridify_occaware
 
 
 def GridifyUp(downdata, updata, down_actual_numpoints, up_actual_numpoints, *, max_p_grid=0,

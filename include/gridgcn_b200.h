@@ -44,6 +44,9 @@ extern "C" {
                                      the reference's shipped sm_75 cubin -- instead of the
                                      canonical ((dx*dx+dy*dy)+dz*dz) of SURVEY.md s8c rule 10   */
 
+#define GRIDGCN_FLAG_KNN_QUERY 2  /* gridgcn_gridify_occaware_fwd only: run the GridifyKNN query
+                                     (K4) on the sampled centres instead of the Gridify one (K2) */
+
 int gridgcn_abi_version(void);
 
 /* Human-readable text for a return code of this library (static storage). */
@@ -77,6 +80,29 @@ int gridgcn_gridify_knn_fwd(const float *data, const int *actual_numpoints, int 
                             const int grid_size[3], int flags, int *nebidx, float *nebidxmsk,
                             float *cent, float *centmsk, int *actual_centnum, void *workspace,
                             size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Gridify_occaware -- Gridify with Coverage-Aware Sampling (CAS) of the centre voxels.         */
+/*   Replaces the operators `Gridify_occaware` registered by gridifyop/additional.so, whose    */
+/*   kernels gridify_kernel_build_index_occaware / gridify_occaware_sampling /                  */
+/*   gridify_kernel_query_neighs_occaware exist in the reference ONLY as sm_61/sm_75 cubins    */
+/*   (`cuobjdump -elf additional.so`; gridify_occaware.cu is not in the tree).    */
+/*   Semantics: restated from the sm_75 SASS + arXiv:1912.02984 s3.2 under the canonical        */
+/*   schedule (oracle/gridgcn_oracle.c, "Coverage-Aware Sampling"); parity unpinned.            */
+/*   Same tensors as gridgcn_gridify_fwd.  `seed` replaces the reference's 2*tv_usec term: the   */
+/*   challenger of first-occurrence rank i draws from XORWOW(seed + i).  Limits: those of        */
+/*   Gridify, and max_o_grid <= 8192.  flags: GRIDGCN_FLAG_KNN_QUERY, GRIDGCN_FLAG_DIST_FMA.     */
+/* ------------------------------------------------------------------------------------------ */
+size_t gridgcn_gridify_occaware_workspace_bytes(int B, int N, int max_o_grid,
+                                                const int grid_size[3]);
+
+int gridgcn_gridify_occaware_fwd(const float *data, const int *actual_numpoints, int B, int N,
+                                 int max_o_grid, int max_p_grid, int kernel_size, int stride,
+                                 int loc, const float coord_shift[3], const float voxel_size[3],
+                                 const int grid_size[3], int flags, unsigned long long seed,
+                                 int *nebidx, float *nebidxmsk, float *cent, float *centmsk,
+                                 int *actual_centnum, void *workspace, size_t workspace_bytes,
+                                 void *stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* GridifyUp -- replaces GridifyUpOp<gpu>::Forward, gridify_up-inl.h:93-119 +                   */

@@ -185,13 +185,109 @@ static void init_outputs(int *nebidx, float *nebmsk, float *cent, float *centmsk
     centnum[0] = 0;
 }
 
+/* ---------------------------------------------------------------------------------- */
+/* Coverage-Aware Sampling (CAS), ops Gridify_occaware in the reference.                  */
+/* The reference ships these kernels ONLY as sm_61/sm_75 cubins inside                    */
+/* gridifyop/additional.so (gridify_occaware.cu / gridify_occaware-inl.h are absent from  */
+/* the tree).  The restatement below follows the sm_75 SASS of               */
+/*   gridify_kernel_build_index_occaware<float>   (K9;  `cuobjdump -sass -arch sm_75`)     */
+/*   gridify_occaware_sampling<float>             (K10)                                    */
+/* and the paper (arXiv:1912.02984 s3.2).  PARITY UNPINNED: no source, no call site, no    */
+/* test in the reference.  What the SASS shows (offsets of K10):                           */
+/*  - one thread per challenger = occupied voxel whose arrival rank is >= max_o            */
+/*    (0x0200-0x02a0: rank >= max_o and rank < actual_centnum[b]);                         */
+/*  - curand_init(2*seconds + index*iter, 0, 0), slot = ceilf(max_o * uniform) - 1         */
+/*    (0x0520-0x06a0); incumbent = voxelidx_to_coor[b*max_o + slot] (0x06b0-0x06d0);       */
+/*  - loop over the size = kernel^3 neighbour voxels of both, raster order d -> h -> w     */
+/*    (0x0910-0x12c0); incumbent side: coverage count == 1  =>  H_rmv += 0.7, and += 0.3   */
+/*    more when that neighbour voxel is occupied (coor_to_voxelidx >= 0); challenger side:  */
+/*    coverage count == 0  =>  H_add += 0.7 (+ 0.3 if occupied).  Each += is a DADD on the  */
+/*    float accumulator widened to double and narrowed back (F2F.F64.F32, DADD c[2][0]=0.7  */
+/*    / c[2][8]=0.3, F2F.F32.F64);                                                          */
+/*  - swap iff H_add > H_rmv (the `> H_rmv + 3` branch at 0x12d0-0x1320 takes the same       */
+/*    atomicCAS, it only changes the retry bookkeeping): atomicCAS(voxelidx_to_coor slot,   */
+/*    incumbent, challenger), then -1 on the coverage count of every incumbent neighbour    */
+/*    and +1 on every challenger neighbour (0x13d0-0x1e20); a lost CAS retries with         */
+/*    iter+1 / iter+2 while iter <= 3 (0x13a0-0x13c0, 0x28e0-0x2940).                        */
+/* Canonical schedule: challengers in ascending arrival rank, one after the other, so no    */
+/* CAS is ever lost and every challenger makes exactly one attempt (iter = 1).              */
+/* Oracle definitions where the reference is time-seeded or undefined:                      */
+/*  - seed: the reference uses 2*tv_usec + global thread index; canonical = caller's `seed` */
+/*    + the challenger's arrival rank inside its cloud (no batch term, so a cloud's result  */
+/*    does not depend on its position in the batch);                                        */
+/*  - neighbours outside the grid: the reference leaves their slots of the thread-local     */
+/*    index arrays unwritten and still issues the 27 unrolled REDs on them; here they are    */
+/*    skipped;                                                                              */
+/*  - the unrolled update handles exactly 27 neighbours (kernel_size 3); other odd kernel   */
+/*    sizes run the same loop here.                                                         */
+/* ---------------------------------------------------------------------------------- */
+typedef struct {
+    int *all_coor; /* G: linear voxel index of every occupied voxel, arrival order (K9 `Y`) */
+    int *cover;    /* G: number of selected centres whose neighbourhood holds the voxel     */
+    int ks;
+} occaware_t;
+
+static void occaware_cover_add(const occaware_t *oa, const int coor[3], const float *gridf,
+                               int delta) {
+    const int ks = oa->ks, size = ks * ks * ks, r = (ks - 1) / 2;
+    for (int k = 0; k < size; k++) {
+        int d = k / (ks * ks) - r + coor[2];
+        int h = (k % (ks * ks)) / ks - r + coor[1];
+        int w = k % ks - r + coor[0];
+        if (!in_grid(d, h, w, gridf)) continue;
+        oa->cover[linear_index3(d, h, w, gridf)] += delta;
+    }
+}
+
+/* H accumulation of K10 (0x0f90-0x0ff0 / 0x1220-0x1280): float -> double, DADD, -> float.   */
+static float occaware_h_step(float H, int occupied) {
+    H = (float)((double)H + 0.7);
+    if (occupied) H = (float)((double)H + 0.3);
+    return H;
+}
+
+/* K10: gridify_occaware_sampling, one cloud, canonical schedule.                           */
+static void occaware_sampling_cloud(int O, const float *gridf, gridify_scratch_t *s,
+                                    const occaware_t *oa, int nocc, uint64_t seed) {
+    const int ks = oa->ks, size = ks * ks * ks, r = (ks - 1) / 2;
+    for (int i = O; i < nocc; i++) {
+        const int chal = oa->all_coor[i];
+        xorwow_t st;
+        xorwow_init(&st, seed + (uint64_t)i);
+        float u = xorwow_uniform(&st);
+        int slot = (int)(ceilf((float)O * u) - 1.0f);
+        const int inc = s->voxelidx_to_coor[slot];
+        int ci[3], cc[3];
+        decode_center(inc, gridf, &ci[2], &ci[1], &ci[0]);
+        decode_center(chal, gridf, &cc[2], &cc[1], &cc[0]);
+        float H_add = 0.0f, H_rmv = 0.0f;
+        for (int k = 0; k < size; k++) {
+            int od = k / (ks * ks) - r, oh = (k % (ks * ks)) / ks - r, ow = k % ks - r;
+            if (in_grid(ci[2] + od, ci[1] + oh, ci[0] + ow, gridf)) {
+                int v = linear_index3(ci[2] + od, ci[1] + oh, ci[0] + ow, gridf);
+                if (oa->cover[v] == 1) H_rmv = occaware_h_step(H_rmv, s->coor_to_voxelidx[v] >= 0);
+            }
+            if (in_grid(cc[2] + od, cc[1] + oh, cc[0] + ow, gridf)) {
+                int v = linear_index3(cc[2] + od, cc[1] + oh, cc[0] + ow, gridf);
+                if (oa->cover[v] == 0) H_add = occaware_h_step(H_add, s->coor_to_voxelidx[v] >= 0);
+            }
+        }
+        if (H_add > H_rmv) {
+            s->voxelidx_to_coor[slot] = chal;
+            occaware_cover_add(oa, ci, gridf, -1);
+            occaware_cover_add(oa, cc, gridf, +1);
+        }
+    }
+}
+
 /* K1 = K3: gridify_kernel_build_index, gridify.cu:126-190 (== gridifyknn.cu:139-203),
  * one cloud, threads i_pt = 0..npts-1 executed in ascending order.
  * Canonical overflow rule (SURVEY s8c rule 7): keep-first, i.e. the time-seeded reservoir
  * branches (gridify.cu:148-153, :181-186) never replace.                                */
 static void build_index_cloud(const float *data, int npts, int O, int P, int loc,
                               const float *shift, const float *voxel, const float *gridf,
-                              gridify_scratch_t *s, float *centmsk, int *centcount) {
+                              gridify_scratch_t *s, float *centmsk, int *centcount,
+                              const occaware_t *oa) {
     int ncent = 0;
     for (int i_pt = 0; i_pt < npts; i_pt++) {
         const float *p_pt = data + (size_t)i_pt * DATA_NDIM;
@@ -216,10 +312,12 @@ static void build_index_cloud(const float *data, int npts, int O, int P, int loc
         if (s->coor_to_voxelidx[coor_indx] == -1) { /* :165-171 CAS -1 -> 0 */
             s->coor_to_voxelidx[coor_indx] = 0;
             int tmp = ncent++; /* :175 atomicAdd(out_actual_centnum) */
+            if (oa) oa->all_coor[tmp] = coor_indx; /* K9 only: every occupied voxel, arrival order */
             if (tmp < O) {
                 s->voxelidx_to_coor[tmp] = coor_indx; /* :178 */
                 centmsk[tmp] = 1.0f;                  /* :179 */
-            } /* else: keep-first */
+                if (oa) occaware_cover_add(oa, coor, gridf, +1); /* K9: coverage counts */
+            } /* else: keep-first (Gridify) / challenger of the sampling kernel (occaware) */
         }
     }
     *centcount = ncent;
@@ -425,7 +523,7 @@ static int gridify_common(int knn, const float *data, const int *npts, int B, in
             init_outputs(nb, nm, ce, cm, cn, O, P);
             scratch_reset(&s, (int)G);
             int ncent = 0;
-            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &ncent);
+            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &ncent, NULL);
             if (knn)
                 query_knn_cloud(d, O, P, ks, loc, voxel, gridf, &s, ncent, mode, nb, nm, ce, cn,
                                 best, besti);
@@ -453,6 +551,67 @@ int gridgcn_oracle_gridify_knn(const float *data, const int *npts, int B, int N,
                                float *cent, float *centmsk, int *centnum) {
     return gridify_common(1, data, npts, B, N, O, P, ks, loc, shift, voxel, grid, dist_fma,
                           nebidx, nebmsk, cent, centmsk, centnum);
+}
+
+/* Gridify_occaware: K9 build (coverage counts of the first max_o voxels), K10 sampling,
+ * then the K2 query on the selected centres (K11 has K2's signature minus the challenger
+ * list; it is taken to be K2).  knn_query != 0 runs the GridifyKNN query (K4) on the CAS
+ * centres instead -- an extension the reference does not have.  See the CAS block comment
+ * above for the parity status (unpinned).                                                  */
+int gridgcn_oracle_gridify_occaware(const float *data, const int *npts, int B, int N, int O, int P,
+                                    int ks, int loc, const float shift[3], const float voxel[3],
+                                    const int grid[3], int knn_query, int dist_fma,
+                                    unsigned long long seed, int *nebidx, float *nebmsk,
+                                    float *cent, float *centmsk, int *centnum) {
+    if (B < 0 || N < 0 || O < 1 || P < 1 || ks < 1 || (ks & 1) == 0) return -1;
+    float gridf[3];
+    set_gridf(grid, gridf);
+    const long G = (long)grid[0] * grid[1] * grid[2];
+    if (G <= 0 || G >= (1L << 24)) return -1;
+    int err = 0;
+#pragma omp parallel num_threads(g_num_threads)
+    {
+        gridify_scratch_t s;
+        occaware_t oa;
+        float *best = (float *)malloc(sizeof(float) * (size_t)P);
+        int *besti = (int *)malloc(sizeof(int) * (size_t)P);
+        oa.all_coor = (int *)malloc(sizeof(int) * (size_t)G);
+        oa.cover = (int *)malloc(sizeof(int) * (size_t)G);
+        oa.ks = ks;
+        int ok = scratch_alloc(&s, (int)G, O, P) && best && besti && oa.all_coor && oa.cover;
+        if (!ok) {
+#pragma omp atomic write
+            err = -1;
+        }
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; b++) {
+            if (!ok) continue;
+            int *nb = nebidx + (size_t)b * O * P;
+            float *nm = nebmsk + (size_t)b * O * P;
+            float *ce = cent + (size_t)b * O * DATA_NDIM;
+            float *cm = centmsk + (size_t)b * O;
+            int *cn = centnum + b;
+            const float *d = data + (size_t)b * N * DATA_NDIM;
+            int n = npts[b] < N ? npts[b] : N;
+            init_outputs(nb, nm, ce, cm, cn, O, P);
+            scratch_reset(&s, (int)G);
+            memset(oa.cover, 0, sizeof(int) * (size_t)G);
+            int nocc = 0;
+            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &nocc, &oa);
+            occaware_sampling_cloud(O, gridf, &s, &oa, nocc, (uint64_t)seed);
+            if (knn_query)
+                query_knn_cloud(d, O, P, ks, loc, voxel, gridf, &s, nocc, dist_fma, nb, nm, ce, cn,
+                                best, besti);
+            else
+                query_neighs_cloud(d, b, O, P, ks, loc, gridf, &s, nocc, 0, nb, nm, ce, cn);
+        }
+        scratch_free(&s);
+        free(best);
+        free(besti);
+        free(oa.all_coor);
+        free(oa.cover);
+    }
+    return err;
 }
 
 /* GridifyUp: gridify_up-inl.h:111-112 (outputs 0) + gridify_up.cu:121-169 (K5 build, the

@@ -83,7 +83,9 @@ def _center_xyz(data, csr, v, loc, cent_row):
 
 
 def gridify(data, npts, *, max_p_grid, max_o_grid, kernel_size, loc, coord_shift, voxel_size,
-            grid_size):
+            grid_size, select_centers=None):
+    """``select_centers(csr) -> list of centre voxels`` overrides the keep-first centre choice
+    (used by gridify_occaware below)."""
     data = np.asarray(data, F)
     B, N, _ = data.shape
     O, P, ks = max_o_grid, max_p_grid, kernel_size
@@ -93,6 +95,8 @@ def gridify(data, npts, *, max_p_grid, max_o_grid, kernel_size, loc, coord_shift
     r = (ks - 1) // 2
     for b in range(B):
         csr = _Csr(data[b], int(np.asarray(npts).reshape(-1)[b]), shift, voxel, grid)
+        if select_centers is not None:
+            csr.center_voxels = select_centers(csr)
         nc = min(len(csr.center_voxels), O)
         centnum[b, 0] = nc
         centmsk[b, :nc] = 1.0
@@ -220,3 +224,85 @@ def knn(unknown, known, downnum, upnum, *, k, radius=None, dist_fma=False):
             idx[b, q, :] = -1 if radius is not None else 0
             idx[b, q, :len(order)] = order
     return idx
+
+
+# ---------------------------------------------------------------------------------------------
+# Coverage-Aware Sampling twin (Gridify_occaware; binary-only in the reference, see the CAS block
+# comment of gridgcn_oracle.c for what the SASS of additional.so shows).  Formulated with a
+# dictionary of coverage counts and Python-integer XORWOW, independently of the C arrays.
+# ---------------------------------------------------------------------------------------------
+_M32 = 0xFFFFFFFF
+
+
+def _xorwow_first_uniform(seed):
+    """curand_init(seed, 0, 0) + one curand_uniform (curand_kernel.h:772-798,863-874;
+    curand_uniform.h:69-72 contracted to one FMA on the device)."""
+    s0 = (seed & _M32) ^ 0xaad26b49
+    s1 = ((seed >> 32) & _M32) ^ 0xf7dcefdd
+    t0 = (1099087573 * s0) & _M32
+    t1 = (2591861531 * s1) & _M32
+    d = (6615241 + t1 + t0) & _M32
+    v = [(123456789 + t0) & _M32, 362436069 ^ t0, (521288629 + t1) & _M32, 88675123 ^ t1,
+         (5783321 + t0) & _M32]
+    t = v[0] ^ (v[0] >> 2)
+    v4 = (v[4] ^ ((v[4] << 4) & _M32)) ^ (t ^ ((t << 1) & _M32))
+    d = (d + 362437) & _M32
+    x = (v4 + d) & _M32
+    # single rounding of x * 2^-32 + 2^-33: exact in float64 (x < 2^32), then one rounding to f32
+    return F(np.float64(F(x)) * np.float64(F(2.3283064e-10)) + np.float64(F(2.3283064e-10) / F(2.0)))
+
+
+def cas_select(center_voxels, occupied, O, ks, grid, seed):
+    """Returns the centre voxels after coverage-aware sampling: the first O occupied voxels (arrival
+    order) are incumbents, every later one challenges a random incumbent once, in arrival order."""
+    r = (ks - 1) // 2
+    offs = [(t // (ks * ks) - r, (t % (ks * ks)) // ks - r, t % ks - r) for t in range(ks ** 3)]
+
+    def nbrs(v):
+        c2, c1, c0 = _decode(v, grid)
+        out = []
+        for od, oh, ow in offs:
+            d, h, w = c2 + od, c1 + oh, c0 + ow
+            if 0 <= d < grid[2] and 0 <= h < grid[1] and 0 <= w < grid[0]:
+                out.append(int(d * grid[0] * grid[1] + h * grid[0] + w))
+        return out
+
+    slots = list(center_voxels[:O])
+    cover = {}
+    for v in slots:
+        for n in nbrs(v):
+            cover[n] = cover.get(n, 0) + 1
+
+    def H(v, flip):
+        h = F(0)
+        for n in nbrs(v):
+            if cover.get(n, 0) == flip:
+                h = F(np.float64(h) + 0.7)
+                if n in occupied:
+                    h = F(np.float64(h) + 0.3)
+        return h
+
+    for i in range(O, len(center_voxels)):
+        chal = center_voxels[i]
+        u = _xorwow_first_uniform(seed + i)
+        slot = int(np.ceil(F(F(O) * u)) - 1)
+        inc = slots[slot]
+        if H(chal, 0) > H(inc, 1):
+            slots[slot] = chal
+            for n in nbrs(inc):
+                cover[n] -= 1
+            for n in nbrs(chal):
+                cover[n] = cover.get(n, 0) + 1
+    return slots
+
+
+def gridify_occaware(data, npts, *, max_p_grid, max_o_grid, kernel_size, loc, coord_shift, voxel_size,
+                     grid_size, seed=0):
+    grid = np.asarray(grid_size, np.int64)
+
+    def select(csr):
+        return cas_select(csr.center_voxels, set(csr.members.keys()), max_o_grid, kernel_size, grid, seed)
+
+    return gridify(data, npts, max_p_grid=max_p_grid, max_o_grid=max_o_grid, kernel_size=kernel_size,
+                   loc=loc, coord_shift=coord_shift, voxel_size=voxel_size, grid_size=grid_size,
+                   select_centers=select)

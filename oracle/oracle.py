@@ -117,6 +117,40 @@ def gridify_knn(data, actual_numpoints, *, max_p_grid, max_o_grid, kernel_size, 
                     coord_shift, voxel_size, grid_size, 1 if dist_fma else 0)
 
 
+def gridify_occaware(data, actual_numpoints, *, max_p_grid, max_o_grid, kernel_size, stride=1, loc=0,
+                     coord_shift=(0, 0, 0), voxel_size=(1, 1, 1), grid_size=(1, 1, 1), seed=0,
+                     knn_query=False, dist_fma=False):
+    """Gridify_occaware = Gridify with Coverage-Aware Sampling of the centre voxels (binary-only in
+    the reference: additional.so, kernels gridify_kernel_build_index_occaware /
+    gridify_occaware_sampling; restated from the sm_75 SASS, see gridgcn_oracle.c).  Parity
+    unpinned."""
+    fn = lib().gridgcn_oracle_gridify_occaware
+    fn.restype = ctypes.c_int
+    fn.argtypes = [_f32p, _i32p] + [ctypes.c_int] * 6 + [_f32p, _f32p, _i32p, ctypes.c_int, ctypes.c_int,
+                                                         ctypes.c_ulonglong, _i32p, _f32p, _f32p, _f32p, _i32p]
+    data, pd = _f(data)
+    assert data.ndim == 3 and data.shape[2] == 4, "data should be (B, N, 4)"
+    B, N, _ = data.shape
+    npts, pn = _i(np.asarray(actual_numpoints).reshape(B))
+    O, P = int(max_o_grid), int(max_p_grid)
+    shift = _triple(coord_shift, np.float32)
+    voxel = _triple(voxel_size, np.float32)
+    grid = _triple(grid_size, np.int32)
+    nebidx = np.empty((B, O, P), np.int32)
+    nebmsk = np.empty((B, O, P), np.float32)
+    cent = np.empty((B, O, 4), np.float32)
+    centmsk = np.empty((B, O), np.float32)
+    centnum = np.empty((B, 1), np.int32)
+    rc = fn(pd, pn, B, N, O, P, int(kernel_size), int(loc), shift.ctypes.data_as(_f32p),
+            voxel.ctypes.data_as(_f32p), grid.ctypes.data_as(_i32p), 1 if knn_query else 0,
+            1 if dist_fma else 0, int(seed), nebidx.ctypes.data_as(_i32p),
+            nebmsk.ctypes.data_as(_f32p), cent.ctypes.data_as(_f32p), centmsk.ctypes.data_as(_f32p),
+            centnum.ctypes.data_as(_i32p))
+    if rc != 0:
+        raise ValueError("oracle rejected the arguments (rc=%d)" % rc)
+    return nebidx, nebmsk, cent, centmsk, centnum
+
+
 def gridify_up(downdata, updata, down_actual_numpoints, up_actual_numpoints, *, max_p_grid,
                max_o_grid, kernel_size, coord_shift=(0, 0, 0), voxel_size=(1, 1, 1),
                grid_size=(1, 1, 1)):

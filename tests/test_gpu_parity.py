@@ -98,6 +98,61 @@ def test_chained_layers_feed_centres_back(gg, cuda_dev, oracle_mod):
         hd, hn = want[2], want[4]
 
 
+CAS_CASES = [
+    ("seg8192_L0", 3, 8192, "surface",
+     dict(max_p_grid=64, max_o_grid=1024, kernel_size=3, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("few_slots", 2, 2048, "surface",
+     dict(max_p_grid=16, max_o_grid=256, kernel_size=3, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("clipped_aniso", 2, 600, "ball",
+     dict(max_p_grid=8, max_o_grid=20, kernel_size=3, loc=1, voxel_size=(0.25, 0.25, 0.5), grid_size=(8, 8, 4))),
+    ("kernel5", 2, 4096, "surface",
+     dict(max_p_grid=32, max_o_grid=128, kernel_size=5, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("no_challengers", 2, 200, "surface",
+     dict(max_p_grid=16, max_o_grid=512, kernel_size=3, loc=1, voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("cover_in_global", 1, 20000, "ball",
+     dict(max_p_grid=16, max_o_grid=512, kernel_size=3, loc=0, voxel_size=(0.04,) * 3, grid_size=(50,) * 3)),
+]
+
+
+@pytest.mark.parametrize("name,B,N,kind,kw", CAS_CASES, ids=[c[0] for c in CAS_CASES])
+def test_gridify_occaware_matches_oracle(gg, cuda_dev, oracle_mod, name, B, N, kind, kw):
+    """Coverage-aware sampling: the CUDA path against the canonical-schedule restatement (both follow
+    the SASS of the reference's cubins; parity with the reference itself is unpinned)."""
+    data, npts = synth.make_batch(B, N, seed0=300, kind=kind, voxels=(kw["voxel_size"][0],))
+    npts[-1, 0] = N - N // 9
+    kw = dict(kw, coord_shift=(1.0, 1.0, 1.0))
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    for seed in (0, 123456789012345):
+        _check5(gg.Gridify_occaware(d, n, stride=1, seed=seed, **kw),
+                oracle_mod.gridify_occaware(data, npts, seed=seed, **kw), "%s/occaware seed %d" % (name, seed))
+    _check5(gg.Gridify_occaware(d, n, stride=1, seed=9, knn_query=True, **kw),
+            oracle_mod.gridify_occaware(data, npts, seed=9, knn_query=True, **kw), name + "/occaware knn")
+
+
+def test_gridify_occaware_golden_and_coverage(gg, cuda_dev):
+    z = np.load(os.path.join(GOLDEN, "gridify_occaware.npz"))
+    kw = dict(max_p_grid=16, max_o_grid=256, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+              voxel_size=(0.05,) * 3, grid_size=(40,) * 3)
+    d, n = _t(z["data"], cuda_dev), _t(z["npts"], cuda_dev)
+    got = gg.Gridify_occaware(d, n, seed=2026, **kw)
+    _check5(got, [z[k] for k in NAMES], "golden/occaware")
+    # size-independent property at full size: CAS covers more occupied voxels than keep-first sampling
+    data, npts = synth.make_batch(4, 8192, seed0=900)
+    kw = dict(kw, max_p_grid=64, max_o_grid=1024)
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    cas = gg.Gridify_occaware(d, n, seed=1, **kw)[2].cpu().numpy()
+    rvs = gg.Gridify(d, n, **kw)[2].cpu().numpy()
+    for b in range(4):
+        occ = set(map(tuple, np.floor((data[b, :, :3] + np.float32(1)) / np.float32(0.05)).astype(int)))
+
+        def covered(cent):
+            cv = np.floor((cent[b, :, :3] + np.float32(1)) / np.float32(0.05)).astype(int)
+            cov = {(c[0] + i, c[1] + j, c[2] + k) for c in cv for i in (-1, 0, 1) for j in (-1, 0, 1)
+                   for k in (-1, 0, 1)}
+            return len(occ & cov) / len(occ)
+        assert covered(cas) > 0.95 and covered(cas) > covered(rvs)
+
+
 def test_gridify_up_matches_oracle(gg, cuda_dev, oracle_mod):
     for (nd, nu, P, ks, vox, grid) in ((24, 256, 5, 3, 0.4, 5), (256, 1024, 5, 3, 0.133333, 15),
                                        (1024, 8192, 5, 3, 0.05, 40), (300, 900, 40, 5, 0.25, 8),

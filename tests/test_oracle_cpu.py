@@ -186,3 +186,75 @@ def test_golden_fixtures(oracle_mod):
                 assert np.allclose(z[k], v, rtol=1e-5, atol=1e-6), (f, k)
             else:
                 assert np.array_equal(z[k], v), (f, k)
+
+
+# ------------------------------------------------------------------------------------------------
+# Coverage-Aware Sampling (Gridify_occaware): restated from the SASS of additional.so, parity unpinned
+# ------------------------------------------------------------------------------------------------
+CAS_KW = dict(max_p_grid=16, max_o_grid=256, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+              voxel_size=(0.05,) * 3, grid_size=(40,) * 3)
+
+
+def _covered_fraction(data, cent, centnum, b, voxel=0.05):
+    vox = np.floor((data[b, :, :3] + np.float32(1)) / np.float32(voxel)).astype(int)
+    occ = set(map(tuple, vox))
+    cv = np.floor((cent[b, :centnum[b, 0], :3] + np.float32(1)) / np.float32(voxel)).astype(int)
+    cov = {(c[0] + dx, c[1] + dy, c[2] + dz) for c in cv for dx in (-1, 0, 1) for dy in (-1, 0, 1)
+           for dz in (-1, 0, 1)}
+    return len(occ & cov) / len(occ)
+
+
+def test_occaware_c_oracle_matches_numpy_twin(oracle_mod):
+    from gridgcn_b200 import synth
+    from oracle import np_twin
+    data, npts = synth.make_batch(2, 1500, seed0=3)
+    npts[1, 0] = 1333
+    for seed in (0, 77, 2 ** 40 + 5):
+        a = oracle_mod.gridify_occaware(data, npts, seed=seed, **CAS_KW)
+        b = np_twin.gridify_occaware(data, npts, seed=seed, **{k: v for k, v in CAS_KW.items()})
+        for x, y, n in zip(a, b, ("nebidx", "nebidxmsk", "cent", "centmsk", "actual_centnum")):
+            assert np.array_equal(x, y), (seed, n)
+    # boundary voxels (neighbourhoods clipped by the grid) and an anisotropic grid
+    kw = dict(max_p_grid=8, max_o_grid=20, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+              voxel_size=(0.25, 0.25, 0.5), grid_size=(8, 8, 4))
+    data, npts = synth.make_batch(2, 600, seed0=9, kind="ball", voxels=(0.25,))
+    a = oracle_mod.gridify_occaware(data, npts, seed=1, **kw)
+    b = np_twin.gridify_occaware(data, npts, seed=1, **kw)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_occaware_properties(oracle_mod):
+    from gridgcn_b200 import synth
+    data, npts = synth.make_batch(3, 4096, seed0=11)
+    kw = dict(CAS_KW, max_o_grid=512)
+    cas = oracle_mod.gridify_occaware(data, npts, seed=5, **kw)
+    rvs = oracle_mod.gridify(data, npts, **kw)
+    assert np.array_equal(cas[4], rvs[4]) and np.array_equal(cas[3], rvs[3])  # count / mask unchanged
+    for b in range(3):
+        # the selected centres are distinct occupied voxels ...
+        cv = np.floor((cas[2][b, :, :3] + np.float32(1)) / np.float32(0.05)).astype(int)
+        assert len(set(map(tuple, cv))) == 512
+        # ... and cover (much) more of the occupied space than keep-first sampling: the point of CAS
+        assert _covered_fraction(data, cas[2], cas[4], b) > _covered_fraction(data, rvs[2], rvs[4], b) + 0.1
+        assert _covered_fraction(data, cas[2], cas[4], b) > 0.9
+    # different seeds give different (but equally valid) selections
+    other = oracle_mod.gridify_occaware(data, npts, seed=6, **kw)
+    assert not np.array_equal(other[2], cas[2])
+    # no challengers (occupied voxels <= max_o): identical to Gridify
+    few, nf = synth.make_batch(2, 200, seed0=2)
+    a = oracle_mod.gridify_occaware(few, nf, seed=5, **kw)
+    b = oracle_mod.gridify(few, nf, **kw)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # batch independence: a cloud's result does not depend on its position in the batch
+    solo = oracle_mod.gridify_occaware(data[2:3], npts[2:3], seed=5, **kw)
+    for x, y in zip(solo, cas):
+        assert np.array_equal(x[0], y[2])
+
+
+def test_occaware_golden(oracle_mod):
+    z = np.load(os.path.join(GOLDEN, "gridify_occaware.npz"))
+    got = oracle_mod.gridify_occaware(z["data"], z["npts"], seed=2026, **CAS_KW)
+    for g, n in zip(got, ("nebidx", "nebidxmsk", "cent", "centmsk", "actual_centnum")):
+        assert np.array_equal(g, z[n]), n
