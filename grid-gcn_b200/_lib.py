@@ -35,7 +35,7 @@ SIGNATURES = {
     "gridgcn_gridify_workspace_bytes": (_sz, [_i, _i, _i, _i3]),
     "gridgcn_gridify_fwd": (_i, _GRIDIFY_ARGS),
     "gridgcn_gridify_knn_fwd": (_i, _GRIDIFY_ARGS),
-    "gridgcn_gridify_occaware_workspace_bytes": (_sz, [_i, _i, _i, _i3]),
+    "gridgcn_gridify_occaware_workspace_bytes": (_sz, [_i, _i, _i, _i, _i3]),
     "gridgcn_gridify_occaware_fwd": (_i, _GRIDIFY_ARGS[:13] + [ctypes.c_ulonglong] + _GRIDIFY_ARGS[13:]),
     "gridgcn_gridify_up_workspace_bytes": (_sz, [_i, _i, _i3]),
     "gridgcn_gridify_up_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f3, _f3, _i3, _vp, _vp,

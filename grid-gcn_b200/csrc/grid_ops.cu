@@ -136,26 +136,27 @@ struct CasPlan {
     WsLayout L;        // build layout (cent_lin / cent_acc hold every occupied voxel)
     WsLayout Lq;       // same memory, centre arrays redirected to the sampled ones (query kernel)
     CasLayout C;
-    bool cover_in_smem, bitmap_in_smem;
+    bool cover_in_smem;
     size_t smem;
 };
 
-static CasPlan make_cas_plan(int N, int O, int G) {
+static CasPlan make_cas_plan(int N, int O, const int grid[3], int ks) {
     CasPlan p;
-    const int V = N < G ? N : G, W = (G + 31) / 32;
+    const int G = grid[0] * grid[1] * grid[2];
+    const int V = N < G ? N : G;
+    const long long Gp = cas_padded_volume(grid, ks);
     p.L = make_layout(N, V < 1 ? 1 : V, G);
     long long off = p.L.stride;
     p.C.cent_lin_out = (int)off;  off += round4(O);
     p.C.cent_acc_out = (int)off;  off += round4(4LL * O);
-    p.cover_in_smem = cas_smem_bytes(G, W, O, true, false) <= kBuildSmemLimit;
-    p.bitmap_in_smem = cas_smem_bytes(G, W, O, p.cover_in_smem, true) <= kBuildSmemLimit;
+    p.cover_in_smem = cas_smem_bytes(Gp, O, true) <= kBuildSmemLimit;
     p.C.cover = (int)off;
-    if (!p.cover_in_smem) off += round4((G + 1) / 2);
+    if (!p.cover_in_smem) off += round4((Gp + 1) / 2);
     p.L.stride = off;
     p.Lq = p.L;
     p.Lq.cent_lin = p.C.cent_lin_out;
     p.Lq.cent_acc = p.C.cent_acc_out;
-    p.smem = cas_smem_bytes(G, W, O, p.cover_in_smem, p.bitmap_in_smem);
+    p.smem = cas_smem_bytes(Gp, O, p.cover_in_smem);
     return p;
 }
 
@@ -168,28 +169,26 @@ static int gridify_occaware_impl(const float *data, const int *npts, int B, int 
     int rc = check_grid_args(B, N, O, P, ks, shift, voxel, grid, g);
     if (rc) return rc;
     if (!data || !npts || !nebidx || !nebmsk || !cent || !centmsk || !centnum) return GRIDGCN_EINVAL;
-    if (O > 8192) return GRIDGCN_ELIMIT;  // slot tables live in shared memory
+    if (O > 8192 || ks > 9) return GRIDGCN_ELIMIT;  // slot table in shared memory; padded grid
     g.loc = loc;
     g.flags = flags;
     if (B == 0) return 0;
-    if (!ws || ws_bytes < gridgcn_gridify_occaware_workspace_bytes(B, N, O, grid))
+    if (!ws || ws_bytes < gridgcn_gridify_occaware_workspace_bytes(B, N, O, ks, grid))
         return GRIDGCN_EWORKSPACE;
     if ((reinterpret_cast<uintptr_t>(ws) & 15) || (reinterpret_cast<uintptr_t>(data) & 15) ||
         (reinterpret_cast<uintptr_t>(cent) & 15))
         return GRIDGCN_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const CasPlan p = make_cas_plan(N, O, g.G);
+    const CasPlan p = make_cas_plan(N, O, grid, ks);
     GridParams gb = g;  // build: every occupied voxel is a candidate centre
     gb.O = N < g.G ? N : g.G;
     if (gb.O < 1) gb.O = 1;
     cudaError_t e = launch_build(data, npts, gb, static_cast<int *>(ws), p.L, nullptr, nullptr, 1, st);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(cas_sampling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)kBuildSmemLimit);
+    auto kern = p.cover_in_smem ? cas_sampling_kernel<true> : cas_sampling_kernel<false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBuildSmemLimit);
     if (e != cudaSuccess) return (int)e;
-    cas_sampling_kernel<<<B, kCasThreads, p.smem, st>>>(g, static_cast<int *>(ws), p.L, p.C, seed,
-                                                        centmsk, centnum, p.cover_in_smem ? 1 : 0,
-                                                        p.bitmap_in_smem ? 1 : 0);
+    kern<<<B, kCasThreads, p.smem, st>>>(g, static_cast<int *>(ws), p.L, p.C, seed, centmsk, centnum);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     return launch_gridify_query((flags & GRIDGCN_FLAG_KNN_QUERY) != 0, data, g, ws, p.Lq, nebidx,
@@ -250,12 +249,12 @@ int gridgcn_gridify_knn_fwd(const float *data, const int *actual_numpoints, int 
                         centmsk, actual_centnum, workspace, workspace_bytes, stream);
 }
 
-size_t gridgcn_gridify_occaware_workspace_bytes(int B, int N, int max_o_grid,
+size_t gridgcn_gridify_occaware_workspace_bytes(int B, int N, int max_o_grid, int kernel_size,
                                                 const int grid_size[3]) {
-    if (B <= 0 || N < 0 || max_o_grid < 1 || !grid_size) return 0;
+    if (B <= 0 || N < 0 || max_o_grid < 1 || kernel_size < 1 || kernel_size > 9 || !grid_size) return 0;
     long long G = (long long)grid_size[0] * grid_size[1] * grid_size[2];
     if (G < 1 || G > kMaxGridVoxels) return 0;
-    return (size_t)make_cas_plan(N, max_o_grid, (int)G).L.stride * 4 * (size_t)B;
+    return (size_t)make_cas_plan(N, max_o_grid, grid_size, kernel_size).L.stride * 4 * (size_t)B;
 }
 
 int gridgcn_gridify_occaware_fwd(const float *data, const int *actual_numpoints, int B, int N,

@@ -48,8 +48,12 @@ def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_siz
     O, P = int(max_o_grid), int(max_p_grid)
     dev = data.device
     grid = _lib.triple_i(grid_size)
-    ws_fn = L.gridgcn_gridify_workspace_bytes if seed is None else L.gridgcn_gridify_occaware_workspace_bytes
-    ws_bytes = ws_fn(B, N, O, grid) if B > 0 else 0
+    if B <= 0:
+        ws_bytes = 0
+    elif seed is None:
+        ws_bytes = L.gridgcn_gridify_workspace_bytes(B, N, O, grid)
+    else:
+        ws_bytes = L.gridgcn_gridify_occaware_workspace_bytes(B, N, O, int(kernel_size), grid)
     if B > 0 and ws_bytes == 0:
         raise _lib.GridGcnError("%s: unsupported sizes (max_o_grid >= 1, grid volume <= 262144)" % fn_name)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)

@@ -91,9 +91,9 @@ int gridgcn_gridify_knn_fwd(const float *data, const int *actual_numpoints, int 
 /*   schedule (oracle/gridgcn_oracle.c, "Coverage-Aware Sampling"); parity unpinned.            */
 /*   Same tensors as gridgcn_gridify_fwd.  `seed` replaces the reference's 2*tv_usec term: the   */
 /*   challenger of first-occurrence rank i draws from XORWOW(seed + i).  Limits: those of        */
-/*   Gridify, and max_o_grid <= 8192.  flags: GRIDGCN_FLAG_KNN_QUERY, GRIDGCN_FLAG_DIST_FMA.     */
+/*   Gridify, max_o_grid <= 8192, kernel_size <= 9.  flags: GRIDGCN_FLAG_KNN_QUERY, GRIDGCN_FLAG_DIST_FMA.     */
 /* ------------------------------------------------------------------------------------------ */
-size_t gridgcn_gridify_occaware_workspace_bytes(int B, int N, int max_o_grid,
+size_t gridgcn_gridify_occaware_workspace_bytes(int B, int N, int max_o_grid, int kernel_size,
                                                 const int grid_size[3]);
 
 int gridgcn_gridify_occaware_fwd(const float *data, const int *actual_numpoints, int B, int N,

@@ -1,5 +1,7 @@
 """CPU suite, part 3: host-side logic of the product (BN folding, parameter naming, ladders,
 synthetic inputs) -- no GPU needed."""
+import os
+
 import numpy as np
 
 from gridgcn_b200 import gridconv, stack, synth
@@ -80,3 +82,26 @@ def test_reference_yaml_keys_are_understood():
         stack.from_reference_config(dict(max_o_grid_lst=[8], voxel_size_lst=[[0.1, 0.2, 0.1]],
                                          grid_size_lst=[[4, 4, 4]], max_p_grid_lst=[4], kernel_size_lst=[3],
                                          pt_ele_dim=[[8]], num_points=16))
+
+
+def test_cas_state_table_is_current():
+    """grid-gcn_b200/csrc/cas_h_table.inc is generated: regenerate and compare; spot-check that walking
+    the table reproduces the float/double arithmetic it stands for and that ids order like values."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_cas_table", os.path.join(root, "tools", "gen_cas_table.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    with open(gen.PATH) as f:
+        assert f.read() == gen.render()
+    values, nxt_a, nxt_ac = gen.build()
+    assert values[0] == 0 and all(a < b for a, b in zip(values, values[1:]))
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        s, h = 0, np.float32(0)
+        for occ in rng.integers(0, 2, size=27):
+            s = (nxt_ac if occ else nxt_a)[s]
+            h = np.float32(np.float64(h) + 0.7)
+            if occ:
+                h = np.float32(np.float64(h) + 0.3)
+            assert values[s] == h
