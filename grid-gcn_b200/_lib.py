@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgridgcn_b200.so")
+# GRIDGCN_B200_LIB: developer override to A/B an experimental build of the same C-ABI (tools/)
+LIB_PATH = os.environ.get("GRIDGCN_B200_LIB") or os.path.join(_HERE, "libgridgcn_b200.so")
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -298,8 +298,11 @@ __device__ __forceinline__ void append_batch(TopP<CAP> &tp, const int *sorted, i
 // ids of every voxel in loop order w -> h -> d, stable sort by squared distance to the voxel
 // centre in the shifted frame, stop after the first shell with cumulative candidates >= P.
 // ------------------------------------------------------------------------------------------------
+#ifndef GG_KNN_MIN_CTAS
+#define GG_KNN_MIN_CTAS 4  // resident CTAs per SM the register allocation is bounded for (tools/build_variant.py)
+#endif
 template <int CAP>
-__global__ void __launch_bounds__(kQueryWarps * 32, 3)
+__global__ void __launch_bounds__(kQueryWarps * 32, GG_KNN_MIN_CTAS)
 gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
                          const int *__restrict__ ws_base, WsLayout L,
                          const int *__restrict__ centnum, int *__restrict__ nebidx,

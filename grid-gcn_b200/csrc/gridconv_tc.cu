@@ -120,6 +120,48 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// ---- attention stage 0, folded --------------------------------------------------------------------
+// att_vec = [dist, d, c, n] with n = c + d (gcn_module_g_att.py:209-222), so
+//     W a + b = w_dist dist + (W_d + W_n) d + (W_c + W_n) c + b :
+// 7 multiply-adds per channel instead of 10 and two 16-byte weight loads instead of three.  The kernels
+// keep the folded weights in shared memory as wa0_s[kh][8] = (w_dist, wd_x, wd_y, wd_z | wc_x, wc_y, wc_z, b).
+struct Att7 {
+    float dist, dx, dy, dz, cx, cy, cz;
+};
+__device__ __forceinline__ Att7 fold_att(int attfdim, const float *att) {
+    Att7 a;
+    if (attfdim <= 3) {
+        a.dist = 0.f; a.dx = att[0]; a.dy = att[1]; a.dz = att[2];
+    } else {
+        a.dist = att[0]; a.dx = att[1]; a.dy = att[2]; a.dz = att[3];
+    }
+    const bool full = attfdim >= 10;
+    a.cx = full ? att[4] : 0.f; a.cy = full ? att[5] : 0.f; a.cz = full ? att[6] : 0.f;
+    return a;
+}
+// element q (0..7) of channel j's folded row
+__device__ __forceinline__ float att0_folded_weight(const float *w, const float *b, int cin, int cout, int j,
+                                                   int q) {
+    if (j >= cout) return 0.f;
+    const float *r = w + (size_t)j * cin;
+    if (q == 7) return __ldg(b + j);
+    if (cin >= 10) {
+        if (q == 0) return __ldg(r);
+        if (q < 4) return __ldg(r + q) + __ldg(r + q + 6);        // W_d + W_n
+        return __ldg(r + q) + __ldg(r + q + 3);                   // W_c + W_n   (q = 4..6)
+    }
+    if (q >= 4) return 0.f;
+    if (cin == 4) return __ldg(r + q);
+    return q == 0 ? 0.f : (q - 1 < cin ? __ldg(r + q - 1) : 0.f);  // [d] only
+}
+__device__ __forceinline__ float att0_channel(const float4 wd, const float4 wc, const Att7 &a) {
+    float acc = wc.w;
+    acc = fmaf(wc.x, a.cx, acc); acc = fmaf(wc.y, a.cy, acc); acc = fmaf(wc.z, a.cz, acc);
+    acc = fmaf(wd.x, a.dist, acc); acc = fmaf(wd.y, a.dx, acc);
+    acc = fmaf(wd.z, a.dy, acc); acc = fmaf(wd.w, a.dz, acc);
+    return acc;
+}
+
 constexpr int kMaxSeq = 128;  // slices per tile (3 stages x <= 4 chunks x <= 8 slices)
 
 // Weight ring.  All bookkeeping is done by ONE thread (the MMA issuer) and sits on its critical path between
@@ -672,7 +714,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     size_t wres_bytes = 0;
     for (int s = 0; s < p.nfh; s++) wres_bytes += (size_t)2 * p.fh[s].Np * p.fh[s].Kp * 4;
     // CUDA-core stage weights, zero padded so that the inner loops need no bounds checks:
-    //   wa0_s[kh][12]: 10 weights, bias in slot 10 (att[10] == 1), 0;   wf0_s[kf0][4]: w0 w1 w2 bias
+    //   wa0_s[kh][8]: folded attention stage-0 rows (att0_folded_weight; the region keeps its kh*12 floats);   wf0_s[kf0][4]: w0 w1 w2 bias
     float *wa0_s = reinterpret_cast<float *>(wres + wres_bytes);
     const int kf0 = (FIRST && p.f0_cuda) ? pad_to(p.f0_cout, 8) : 0;
     float *wf0_s = wa0_s + kh * 12;
@@ -731,15 +773,8 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             for (int i = tid; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
             off += (size_t)n4 * 16;
         }
-        for (int i = tid; i < kh * 12; i += kTcThreads) {
-            const int j = i / 12, q = i % 12;
-            float v = 0.f;
-            if (j < p.a0_cout) {
-                if (q < p.a0_cin) v = __ldg(p.a0_w + (size_t)j * p.a0_cin + q);
-                else if (q == 10) v = __ldg(p.a0_b + j);
-            }
-            wa0_s[i] = v;
-        }
+        for (int i = tid; i < kh * 8; i += kTcThreads)  // folded rows, see att0_folded_weight
+            wa0_s[i] = att0_folded_weight(p.a0_w, p.a0_b, p.a0_cin, p.a0_cout, i >> 3, i & 7);
         for (int i = tid; i < kf0 * 4; i += kTcThreads) {
             const int j = i / 4, q = i % 4;
             wf0_s[i] = j < p.f0_cout ? (q < 3 ? __ldg(p.f0_w + (size_t)j * 3 + q) : __ldg(p.f0_b + j)) : 0.f;
@@ -826,6 +861,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             float dx = 0.f, dy = 0.f, dz = 0.f;
             const uint32_t roff = pf_roff;
             if (pf_valid) att_vector(attfdim, pf_cent, pf_head.x, pf_head.y, pf_head.z, att, dx, dy, dz);
+            const Att7 a7 = fold_att(attfdim, att);
             {   // request the next tile's neighbour index now; its row / centre are requested later
                 const long long ncenter = (long long)(tile + gridDim.x) * cpt + my_cl;
                 pf_valid = (tile + (int)gridDim.x) < num_tiles && my_cl < cpt && ncenter < centers_total;
@@ -835,17 +871,11 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             if (!FIRST) rowoff_s[tid] = roff;
             // attention stage 0: h = relu(W a + b), K <= 10, exact fp32 (bias folded in as w[10] * 1)
             for (int g = 0; g < kh / 4; g++) {
-                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 48);
+                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 32);
                 float hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const float4 w0 = w4[i * 3], w1 = w4[i * 3 + 1], w2 = w4[i * 3 + 2];
-                    float acc = w2.z;  // bias (att[10] == 1)
-                    acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
-                    acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
-                    acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
-                    acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
-                    acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
+                    const float acc = att0_channel(w4[i * 2], w4[i * 2 + 1], a7);
                     tc::split_op<NSPLIT>(fmaxf(acc, 0.f), hi[i], lo[i]);
                 }
                 const uint32_t off = row_off + (uint32_t)g * LBO;
@@ -1058,8 +1088,12 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
 //     needs one SHFL, and all four epilogue warps are busy (the 128-row variant idles two).
 //   * TMEM: 128 columns (F|G) + a second allocation for the hidden-stage accumulators (32): 160 <= 512/3.
 //   * shared memory: the attention operand image aliases the lo half of the feature image (attention stage 1
-//     is issued first and has retired before the feature path writes its lo parts), and the last-stage weight
-//     images keep only their 64 live rows: ~66 KB per CTA instead of ~108 KB.
+//     is issued first and has retired before the feature path writes its lo parts -- which wait in the idle
+//     hidden accumulator's TMEM columns of their thread's lane meanwhile, tcgen05.st / ld), and the last-stage
+//     weight images keep only their 64 live rows: ~66 KB per CTA instead of ~108 KB.
+//   Tried and dropped (r01, measured): starting the F|G accumulators at the bias through tcgen05.st (saves the
+//     bias adds, but the stores + wait::st sit on the tile's critical path: +6 %); picking the epilogue halves
+//     by TMEM address (tcgen05.ld addresses must be warp-uniform).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc_raw(uint32_t *smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_dst)),
@@ -1099,7 +1133,7 @@ __host__ __device__ inline First64Layout first64_layout(const TcParams &p) {
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 3)
-edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, int hid_cols) {
+edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, int hid_cols, int stash_lo) {
     static_assert(NSPLIT == 3, "compact first-layer kernel: 3-pass mode only");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar_mma_s;
@@ -1152,15 +1186,8 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
         };
         load_compact(p.ff, L.wff_hi, L.wff_lo);
         load_compact(p.a1, L.wa1_hi, L.wa1_lo);
-        for (int i = tid; i < kh * 12; i += kTcThreads) {
-            const int j = i / 12, q = i % 12;
-            float v = 0.f;
-            if (j < p.a0_cout) {
-                if (q < p.a0_cin) v = __ldg(p.a0_w + (size_t)j * p.a0_cin + q);
-                else if (q == 10) v = __ldg(p.a0_b + j);
-            }
-            wa0_s[i] = v;
-        }
+        for (int i = tid; i < kh * 8; i += kTcThreads)  // folded rows, see att0_folded_weight
+            wa0_s[i] = att0_folded_weight(p.a0_w, p.a0_b, p.a0_cin, p.a0_cout, i >> 3, i & 7);
         for (int i = tid; i < kf0 * 4; i += kTcThreads) {
             const int j = i / 4, q = i % 4;
             wf0_s[i] = j < p.f0_cout ? (q < 3 ? __ldg(p.f0_w + (size_t)j * 3 + q) : __ldg(p.f0_b + j)) : 0.f;
@@ -1189,6 +1216,7 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
     const bool chv = warp < 4 && ch < C;
     const float bias_fg = chv ? __ldg((is_g ? p.a1.bias : p.ff.bias) + ch) : 0.f;
     const float pre_floor = c.pre_relu ? 0.f : -3.402823466e+38f;
+    const uint32_t lane_taddr = ((uint32_t)((warp & 3) * 32)) << 16;  // this thread's TMEM lane quadrant
 
     const int my_cl = tid / K, my_slot = tid - my_cl * K;
     bool pf_valid = false;
@@ -1223,6 +1251,7 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
             for (int i = 0; i < 12; i++) att[i] = 0.f;
             att[10] = 1.f;
             if (pf_valid) att_vector(attfdim, pf_cent, pf_head.x, pf_head.y, pf_head.z, att, dx, dy, dz);
+            const Att7 a7 = fold_att(attfdim, att);
             {
                 const long long ncenter = (long long)(tile + gridDim.x) * cpt + my_cl;
                 pf_valid = (tile + (int)gridDim.x) < num_tiles && my_cl < cpt && ncenter < centers_total;
@@ -1230,17 +1259,11 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
                 if (pf_valid) pf_idx = __ldg(c.nebidx + ncenter * K + my_slot);
             }
             for (int g = 0; g < kh / 4; g++) {
-                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 48);
+                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 32);
                 float hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const float4 w0 = w4[i * 3], w1 = w4[i * 3 + 1], w2 = w4[i * 3 + 2];
-                    float acc = w2.z;
-                    acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
-                    acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
-                    acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
-                    acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
-                    acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
+                    const float acc = att0_channel(w4[i * 2], w4[i * 2 + 1], a7);
                     tc::split_op<NSPLIT>(fmaxf(acc, 0.f), hi[i], lo[i]);
                 }
                 const uint32_t off = row_off + (uint32_t)g * LBO;
@@ -1283,12 +1306,32 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
                     v[i] = fmaxf(fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, w.w))), 0.f);
                 }
                 *reinterpret_cast<float4 *>(xf_hi + row_off + (uint32_t)g * LBO) = make_float4(v[0], v[1], v[2], v[3]);
+                if (stash_lo) {  // the lo parts wait in this thread's lane of the (idle) hidden accumulator
+                    float h0, h1, h2, h3, l0, l1, l2, l3;
+                    tc::split_op<NSPLIT>(v[0], h0, l0); tc::split_op<NSPLIT>(v[1], h1, l1);
+                    tc::split_op<NSPLIT>(v[2], h2, l2); tc::split_op<NSPLIT>(v[3], h3, l3);
+                    tc::tmem_st4(tmem_h + lane_taddr + (uint32_t)(g * 4), l0, l1, l2, l3);
+                }
             }
+            if (stash_lo) tc::tmem_st_wait();
         }
         wait_bar(bar_mma, mma_phase);
         mma_phase ^= 1;
         tc::fence_after_sync();
-        if (warp < 4) {
+        if (warp < 4 && stash_lo) {
+            for (int g = 0; g < kf0 / 4; g += 4) {  // kf0 is a multiple of 8: groups of up to 4 x 4 columns
+                uint32_t l[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (g + q < kf0 / 4) tc::tmem_ld4(tmem_h + lane_taddr + (uint32_t)((g + q) * 4), l[q]);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (g + q < kf0 / 4)
+                        *reinterpret_cast<uint4 *>(xf_lo + row_off + (uint32_t)(g + q) * LBO) =
+                            make_uint4(l[q][0], l[q][1], l[q][2], l[q][3]);
+            }
+        } else if (warp < 4) {  // no room in the hidden accumulator: recompute
             for (int g = 0; g < kf0 / 4; g++) {
                 const float4 *w4 = reinterpret_cast<const float4 *>(wf0_s + g * 16);
                 float lo[4];
@@ -1490,15 +1533,8 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
         tc::mbar_init(bar_mma, 1);
         tc::mbar_init_fence();
     }
-    for (int i = tid; i < kh * 12; i += kWideThreads) {
-        const int j = i / 12, q = i % 12;
-        float v = 0.f;
-        if (j < p.a0_cout) {
-            if (q < p.a0_cin) v = __ldg(p.a0_w + (size_t)j * p.a0_cin + q);
-            else if (q == 10) v = __ldg(p.a0_b + j);
-        }
-        wa0_s[i] = v;
-    }
+    for (int i = tid; i < kh * 8; i += kWideThreads)  // folded rows, see att0_folded_weight
+        wa0_s[i] = att0_folded_weight(p.a0_w, p.a0_b, p.a0_cin, p.a0_cout, i >> 3, i & 7);
     for (int i = tid; i < Cp; i += kWideThreads) bias_a1_s[i] = i < C ? __ldg(p.a1.bias + i) : 0.f;
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -1557,6 +1593,7 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             float dx, dy, dz;
             const uint32_t roff = pf_roff;
             if (pf_valid) att_vector(attfdim, pf_cent, pf_head.x, pf_head.y, pf_head.z, att, dx, dy, dz);
+            const Att7 a7 = fold_att(attfdim, att);
             {
                 const long long ncenter = (long long)(tile + gridDim.x) * cpt + my_cl;
                 pf_valid = (tile + (int)gridDim.x) < num_tiles && my_cl < cpt && ncenter < centers_total;
@@ -1566,17 +1603,11 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             if (half == 0) rowoff_s[row] = roff;
             const int gh = kh / 8;  // groups of 4 channels per half
             for (int g = half * gh; g < (half + 1) * gh; g++) {
-                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 48);
+                const float4 *w4 = reinterpret_cast<const float4 *>(wa0_s + g * 32);
                 float hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const float4 w0 = w4[i * 3], w1 = w4[i * 3 + 1], w2 = w4[i * 3 + 2];
-                    float acc = w2.z;
-                    acc = fmaf(w0.x, att[0], acc); acc = fmaf(w0.y, att[1], acc);
-                    acc = fmaf(w0.z, att[2], acc); acc = fmaf(w0.w, att[3], acc);
-                    acc = fmaf(w1.x, att[4], acc); acc = fmaf(w1.y, att[5], acc);
-                    acc = fmaf(w1.z, att[6], acc); acc = fmaf(w1.w, att[7], acc);
-                    acc = fmaf(w2.x, att[8], acc); acc = fmaf(w2.y, att[9], acc);
+                    const float acc = att0_channel(w4[i * 2], w4[i * 2 + 1], a7);
                     tc::split_op<NSPLIT>(fmaxf(acc, 0.f), hi[i], lo[i]);
                 }
                 const uint32_t off = row_off + (uint32_t)g * LBO;
@@ -1792,13 +1823,13 @@ static void kernel_b_sequence(const TcParams &p, int &n_slices, size_t &seq_byte
 constexpr size_t kSmemCap = 224 * 1024;  // dynamic part; static barriers/index cache use < 3 KB of the 227 KB
 
 static void launch_first64(const TcParams &p, int blocks, size_t smem, cudaStream_t st, int tiles, int cpt,
-                           int hid) {
+                           int hid, int stash_lo) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(edge_first64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
         attr_set = true;
     }
-    edge_first64_kernel<3><<<blocks, kTcThreads, smem, st>>>(p, tiles, cpt, hid);
+    edge_first64_kernel<3><<<blocks, kTcThreads, smem, st>>>(p, tiles, cpt, hid, stash_lo);
 }
 
 template <int NSPLIT>
@@ -1897,7 +1928,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
                 const long long tiles = (centers + cpt - 1) / cpt;
                 if (tiles > 0x7fffffff) return GRIDGCN_ELIMIT;
                 const int blocks = (int)min(tiles, (long long)sms * per_sm);
-                launch_first64(p, blocks, smem, st, (int)tiles, cpt, hid);
+                launch_first64(p, blocks, smem, st, (int)tiles, cpt, hid, L.kf0 <= hid ? 1 : 0);
                 return (int)cudaGetLastError();
             }
         }
