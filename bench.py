@@ -94,7 +94,10 @@ class ClockSampler(threading.Thread):
 def cpu_stack(oracle, gridconv_oracle, cfg, params, data, npts, pool=None):
     """The reference algorithm's CPU port over a batch: oracle query (C, OpenMP over clouds) + numpy
     GridConv per layer (one cloud per worker thread; numpy releases the GIL)."""
-    q = oracle.gridify_knn if cfg.query == "gridifyknn" else oracle.gridify
+    if cfg.query.startswith("occaware"):
+        q = lambda *a, **kw: oracle.gridify_occaware(*a, seed=cfg.cas_seed, knn_query=cfg.query.endswith("knn"), **kw)
+    else:
+        q = oracle.gridify_knn if cfg.query == "gridifyknn" else oracle.gridify
     table, loc, num = data, data, npts
     for l, p in zip(cfg.layers, params):
         nebidx, _, cent, centmsk, num = q(loc, num, max_p_grid=l.max_p_grid, max_o_grid=l.max_o_grid,
@@ -151,7 +154,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=192, help="clouds per GPU per step")
     ap.add_argument("--K", type=int, default=64)
-    ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify"])
+    ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify", "occaware", "occaware_knn"],
+                    help="centre sampling + neighbour query operator (occaware = coverage-aware sampling)")
+    ap.add_argument("--workload", default="seg8192", choices=["seg8192", "cls1024", "seg81920"],
+                    help="seg8192: BASELINE.json's metric configuration (N=8192, 4 layers); cls1024: N=1024 4-layer "
+                         "ladder (config 2); seg81920: the shipped 81920-point ladder (config 4, 3 layers, P0=128)")
     ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "tf32x3"),
                     choices=["tf32x3", "tf32", "fp32"])
     ap.add_argument("--cpu-clouds", type=int, default=0,
@@ -165,16 +172,26 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     from gridgcn_b200 import stack
-    cfg = stack.seg8192_4layer(args.K, args.query)
+    if args.workload == "seg8192":
+        cfg = stack.seg8192_4layer(args.K, args.query)
+        wl_name = "seg8192 4-layer GridConv encoder (O=1024/256/64/16, K=%d, N=8192)" % args.K
+    elif args.workload == "cls1024":
+        cfg = stack.cls1024_4layer(args.K, args.query)
+        wl_name = "cls1024 4-layer GridConv encoder (O=512/128/32/8, K=%d, N=1024)" % args.K
+    else:
+        cfg = stack.seg81920_shipped(args.query)
+        wl_name = "seg81920 shipped 3-layer GridConv encoder (O=1024/256/24, P=128/32/32, N=81920)"
     params = stack.init_params(cfg, seed=0)
     macs = layer_macs(params)
     flops_cloud = [2 * l.max_o_grid * l.max_p_grid * m for l, m in zip(cfg.layers, macs)]
-    config = {"workload": "seg8192 4-layer GridConv encoder (O=1024/256/64/16, K=%d, N=8192), "
-                          "query=%s, synthetic surface clouds" % (args.K, args.query),
+    config = {"workload": "%s, query=%s, synthetic surface clouds" % (wl_name, args.query),
               "clouds_per_gpu": args.batch, "points_per_cloud": cfg.num_points, "K": args.K,
               "precision": args.precision, "parallelism": "batch-sharded clouds x%d, no collective" % world,
               "l2": "value: L2 flushed (256 MiB write) between timed steps; e2e: inputs rewritten by H2D every step and "
                     "the per-step working set (index + feature tables) exceeds the 126 MB L2"}
+
+    metric_name = "points/sec through %d-layer GridConv @ N=%d, K=%d" % (len(cfg.layers), cfg.num_points,
+                                                                        cfg.layers[0].max_p_grid)
 
     # ------------------------------------------------------------------ reference (CPU) arm
     if args.impl == "reference":
@@ -182,14 +199,15 @@ def main():
             return 0
         steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
         val, dt, cores = time_cpu(cfg, params, args.cpu_clouds, steps, warmup)
-        line = {"impl": "reference", "metric": "points/sec through 4-layer GridConv @ N=8192, K=%d" % args.K,
+        line = {"impl": "reference", "metric": metric_name,
                 "value": val, "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
-                                 "sample": "%d clouds of 8192 points per step, %d steps (oracle C port: OpenMP over "
+                                 "sample": "%d clouds of %d points per step, %d steps (oracle C port: OpenMP over "
                                            "clouds for the grid ops, one thread per cloud for the numpy GridConv); "
-                                           "the reference has no CPU Gridify (gridify.cc:30-39)" % (args.cpu_clouds, steps)},
+                                           "the reference has no CPU Gridify (gridify.cc:30-39)"
+                                           % (args.cpu_clouds, cfg.num_points, steps)},
                 "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -325,7 +343,7 @@ def main():
     for i, l in enumerate(cfg.layers):
         loc_in = data_d if i == 0 else trace[i - 1]["cent"]
         num_in = npts_d if i == 0 else trace[i - 1]["actual_centnum"]
-        qf = gg.GridifyKNN if cfg.query == "gridifyknn" else gg.Gridify
+        qf = stack.query_fn(cfg)
         kwl = dict(max_o_grid=l.max_o_grid, max_p_grid=l.max_p_grid, kernel_size=l.kernel_size, stride=1,
                    coord_shift=cfg.coord_shift, voxel_size=[l.voxel_size] * 3,
                    grid_size=[l.grid_size] * 3, loc=cfg.loc)
@@ -361,11 +379,13 @@ def main():
     q_bytes = B * gridify_bytes(cfg.num_points, l0.max_o_grid, l0.max_p_grid)
     q_gbs = q_bytes / (q_ms * 1e-3) / 1e9
 
-    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01_traffic.json),
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01p_traffic.json),
     # scaled to this run's batch; null when no capture exists for the kernel
     traffic = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        if not (args.workload == "seg8192" and args.K == 64 and args.query == "gridifyknn"):
+            raise KeyError("the committed capture is of the default workload only")
+        with open(os.path.join(ROOT, "profiles", "r01p_traffic.json")) as f:
             tj = json.load(f)["per_launch"]
         for k, v in tj.items():
             traffic[k] = (v["dram_read_bytes"] + v["dram_write_bytes"]) * B / v["clouds"]
@@ -379,7 +399,7 @@ def main():
                 "note": "achieved = flops the restructured layer executes (x1, split passes not counted) / "
                         "duration; algorithmic_tflops uses SURVEY s8d's per-edge formula 2*O*K*MAC",
                 "peak_source": peaks["_source"] + " dense bf16 cuBLAS (sustained); tf32 nominal peak is half of bf16"}
-    roofline_hbm = {"kernel": "gridifyknn (build + query) N=8192 O=1024 P=%d" % l0.max_p_grid,
+    roofline_hbm = {"kernel": "gridifyknn (build + query) N=%d O=%d P=%d" % (cfg.num_points, l0.max_o_grid, l0.max_p_grid),
                     "bound": "hbm", "achieved": q_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": q_gbs / peaks["hbm_gbs"],
                     "traffic": (traffic["knn_query"] + traffic.get("build", 0.0)) if "knn_query" in traffic else None,
@@ -387,7 +407,7 @@ def main():
                     "algorithmic_bytes": q_bytes, "peak_source": peaks["_source"]}
 
     cpu_val, cpu_dt, cores = time_cpu(cfg, params, args.cpu_clouds, 2, 1)
-    line = {"metric": "points/sec through 4-layer GridConv @ N=8192, K=%d" % args.K,
+    line = {"metric": metric_name,
             "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -395,11 +415,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(world * (data_h.numel() * 4 + npts_h.numel() * 4)),
                     "d2h_bytes_per_step": int(world * out_h.numel() * 4)},
-            "gpu_launches": args.steps * (len(cfg.layers) * 3 + (0 if args.precision == "fp32" else len(cfg.layers) - 1)),
+            # per layer: voxel-table build, query (+ the sampling kernel for occaware), edge kernel; layers with input
+            # features run the per-point MLP kernel first in the tensor-core precisions
+            "gpu_launches": args.steps * (len(cfg.layers) * (4 if args.query.startswith("occaware") else 3) +
+                                          (0 if args.precision == "fp32" else len(cfg.layers) - 1)),
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": {"value": cpu_val, "unit": "points/s", "cores": cores, "kind": "port",
-                             "sample": "%d clouds of 8192 points, 2 steps (oracle C port: OpenMP over clouds for the grid "
-                                       "ops, one thread per cloud for the numpy GridConv)" % args.cpu_clouds},
+                             "sample": "%d clouds of %d points, 2 steps (oracle C port: OpenMP over clouds for the grid "
+                                       "ops, one thread per cloud for the numpy GridConv)" % (args.cpu_clouds, cfg.num_points)},
             "breakdown_ms": {"query": query_ms, "gridconv": conv_ms,
                              "note": "each operator timed alone, L2 flushed before every call"},
             "clocks": sampler.summary()}

@@ -37,7 +37,9 @@ class StackCfg:
     loc: int = 1                                     # loc_within: True
     attfdim: int = 10
     pre_relu: bool = True                            # configs["relu"]
-    query: str = "gridifyknn"                        # or "gridify" (what the seg graph calls)
+    query: str = "gridifyknn"                        # "gridify" (what the seg graph calls), "gridifyknn",
+                                                     # "occaware" / "occaware_knn" (coverage-aware sampling)
+    cas_seed: int = 0                                # seed of the coverage-aware sampling
     voxels: Sequence[float] = field(default_factory=tuple)
 
     def __post_init__(self):
@@ -96,6 +98,23 @@ def init_params(cfg: StackCfg, seed=0):
     return layers
 
 
+QUERIES = ("gridify", "gridifyknn", "occaware", "occaware_knn")
+
+
+def query_fn(cfg, module=ops):
+    """The centre-sampling + neighbour-query operator a configuration names, bound to its extra
+    arguments.  ``module`` is anything with Gridify / GridifyKNN / Gridify_occaware (the product ops, or
+    an oracle front-end with snake_case names through ``oracle_query_fn`` in the tests)."""
+    if cfg.query not in QUERIES:
+        raise ValueError("query must be one of %s" % (QUERIES,))
+    if cfg.query == "gridify":
+        return module.Gridify
+    if cfg.query == "gridifyknn":
+        return module.GridifyKNN
+    knn = cfg.query == "occaware_knn"
+    return lambda *a, **kw: module.Gridify_occaware(*a, seed=cfg.cas_seed, knn_query=knn, **kw)
+
+
 class GridGcnEncoder:
     """``feats_table = enc(data, actual_numpoints)``: data (B,N,4) f32 cuda, actual_numpoints
     (B,1) i32 -> last layer's table (B, O_last, 4+C_last).  ``enc.trace`` keeps every layer's
@@ -110,7 +129,7 @@ class GridGcnEncoder:
 
     def __call__(self, data, actual_numpoints, keep_trace=False):
         cfg = self.cfg
-        query = ops.GridifyKNN if cfg.query == "gridifyknn" else ops.Gridify
+        query = query_fn(cfg)
         table, data_loc, num = data, data, actual_numpoints
         trace = []
         for l, conv in zip(cfg.layers, self.convs):

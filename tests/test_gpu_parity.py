@@ -338,12 +338,19 @@ def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod, precision):
         cases += [(stack.seg8192_4layer(64), 1),             # BASELINE config 5 and the config-4 shape
                   (stack.seg8192_4layer(32, "gridify"), 1), (stack.seg8192_4layer(128), 1),
                   (stack.seg81920_shipped(), 1)]
+        cas = stack.seg8192_4layer(32, "occaware_knn")  # coverage-aware sampling feeding the GridConv ladder
+        cas.cas_seed = 11
+        cases += [(cas, 2), (stack.seg8192_shipped("occaware"), 1)]
     for cfg, B in cases:
         params = stack.init_params(cfg, seed=1)
         data, npts = synth.make_batch(B, cfg.num_points, seed0=200, voxels=cfg.voxels)
         enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision=precision)
         out = enc(_t(data, cuda_dev), _t(npts, cuda_dev), keep_trace=True)
-        q = oracle_mod.gridify_knn if cfg.query == "gridifyknn" else oracle_mod.gridify
+        if cfg.query.startswith("occaware"):
+            q = lambda *a, **kw: oracle_mod.gridify_occaware(*a, seed=cfg.cas_seed,  # noqa: E731
+                                                             knn_query=cfg.query.endswith("knn"), **kw)
+        else:
+            q = oracle_mod.gridify_knn if cfg.query == "gridifyknn" else oracle_mod.gridify
         table, loc, num = data, data, npts
         for i, (l, p) in enumerate(zip(cfg.layers, params)):
             want = q(loc, num, max_p_grid=l.max_p_grid, max_o_grid=l.max_o_grid,

@@ -105,3 +105,23 @@ def test_cas_state_table_is_current():
             if occ:
                 h = np.float32(np.float64(h) + 0.3)
             assert values[s] == h
+
+
+def test_stack_query_selection():
+    class Fake:
+        Gridify, GridifyKNN = "g", "k"
+
+        @staticmethod
+        def Gridify_occaware(*a, **kw):
+            return kw
+    assert stack.query_fn(stack.seg8192_shipped(), Fake) == "g"
+    assert stack.query_fn(stack.seg8192_4layer(64), Fake) == "k"
+    cfg = stack.seg8192_4layer(64, "occaware_knn")
+    cfg.cas_seed = 5
+    assert stack.query_fn(cfg, Fake)(max_o_grid=1) == dict(seed=5, knn_query=True, max_o_grid=1)
+    cfg.query = "nonsense"
+    try:
+        stack.query_fn(cfg, Fake)
+        assert False
+    except ValueError:
+        pass
