@@ -161,6 +161,9 @@ def main():
                          "ladder (config 2); seg81920: the shipped 81920-point ladder (config 4, 3 layers, P0=128)")
     ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "tf32x3"),
                     choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the forward as ONE CUDA graph (stack.capture_graph) for the device-resident `value`; "
+                         "pays off when the step is launch bound (small batches)")
     ap.add_argument("--cpu-clouds", type=int, default=0,
                     help="clouds per CPU-baseline step (default: one per host core, at most 64)")
     args = ap.parse_args()
@@ -186,7 +189,7 @@ def main():
     flops_cloud = [2 * l.max_o_grid * l.max_p_grid * m for l, m in zip(cfg.layers, macs)]
     config = {"workload": "%s, query=%s, synthetic surface clouds" % (wl_name, args.query),
               "clouds_per_gpu": args.batch, "points_per_cloud": cfg.num_points, "K": args.K,
-              "precision": args.precision, "parallelism": "batch-sharded clouds x%d, no collective" % world,
+              "precision": args.precision, "cuda_graph": bool(args.graph), "parallelism": "batch-sharded clouds x%d, no collective" % world,
               "l2": "value: L2 flushed (256 MiB write) between timed steps; e2e: inputs rewritten by H2D every step and "
                     "the per-step working set (index + feature tables) exceeds the 126 MB L2"}
 
@@ -257,8 +260,10 @@ def main():
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs)
 
+    replay = stack.capture_graph(enc, data_d, npts_d) if args.graph else None
+
     def step_device():
-        return enc(data_d, npts_d)
+        return replay() if replay is not None else enc(data_d, npts_d)
 
     # End-to-end: every step copies its inputs from pinned host memory and reads its result back.  Copies
     # run on their own stream, double buffered, so the H2D of step i+1 and the D2H of step i-1 overlap

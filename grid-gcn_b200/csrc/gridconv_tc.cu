@@ -1078,7 +1078,7 @@ edge_tc_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel B', compact first-layer variant (Cout <= 64, K | 64, 3-pass mode): same math as
+// Kernel B', compact first-layer variant (Cout <= 64, K | 64 or K = 128, 3-pass mode): same math as
 // edge_tc_kernel<3, true>, re-laid-out so that THREE CTAs fit on an SM (the first layer is latency bound:
 // more resident tiles is what speeds it up; profiles/README.md).
 //   * M = 64 MMAs: the 64 feature channels F and the 64 attention channels G share ONE 128-column TMEM
@@ -1448,6 +1448,11 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
                         }
                     }
                 }
+            }
+            if (K == 2 * 64) {  // one centre per tile: its two 64-column halves meet across the lane pair
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                if (!is_g && chv && c_base < centers_total)
+                    out_ch[c_base * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + c_base);
             }
             for (int i = tid; i < cpt * 4; i += 128) {  // centre columns of the output rows
                 const long long center = c_base + i / 4;
@@ -1914,7 +1919,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         if (c.K > kTileRows) return GRIDGCN_ELIMIT;
         if ((long long)c.B * c.Nprev * c.Cout >= (1LL << 32)) return GRIDGCN_ELIMIT;  // 32-bit row offsets
         if (NSPLIT == 3 && p.has_ff && p.has_att && p.f0_cuda && p.dbg == nullptr && c.Cout <= 64 &&
-            64 % c.K == 0) {
+            (64 % c.K == 0 || c.K == 128)) {
             // compact first-layer variant: three CTAs per SM (see edge_first64_kernel)
             const First64Layout L = first64_layout(p);
             int hid = 32;

@@ -224,6 +224,7 @@ CONV_CASES = [
     ("l0_K16_C64", 2, 512, 77, 16, 0, [32, 64]),
     ("l0_K4_C24", 1, 128, 30, 4, 0, [8, 16, 24]),
     ("l0_K64_C64_narrow_f0", 1, 1024, 33, 64, 0, [16, 32, 64]),
+    ("l0_K128_C64", 1, 1024, 21, 128, 0, [32, 32, 64]),  # one centre per tile: halves combined across the lane pair
     # first-layer shapes that must take the general kernel (Cout > 64, K not a divisor of 64)
     ("l0_C96", 1, 512, 40, 32, 0, [32, 96]),
     ("l0_K24", 1, 512, 40, 24, 0, [32, 32, 64]),
@@ -364,6 +365,23 @@ def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod, precision):
             assert err <= 1e-3, "%s layer %d: rel err %.3g" % (cfg.name, i, err)
             loc, num = want[2], want[4]
         assert out.shape == (B, cfg.layers[-1].max_o_grid, 4 + cfg.layers[-1].pt_mlp_lst[-1])
+
+
+def test_cuda_graph_replay_matches_eager(gg, cuda_dev):
+    """The whole encoder forward captured into one CUDA graph replays bit-identically, also on new inputs."""
+    from gridgcn_b200 import stack
+    cfg = stack.cls1024_4layer(32)
+    params = stack.init_params(cfg, seed=3)
+    enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision="tf32x3")
+    d0, n0 = synth.make_batch(4, cfg.num_points, seed0=10, voxels=cfg.voxels)
+    d1, n1 = synth.make_batch(4, cfg.num_points, seed0=20, voxels=cfg.voxels)
+    n1[2, 0] = 900
+    replay = stack.capture_graph(enc, _t(d0, cuda_dev), _t(n0, cuda_dev))
+    for d, n in ((d0, n0), (d1, n1), (d0, n0)):
+        want = enc(_t(d, cuda_dev), _t(n, cuda_dev)).clone()
+        got = replay(_t(d, cuda_dev), _t(n, cuda_dev))
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
 
 
 def test_full_size_properties(gg, cuda_dev):
