@@ -40,7 +40,13 @@ namespace gg {
 
 constexpr int kTcThreads = 160;     // warps 0-3: gather + TMEM epilogue (thread = TMEM lane); warp 4: TMA + MMA issue
 constexpr int kTileRows = 128;
-constexpr int kSliceK = 32;         // k extent of one streamed weight slice
+#ifndef GG_SLICE_K
+#define GG_SLICE_K 32   // k extent of one streamed weight slice (tools/build_variant.py -DGG_SLICE_K=16)
+#endif
+#ifndef GG_RING_CAP
+#define GG_RING_CAP 4   // most ring slots the row-major kernel A / kernel B take (transposed kernel A: + 2)
+#endif
+constexpr int kSliceK = GG_SLICE_K;  // k extent of one streamed weight slice
 constexpr int kSlotBytes = 2 * 128 * kSliceK * 4;  // hi + lo images of a [128 x 32] slice
 constexpr int kMaxRing = 8;
 constexpr int kRowsThreads = 288;    // row-major kernel A: warps 0-7 workers (two per TMEM lane quadrant), warp 8 TMA + MMA
@@ -1877,7 +1883,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
                              (p.a[p.na - 1].Cout & 3) == 0;
         if (rows_ok) {
             p.a_rows = kTileRows;
-            p.ring_slots = (int)min((size_t)4, (kSmemCap - rows_fixed) / kSlotBytes);
+            p.ring_slots = (int)min((size_t)GG_RING_CAP, (kSmemCap - rows_fixed) / kSlotBytes);
             p.ring_sticky = 0;
             int saved_cols = p.tmem_cols;
             p.tmem_cols = npmax <= 128 ? 128 : (npmax <= 256 ? 256 : 512);
@@ -1899,7 +1905,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
                 if (chunks * cand > 256) continue;
                 size_t fixed = kernel_a_smem(p, cand, NSPLIT, 0);
                 if (fixed > kSmemCap) continue;
-                int fit = (int)min((size_t)6, (kSmemCap - fixed) / kSlotBytes);
+                int fit = (int)min((size_t)min(GG_RING_CAP + 2, kMaxRing), (kSmemCap - fixed) / kSlotBytes);
                 if (fit >= 2) { TR = cand; slots = fit; break; }
             }
             if (TR == 0) return GRIDGCN_ELIMIT;
@@ -1949,7 +1955,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         } else {
             p.ring_sticky = 0;
             if (base + 1024 > kSmemCap) return GRIDGCN_ELIMIT;
-            p.ring_slots = (int)min((size_t)4, (kSmemCap - base - 1024) / kSlotBytes);
+            p.ring_slots = (int)min((size_t)GG_RING_CAP, (kSmemCap - base - 1024) / kSlotBytes);
             if (p.ring_slots < 2) return GRIDGCN_ELIMIT;
             smem = base + (size_t)p.ring_slots * kSlotBytes + 1024;
         }
