@@ -174,9 +174,11 @@ def main():
     ap.add_argument("--K", type=int, default=64)
     ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify", "occaware", "occaware_knn"],
                     help="centre sampling + neighbour query operator (occaware = coverage-aware sampling)")
-    ap.add_argument("--workload", default="seg8192", choices=["seg8192", "cls1024", "seg81920"],
+    ap.add_argument("--workload", default="seg8192", choices=["seg8192", "cls1024", "seg81920", "cls1024_shipped"],
                     help="seg8192: BASELINE.json's metric configuration (N=8192, 4 layers); cls1024: N=1024 4-layer "
-                         "ladder (config 2); seg81920: the shipped 81920-point ladder (config 4, 3 layers, P0=128)")
+                         "ladder (config 2); seg81920: the shipped 81920-point ladder (config 4, 3 layers, P0=128); "
+                         "cls1024_shipped: the shipped ModelNet40 ladder with the classification flavour of the block "
+                         "(fp32 CUDA-core kernel, Gridify query)")
     ap.add_argument("--precision", default=os.environ.get("GRIDGCN_PRECISION", "tf32x3"),
                     choices=["tf32x3", "tf32", "fp32"])
     ap.add_argument("--graph", action="store_true",
@@ -199,6 +201,12 @@ def main():
     elif args.workload == "cls1024":
         cfg = stack.cls1024_4layer(args.K, args.query)
         wl_name = "cls1024 4-layer GridConv encoder (O=512/128/32/8, K=%d, N=1024)" % args.K
+    elif args.workload == "cls1024_shipped":
+        args.precision = "fp32"  # the tensor-core kernels implement the segmentation block only
+        if args.query == "gridifyknn":
+            args.query = "gridify"
+        cfg = stack.cls1024_shipped(args.query)
+        wl_name = "cls1024 shipped 3-layer ladder, classification block (O=1024/128/1, P=64/64/128, kernel 7/3/1, N=1024)"
     else:
         cfg = stack.seg81920_shipped(args.query)
         wl_name = "seg81920 shipped 3-layer GridConv encoder (O=1024/256/24, P=128/32/32, N=81920)"

@@ -23,7 +23,8 @@ class MlpDesc(ctypes.Structure):
     """gridgcn_mlp_t"""
     _fields_ = [("n_feat_stages", _i), ("attfdim", _i), ("feat_in", _i),
                 ("widths", _i * MAX_STAGES), ("weight", _vp * MAX_STAGES),
-                ("bias", _vp * MAX_STAGES), ("pre_relu", _i)]
+                ("bias", _vp * MAX_STAGES), ("pre_relu", _i), ("n_att_stages", _i), ("localfdim", _i),
+                ("att_full", _i)]
 
 
 _GRIDIFY_ARGS = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f3, _f3, _i3, _i, _vp, _vp, _vp, _vp, _vp,
@@ -50,6 +51,7 @@ SIGNATURES = {
     "gridgcn_gridconv_packed_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i]),
     "gridgcn_gridconv_pack": (_i, [ctypes.POINTER(MlpDesc), _i, _vp, _sz, _vp]),
     "gridgcn_gridconv_workspace_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i, _i, _i]),
+    "gridgcn_gridconv_fp32_scratch_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i, _i]),
     "gridgcn_gridconv_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(MlpDesc),
                                   _i, _vp, _vp, _sz, _vp, _vp]),
 }
@@ -75,7 +77,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if L.gridgcn_abi_version() != 1:
+        if L.gridgcn_abi_version() != 2:
             raise GridGcnError("libgridgcn_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -19,9 +19,11 @@ struct ConvParams {
     const float4 *cent;    // (B*O)
     const float *centmsk;  // (B*O)
     float *out;            // (B*O, 4+Cout)
+    float *scratch;        // fp32 path only: per-CTA activation buffers when they do not fit in shared memory
     int B, Nprev, Cin, O, K;
     int n_feat, attfdim, feat_in, pre_relu;
-    int n_stages;                        // n_feat + (attfdim > 0 ? 2 : 0)
+    int n_att, localfdim, att_full;      // attention stages (0 or >= 2), geo prefix width, GRIDGCN_ATT_FULL_*
+    int n_stages;                        // n_feat + n_att
     int cin[GRIDGCN_MAX_STAGES];         // input width of each stage
     int cout[GRIDGCN_MAX_STAGES];        // output width of each stage
     const float *w[GRIDGCN_MAX_STAGES];  // (cout, cin) row-major, BN folded

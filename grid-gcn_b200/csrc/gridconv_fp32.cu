@@ -17,24 +17,51 @@ constexpr int kKChunk = 32;
 constexpr int kWsLd = kColBlk + 4;
 constexpr int kPairLd = kColBlk + 1;
 
+constexpr size_t kFp32SmemLimit = 220 * 1024;
+constexpr int kFp32ScratchBlocks = 296;  // CTAs the global activation scratch is sized for (2 per SM)
+
+// Activation buffers of one 64-edge tile (all [64 x ld] fp32):
+//   XA / XB  feature MLP ping-pong (input row [geo | gathered features], hidden stages)
+//   H0       [attention stage 0 | concat part]: with att_full the later attention stages read
+//            [att_0 | feature MLP output ("next") or input ("last")], laid out side by side here
+//   H1 / H2  ping-pong of the middle attention stages (classification block: 3 attention stages)
+// They live in shared memory when everything fits (the segmentation block always does), else in a
+// per-CTA slice of the global scratch (wide classification layers); ATT, the weight chunk, the pair
+// tile and the running max stay in shared memory either way.
 struct ConvSmemLayout {
-    int x0, x1, h, attin, ws, pair, maxbuf, total;  // offsets in floats
-    int ldx, ldh, cpt, Kc, nchunk;
+    int xa, xb, h0, h1, h2;                     // offsets (floats) inside the activation region
+    int attin, ws, pair, maxbuf, total;         // offsets (floats) inside shared memory; total = smem floats
+    int ldx, ldh0, ldh1, cpt, Kc, nchunk;
+    int a0w, extra;                             // width of attention stage 0, of the concat part
+    int act_floats, act_global;
 };
+
+__host__ __device__ inline int pad4p(int w) { return ((w + 3) & ~3) + 4; }
 
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams &p) {
     ConvSmemLayout s;
     int wmax = p.feat_in;
     for (int i = 0; i + 1 < p.n_feat; i++) wmax = max(wmax, p.cout[i]);
-    s.ldx = ((wmax + 3) & ~3) + 4;
-    s.ldh = p.attfdim > 0 ? ((p.cout[p.n_feat] + 3) & ~3) + 4 : 4;
+    s.ldx = pad4p(wmax);
+    s.a0w = p.n_att > 0 ? p.cout[p.n_feat] : 0;
+    s.extra = p.att_full == GRIDGCN_ATT_FULL_NEXT ? p.Cout : (p.att_full == GRIDGCN_ATT_FULL_LAST ? p.feat_in : 0);
+    s.ldh0 = p.n_att > 0 ? pad4p(s.a0w + s.extra) : 4;
+    int mid = 0;
+    for (int i = p.n_feat + 1; i + 1 < p.n_stages; i++) mid = max(mid, p.cout[i]);
+    s.ldh1 = mid > 0 ? pad4p(mid) : 0;
     s.Kc = p.K < kTileM ? p.K : kTileM;
     s.nchunk = (p.K + kTileM - 1) / kTileM;
     s.cpt = kTileM / s.Kc;
     int off = 0;
-    s.x0 = off;     off += kTileM * s.ldx;
-    s.x1 = off;     off += (p.n_feat > 1 ? kTileM * s.ldx : 0);
-    s.h = off;      off += kTileM * s.ldh;
+    s.xa = off;  off += kTileM * s.ldx;
+    s.xb = off;  off += (p.n_feat > 1 ? kTileM * s.ldx : 0);
+    s.h0 = off;  off += kTileM * s.ldh0;
+    s.h1 = off;  off += kTileM * s.ldh1;
+    s.h2 = off;  off += (p.n_att > 3 ? kTileM * s.ldh1 : 0);
+    s.act_floats = off;
+    const int fixed = kTileM * 12 + kKChunk * kWsLd + kTileM * kPairLd + s.cpt * p.Cout;
+    s.act_global = ((size_t)(s.act_floats + fixed) * sizeof(float) > kFp32SmemLimit) ? 1 : 0;
+    off = s.act_global ? 0 : s.act_floats;
     s.attin = off;  off += kTileM * 12;
     s.ws = off;     off += kKChunk * kWsLd;
     s.pair = off;   off += kTileM * kPairLd;
@@ -101,7 +128,9 @@ __global__ void __launch_bounds__(kConvThreads)
 gridconv_fp32_kernel(ConvParams p, int num_tiles) {
     extern __shared__ __align__(16) float smem_f[];
     const ConvSmemLayout s = conv_smem_layout(p);
-    float *X0 = smem_f + s.x0, *X1 = smem_f + s.x1, *H = smem_f + s.h, *ATT = smem_f + s.attin;
+    float *act = s.act_global ? p.scratch + (size_t)blockIdx.x * s.act_floats : smem_f;
+    float *XA = act + s.xa, *XB = act + s.xb, *H0 = act + s.h0, *H1 = act + s.h1, *H2 = act + s.h2;
+    float *ATT = smem_f + s.attin;
     float *Ws = smem_f + s.ws, *PAIR = smem_f + s.pair, *MAXB = smem_f + s.maxbuf;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
@@ -109,6 +138,8 @@ gridconv_fp32_kernel(ConvParams p, int num_tiles) {
     const long long rows_total = (long long)p.B * p.Nprev;
     const long long centers_total = (long long)p.B * p.O;
     const int att_w = p.attfdim <= 0 ? 0 : (p.attfdim <= 3 ? 3 : (p.attfdim < 10 ? 4 : 10));
+    const int gpre = p.Cin > 0 ? p.localfdim : 0;  // geo prefix in front of the gathered features
+    const bool next = p.att_full == GRIDGCN_ATT_FULL_NEXT;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long c_base = (long long)tile * s.cpt;
@@ -120,7 +151,7 @@ gridconv_fp32_kernel(ConvParams p, int num_tiles) {
                 const int cl = r / s.Kc, pslot = chunk * kTileM + r % s.Kc;
                 const long long center = c_base + cl;
                 const bool valid = cl < s.cpt && center < centers_total && pslot < p.K;
-                float *xrow = X0 + r * s.ldx;
+                float *xrow = XA + r * s.ldx;
                 if (!valid) {
                     for (int c = lane; c < s.ldx; c += 32) xrow[c] = 0.f;
                     if (lane < 12) ATT[r * 12 + lane] = 0.f;
@@ -144,20 +175,30 @@ gridconv_fp32_kernel(ConvParams p, int num_tiles) {
                     for (int q = 0; q < 10; q++) v = (lane == q) ? att[q] : v;
                     ATT[r * 12 + lane] = v;
                 }
-                if (p.Cin == 0) {  // has_feats == False: features are the geo vector (:242-243)
-                    if (lane == 0) { xrow[0] = dx; xrow[1] = dy; xrow[2] = dz; }
-                } else if ((row_w & 3) == 0) {
-                    const float4 *s4 = reinterpret_cast<const float4 *>(src) + 1;
-                    for (int c = lane; c < p.Cin / 4; c += 32)
-                        *reinterpret_cast<float4 *>(xrow + c * 4) = __ldg(s4 + c);
-                } else {
-                    for (int c = lane; c < p.Cin; c += 32) xrow[c] = __ldg(src + 4 + c);
+                if (p.Cin == 0 || gpre > 0) {  // geo vector: the whole input (has_feats == False, :242-243)
+                    if (lane == 0) { xrow[0] = dx; xrow[1] = dy; xrow[2] = dz; }  // or its prefix (localfdim)
+                }
+                if (p.Cin > 0) {
+                    if (gpre == 0 && (row_w & 3) == 0) {
+                        const float4 *s4 = reinterpret_cast<const float4 *>(src) + 1;
+                        for (int c = lane; c < p.Cin / 4; c += 32)
+                            *reinterpret_cast<float4 *>(xrow + c * 4) = __ldg(s4 + c);
+                    } else {
+                        for (int c = lane; c < p.Cin; c += 32) xrow[gpre + c] = __ldg(src + 4 + c);
+                    }
                 }
             }
             __syncthreads();
-            // ---- feature MLP hidden stages ----
-            const float *fin = X0;
-            float *fout = X1;
+            if (p.att_full == GRIDGCN_ATT_FULL_LAST) {  // concat part = the feature MLP's input
+                for (int e = tid; e < kTileM * p.feat_in; e += kConvThreads) {
+                    const int r = e / p.feat_in, c = e - r * p.feat_in;
+                    H0[r * s.ldh0 + s.a0w + c] = XA[r * s.ldx + c];
+                }
+            }
+            // ---- feature MLP hidden stages (with att_full "next" the last stage is materialised too,
+            //      next to attention stage 0) ----
+            const float *fin = XA;
+            float *fout = XB;
             for (int st = 0; st + 1 < p.n_feat; st++) {
                 hidden_stage(fin, s.ldx, fout, s.ldx, p.w[st], p.bias[st], p.cin[st], p.cout[st], Ws,
                              tx, ty);
@@ -165,26 +206,39 @@ gridconv_fp32_kernel(ConvParams p, int num_tiles) {
                 fin = fout;
                 fout = const_cast<float *>(t);
             }
-            // ---- attention hidden stage ----
-            if (p.attfdim > 0)
-                hidden_stage(ATT, 12, H, s.ldh, p.w[p.n_feat], p.bias[p.n_feat], p.cin[p.n_feat],
-                             p.cout[p.n_feat], Ws, tx, ty);
+            const int sf = p.n_feat - 1, a0 = p.n_feat, sa = p.n_stages - 1;
+            if (next)
+                hidden_stage(fin, s.ldx, H0 + s.a0w, s.ldh0, p.w[sf], p.bias[sf], p.cin[sf], p.Cout, Ws, tx, ty);
+            // ---- attention stages but the last ----
+            const float *ain = H0;
+            int ald = s.ldh0;
+            if (p.n_att > 0) {
+                hidden_stage(ATT, 12, H0, s.ldh0, p.w[a0], p.bias[a0], p.cin[a0], p.cout[a0], Ws, tx, ty);
+                float *aout = H1;
+                for (int st = a0 + 1; st < sa; st++) {
+                    hidden_stage(ain, ald, aout, s.ldh1, p.w[st], p.bias[st], p.cin[st], p.cout[st], Ws, tx, ty);
+                    ain = aout;
+                    ald = s.ldh1;
+                    aout = aout == H1 ? H2 : H1;
+                }
+            }
             // ---- last feature stage x last attention stage, product, max over K ----
-            const int sf = p.n_feat - 1, sa = p.n_feat + 1;
             for (int cb = 0; cb * kColBlk < p.Cout; cb++) {
                 float accf[4][4], acca[4][4];
-                dense_block(accf, fin, s.ldx, p.w[sf], p.cin[sf], p.Cout, cb, Ws, tx, ty);
-                if (p.attfdim > 0)
-                    dense_block(acca, H, s.ldh, p.w[sa], p.cin[sa], p.Cout, cb, Ws, tx, ty);
+                if (!next) dense_block(accf, fin, s.ldx, p.w[sf], p.cin[sf], p.Cout, cb, Ws, tx, ty);
+                if (p.n_att > 0)
+                    dense_block(acca, ain, ald, p.w[sa], p.cin[sa], p.Cout, cb, Ws, tx, ty);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     int col = cb * kColBlk + tx * 4 + j;
-                    float bf = col < p.Cout ? __ldg(p.bias[sf] + col) : 0.f;
-                    float ba = (p.attfdim > 0 && col < p.Cout) ? __ldg(p.bias[sa] + col) : 0.f;
+                    float bf = (!next && col < p.Cout) ? __ldg(p.bias[sf] + col) : 0.f;
+                    float ba = (p.n_att > 0 && col < p.Cout) ? __ldg(p.bias[sa] + col) : 0.f;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        float f = fmaxf(accf[i][j] + bf, 0.f);
-                        if (p.attfdim > 0) f *= fmaxf(acca[i][j] + ba, 0.f);  // :167 att * feats
+                        float f;
+                        if (next) f = col < p.Cout ? H0[(ty * 4 + i) * s.ldh0 + s.a0w + col] : 0.f;
+                        else f = fmaxf(accf[i][j] + bf, 0.f);
+                        if (p.n_att > 0) f *= fmaxf(acca[i][j] + ba, 0.f);  // :167 att * feats
                         PAIR[(ty * 4 + i) * kPairLd + tx * 4 + j] = f;
                     }
                 }
@@ -229,11 +283,12 @@ void tc_set_phase_buffer(unsigned long long *buf);
 static int launch_gridconv_fp32(const ConvParams &p, cudaStream_t st) {
     ConvSmemLayout s = conv_smem_layout(p);
     size_t smem = (size_t)s.total * sizeof(float);
-    if (smem > 220 * 1024) return GRIDGCN_ELIMIT;
+    if (smem > kFp32SmemLimit) return GRIDGCN_ELIMIT;
+    if (s.act_global && !p.scratch) return GRIDGCN_EWORKSPACE;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gridconv_fp32_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFp32SmemLimit);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -243,8 +298,9 @@ static int launch_gridconv_fp32(const ConvParams &p, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
+    int per_sm = (int)max((size_t)1, min((size_t)8, kFp32SmemLimit / (smem + 1024)));
     int blocks = (int)min(tiles, (long long)sms * per_sm);
+    if (s.act_global) blocks = min(blocks, kFp32ScratchBlocks);
     gridconv_fp32_kernel<<<blocks, kConvThreads, smem, st>>>(p, (int)tiles);
     return (int)cudaGetLastError();
 }
@@ -252,16 +308,22 @@ static int launch_gridconv_fp32(const ConvParams &p, cudaStream_t st) {
 // Validates an MLP description and fills the stage tables shared by every GridConv entry point.
 static int fill_mlp(const gridgcn_mlp_t *m, int Cin, ConvParams &p) {
     if (!m || Cin < 0) return GRIDGCN_EINVAL;
-    if (m->n_feat_stages < 1 || m->n_feat_stages > GRIDGCN_MAX_STAGES - 2) return GRIDGCN_EINVAL;
     if (m->attfdim != 0 && m->attfdim != 3 && m->attfdim != 4 && m->attfdim != 10)
         return GRIDGCN_ELIMIT;
+    if (m->localfdim != 0 && m->localfdim != 3) return GRIDGCN_ELIMIT;
+    if (m->att_full < GRIDGCN_ATT_FULL_OFF || m->att_full > GRIDGCN_ATT_FULL_LAST) return GRIDGCN_EINVAL;
     p.Cin = Cin;
     p.n_feat = m->n_feat_stages;
     p.attfdim = m->attfdim;
-    p.feat_in = Cin == 0 ? 3 : Cin;
+    p.n_att = p.attfdim > 0 ? (m->n_att_stages > 0 ? m->n_att_stages : 2) : 0;
+    if (p.n_feat < 1 || (p.attfdim > 0 && p.n_att < 2) || p.n_feat + p.n_att > GRIDGCN_MAX_STAGES)
+        return GRIDGCN_EINVAL;
+    p.localfdim = Cin > 0 ? m->localfdim : 0;  // without input features the MLP input is the geo vector anyway
+    p.att_full = p.attfdim > 0 ? m->att_full : GRIDGCN_ATT_FULL_OFF;
+    p.feat_in = Cin == 0 ? 3 : Cin + p.localfdim;
     if (m->feat_in != p.feat_in) return GRIDGCN_EINVAL;
     p.pre_relu = m->pre_relu;
-    p.n_stages = p.n_feat + (p.attfdim > 0 ? 2 : 0);
+    p.n_stages = p.n_feat + p.n_att;
     int win = p.feat_in;
     for (int i = 0; i < p.n_feat; i++) {
         p.cin[i] = win;
@@ -270,11 +332,17 @@ static int fill_mlp(const gridgcn_mlp_t *m, int Cin, ConvParams &p) {
     }
     p.Cout = win;
     if (p.attfdim > 0) {
-        p.cin[p.n_feat] = att_in_width(p.attfdim);
-        p.cout[p.n_feat] = m->widths[p.n_feat];
-        p.cin[p.n_feat + 1] = m->widths[p.n_feat];
-        p.cout[p.n_feat + 1] = m->widths[p.n_feat + 1];
-        if (p.cout[p.n_feat + 1] != p.Cout) return GRIDGCN_EINVAL;  // att * feats needs equal widths
+        const int a0 = p.n_feat;
+        p.cin[a0] = att_in_width(p.attfdim);
+        p.cout[a0] = m->widths[a0];
+        win = m->widths[a0] + (p.att_full == GRIDGCN_ATT_FULL_NEXT ? p.Cout
+                               : p.att_full == GRIDGCN_ATT_FULL_LAST ? p.feat_in : 0);
+        for (int i = a0 + 1; i < p.n_stages; i++) {
+            p.cin[i] = win;
+            p.cout[i] = m->widths[i];
+            win = m->widths[i];
+        }
+        if (win != p.Cout) return GRIDGCN_EINVAL;  // att * feats needs equal widths
     }
     for (int i = 0; i < p.n_stages; i++) {
         if (p.cout[i] < 1 || p.cout[i] > 1024 || !m->weight[i] || !m->bias[i]) return GRIDGCN_EINVAL;
@@ -284,13 +352,19 @@ static int fill_mlp(const gridgcn_mlp_t *m, int Cin, ConvParams &p) {
     return 0;
 }
 
+// The tensor-core kernels implement the segmentation block: gathered features as they are, two attention
+// stages, no concat.
+static bool tc_supported(const ConvParams &p) {
+    return p.localfdim == 0 && p.att_full == GRIDGCN_ATT_FULL_OFF && (p.attfdim == 0 || p.n_att == 2);
+}
+
 }  // namespace gg
 
 using namespace gg;
 
 extern "C" size_t gridgcn_gridconv_packed_bytes(const gridgcn_mlp_t *m, int Cin) {
     ConvParams p{};
-    if (fill_mlp(m, Cin, p)) return 0;
+    if (fill_mlp(m, Cin, p) || !tc_supported(p)) return 0;
     int n = tc_packed_floats(p);
     return n < 0 ? 0 : (size_t)n * sizeof(float);
 }
@@ -300,6 +374,7 @@ extern "C" int gridgcn_gridconv_pack(const gridgcn_mlp_t *m, int Cin, void *pack
     ConvParams p{};
     int rc = fill_mlp(m, Cin, p);
     if (rc) return rc;
+    if (!tc_supported(p)) return GRIDGCN_ELIMIT;
     int n = tc_packed_floats(p);
     if (n < 0) return GRIDGCN_ELIMIT;
     if (!packed || packed_bytes < (size_t)n * sizeof(float) || (reinterpret_cast<uintptr_t>(packed) & 15))
@@ -309,8 +384,16 @@ extern "C" int gridgcn_gridconv_pack(const gridgcn_mlp_t *m, int Cin, void *pack
 
 extern "C" size_t gridgcn_gridconv_workspace_bytes(const gridgcn_mlp_t *m, int B, int Nprev, int Cin) {
     ConvParams p{};
-    if (fill_mlp(m, Cin, p) || B < 0 || Nprev < 0) return 0;
+    if (fill_mlp(m, Cin, p) || B < 0 || Nprev < 0 || !tc_supported(p)) return 0;
     return Cin > 0 ? (size_t)B * Nprev * p.Cout * sizeof(float) : 0;
+}
+
+extern "C" size_t gridgcn_gridconv_fp32_scratch_bytes(const gridgcn_mlp_t *m, int Cin, int K) {
+    ConvParams p{};
+    if (fill_mlp(m, Cin, p) || K < 1) return 0;
+    p.K = K;
+    const ConvSmemLayout s = conv_smem_layout(p);
+    return s.act_global ? (size_t)kFp32ScratchBlocks * s.act_floats * sizeof(float) : 0;
 }
 
 extern "C" int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cent,
@@ -334,8 +417,15 @@ extern "C" int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const
     p.B = B; p.Nprev = Nprev; p.O = O; p.K = K;
     if (B == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (precision == GRIDGCN_PRECISION_FP32) return launch_gridconv_fp32(p, st);
+    if (precision == GRIDGCN_PRECISION_FP32) {
+        const size_t need = gridgcn_gridconv_fp32_scratch_bytes(m, Cin, K);
+        if (need && (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15)))
+            return GRIDGCN_EWORKSPACE;
+        p.scratch = need ? static_cast<float *>(workspace) : nullptr;
+        return launch_gridconv_fp32(p, st);
+    }
     if (precision == GRIDGCN_PRECISION_TF32 || precision == GRIDGCN_PRECISION_TF32X3) {
+        if (!tc_supported(p)) return GRIDGCN_ELIMIT;  // classification-block variants: fp32 only
         if (!packed || (reinterpret_cast<uintptr_t>(packed) & 15)) return GRIDGCN_EWORKSPACE;
         if (workspace_bytes < gridgcn_gridconv_workspace_bytes(m, B, Nprev, Cin) ||
             (Cin > 0 && (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15))))

@@ -20,6 +20,7 @@ from . import _lib
 BN_EPS = 1e-3  # MXNet BatchNorm default eps (utils/ops.py:152 does not override it)
 
 PRECISION = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+ATT_FULL = {"": 0, "next": 1, "last": 2}  # GRIDGCN_ATT_FULL_*
 
 
 def init_stage(rng, cin, cout):
@@ -33,9 +34,17 @@ def init_stage(rng, cin, cout):
                 moving_var=rng.uniform(0.5, 1.5, size=cout).astype(np.float32))
 
 
-def init_layer(rng, cin, pt_mlp_lst, attfdim):
-    """Parameter dict of one GridConv layer, keyed like the reference's scopes."""
-    feat_in = 3 if cin == 0 else cin
+def init_layer(rng, cin, pt_mlp_lst, attfdim, att_ele_lst=None, att_full="", localfdim=0):
+    """Parameter dict of one GridConv layer, keyed like the reference's scopes.
+
+    Defaults = the segmentation block (gcn_module_g_att.py: attention MLP att_vec -> C/4 -> C, features
+    = gathered rows).  ``att_ele_lst`` (explicit attention widths, last one forced to C), ``att_full``
+    ("next": the attention MLP's later stages also see the feature MLP's output; "last": its input) and
+    ``localfdim`` = 3 (geo vector concatenated in front of the gathered features) give the
+    classification block (classification/models/gcn_module_g.py:64-114,186-191)."""
+    if att_full in ("off", None):
+        att_full = ""
+    feat_in = 3 if cin == 0 else cin + (3 if localfdim else 0)
     stages, w = [], feat_in
     for c in pt_mlp_lst:
         stages.append(init_stage(rng, w, c))
@@ -44,8 +53,13 @@ def init_layer(rng, cin, pt_mlp_lst, attfdim):
     att = []
     if attfdim > 0:
         ain = 3 if attfdim <= 3 else (4 if attfdim < 10 else 10)
-        att = [init_stage(rng, ain, C // 4), init_stage(rng, C // 4, C)]
-    return dict(feat=stages, att=att, attfdim=attfdim, cin=cin)
+        widths = [C // 4, C] if not att_ele_lst else list(att_ele_lst[:-1]) + [C]  # att_ele_lst[-1] = C, :85
+        att = [init_stage(rng, ain, widths[0])]
+        w = widths[0] + (C if att_full == "next" else feat_in if att_full == "last" else 0)
+        for c in widths[1:]:
+            att.append(init_stage(rng, w, c))
+            w = c
+    return dict(feat=stages, att=att, attfdim=attfdim, cin=cin, att_full=att_full, localfdim=int(localfdim))
 
 
 def fold_bn(weight, bias, gamma, beta, moving_mean, moving_var, eps=BN_EPS):
@@ -70,7 +84,8 @@ def named_params(layer, scope):
         put("%s/conv%d" % (scope, j + 1), st)
     if layer["att"]:
         put(scope + "/update_att_mlp2d_frst/conv1", layer["att"][0])
-        put(scope + "/update_att_mlp2d_scnd/conv1", layer["att"][1])
+        for j, st in enumerate(layer["att"][1:]):
+            put(scope + "/update_att_mlp2d_scnd/conv%d" % (j + 1), st)
     return out
 
 
@@ -99,11 +114,20 @@ class GridConv:
                            st["moving_var"])
             self._w.append(torch.from_numpy(w).to(self.device).contiguous())
             self._b.append(torch.from_numpy(b).to(self.device).contiguous())
+        self.localfdim = int(layer.get("localfdim", 0)) if self.cin > 0 else 0
+        self.att_full = (layer.get("att_full", "") or "") if layer["att"] else ""
+        if self.att_full == "off":
+            self.att_full = ""
+        if self.att_full not in ATT_FULL or self.localfdim not in (0, 3):
+            raise ValueError("unsupported att_full %r / localfdim %r" % (self.att_full, self.localfdim))
         d = _lib.MlpDesc()
         d.n_feat_stages = len(layer["feat"])
         d.attfdim = self.attfdim
-        d.feat_in = 3 if self.cin == 0 else self.cin
+        d.feat_in = 3 if self.cin == 0 else self.cin + self.localfdim
         d.pre_relu = 1 if self.pre_relu else 0
+        d.n_att_stages = len(layer["att"])
+        d.localfdim = self.localfdim
+        d.att_full = ATT_FULL[self.att_full]
         for i, (w, b) in enumerate(zip(self._w, self._b)):
             d.widths[i] = self.widths[i]
             d.weight[i] = w.data_ptr()
@@ -114,7 +138,9 @@ class GridConv:
             L = _lib.lib()
             nbytes = L.gridgcn_gridconv_packed_bytes(ctypes.byref(d), self.cin)
             if nbytes == 0:
-                raise _lib.GridGcnError("this MLP shape is not supported by the tensor-core GridConv")
+                raise _lib.GridGcnError("this MLP shape is not supported by the tensor-core GridConv (the "
+                                        "classification-block variants -- localfdim, att_full, explicit "
+                                        "attention widths -- run with precision='fp32')")
             self._packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 rc = L.gridgcn_gridconv_pack(ctypes.byref(d), self.cin, self._packed.data_ptr(), nbytes,
@@ -139,8 +165,10 @@ class GridConv:
         if self._packed is not None:
             packed = self._packed.data_ptr()
             ws_bytes = L.gridgcn_gridconv_workspace_bytes(ctypes.byref(self._desc), B, Nprev, self.cin)
-            if ws_bytes:
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
+        else:  # fp32: activation scratch for layers too wide for shared memory
+            ws_bytes = L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(self._desc), self.cin, K)
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
         with torch.cuda.device(table.device):
             rc = L.gridgcn_gridconv_fwd(
                 table.data_ptr(), nebidx.data_ptr(), cent.data_ptr(), centmsk.data_ptr(), B, Nprev,
@@ -165,11 +193,14 @@ def sub_g_update(centers_xyz, center_den, neighbors, has_feats, center_masks, ne
 
     centers_xyz (B,3,O), center_den (B,1,O), neighbors (B,4+C,O,P), center_masks (B,O) -> (B,C,O).
     ``layer`` carries the parameters.  The gathered tensor is viewed as a table with an identity
-    index so that the same fused kernel runs.  Only the configuration the shipped seg config uses
-    is supported here (aggtype gcn, max pooling, no context MLP, empty outDim)."""
+    index so that the same fused kernel runs.  Supported: aggtype gcn, max pooling, no context MLP, empty
+    outDim -- what the shipped seg and cls configs use; ``att_full`` ("next" / "last", the classification
+    block, fp32 precision) must agree with the one ``layer`` was initialised with."""
     if aggtype != "gcn" or pool_type not in ("max_pooling", "max") or cntxt_mlp is not None \
-            or len(outDim) != 0 or center_ori_feats is not None or att_full:
+            or len(outDim) != 0 or center_ori_feats is not None:
         raise NotImplementedError("sub_g_update: unsupported configuration for the fused kernel")
+    if (att_full or "") not in ("", "off") and att_full != layer.get("att_full", ""):
+        raise ValueError("att_full=%r but the layer was initialised with %r" % (att_full, layer.get("att_full", "")))
     B, C4, O, P = neighbors.shape
     table = neighbors.permute(0, 2, 3, 1).reshape(B, O * P, C4).contiguous()
     idx = torch.arange(O * P, dtype=torch.int32, device=neighbors.device).reshape(1, O, P)

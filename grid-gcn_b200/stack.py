@@ -26,6 +26,7 @@ class LayerCfg:
     kernel_size: int
     pt_mlp_lst: Sequence[int]
     stride: int = 1
+    att_ele_lst: Sequence[int] = ()  # explicit attention widths (classification block); () = [C/4, C]
 
 
 @dataclass
@@ -40,6 +41,8 @@ class StackCfg:
     query: str = "gridifyknn"                        # "gridify" (what the seg graph calls), "gridifyknn",
                                                      # "occaware" / "occaware_knn" (coverage-aware sampling)
     cas_seed: int = 0                                # seed of the coverage-aware sampling
+    att_full: str = ""                               # "next" / "last": classification block (fp32 precision)
+    localfdim: int = 0                               # 3: geo vector in front of the gathered features
     voxels: Sequence[float] = field(default_factory=tuple)
 
     def __post_init__(self):
@@ -81,6 +84,18 @@ def seg81920_shipped(query="gridify"):
     return cfg
 
 
+def cls1024_shipped(query="gridify"):
+    """classification/configs/configs.yaml:44-68 exactly: 3 layers, kernel 7/3/1, the last layer one voxel
+    holding everything; attfdim 4, localfdim 3, att_full next, explicit attention widths -- the
+    classification flavour of the block (classification/models/gcn_module_g.py), fp32 precision."""
+    vox, grid, O, P, ks = [0.05, 0.25, 2.0], [40, 8, 1], [1024, 128, 1], [64, 64, 128], [7, 3, 1]
+    pt = ([64, 64, 128], [128, 128, 256], [256, 256, 512])
+    att = ([64, 128, 128], [128, 256, 256], [256, 512, 512])
+    return StackCfg("cls1024_shipped", 1024,
+                    [LayerCfg(vox[i], grid[i], O[i], P[i], ks[i], pt[i], att_ele_lst=att[i]) for i in range(3)],
+                    attfdim=4, query=query, att_full="next", localfdim=3)
+
+
 def tiny(K=8, query="gridifyknn"):
     """Small ladder for smoke tests."""
     return StackCfg("tiny_K%d" % K, 256,
@@ -93,7 +108,9 @@ def init_params(cfg: StackCfg, seed=0):
     rng = np.random.default_rng(seed)
     layers, cin = [], 0
     for l in cfg.layers:
-        layers.append(gridconv.init_layer(rng, cin, list(l.pt_mlp_lst), cfg.attfdim))
+        layers.append(gridconv.init_layer(rng, cin, list(l.pt_mlp_lst), cfg.attfdim,
+                                          att_ele_lst=list(l.att_ele_lst) or None, att_full=cfg.att_full,
+                                          localfdim=cfg.localfdim))
         cin = l.pt_mlp_lst[-1]
     return layers
 

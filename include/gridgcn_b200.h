@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GRIDGCN_ABI_VERSION 1
+#define GRIDGCN_ABI_VERSION 2   /* 2: gridgcn_mlp_t grew n_att_stages / localfdim / att_full */
 
 /* rejected-argument codes (negative) */
 #define GRIDGCN_EINVAL      (-1)  /* null pointer, negative size, even kernel_size, ...          */
@@ -148,19 +148,33 @@ int gridgcn_ball_knn_fwd(const float *unknown, const float *known, const int *do
 /*  out     (B,O,4+Cout) f32     rows [cent x y z w | Cout features] = the next layer's table  */
 /*                               (ggcn_models_g.py:186 concat(centers, center_feats))          */
 /*  The MLP is described by `gridgcn_mlp_t`: folded weights W'(C_out,C_in) row-major and bias   */
-/*  b'(C_out) per stage, feature chain first, then the two attention stages.                    */
+/*  b'(C_out) per stage, feature chain first, then the attention stages.                        */
+/*                                                                                              */
+/*  Classification flavour of the block (classification/models/gcn_module_g.py:64-114,116-209):  */
+/*  `localfdim` = 3 puts the geo vector in front of the gathered features (:186-191), the        */
+/*  attention MLP has explicit widths (`n_att_stages` >= 2, the last one = C) and, with          */
+/*  `att_full`, its stages after the first also see the feature MLP's output ("next", :91-93) or */
+/*  its input ("last", :88-90).  These variants run in GRIDGCN_PRECISION_FP32 only (the tensor-  */
+/*  core kernels implement the segmentation block); the other precisions return GRIDGCN_ELIMIT. */
 /* ------------------------------------------------------------------------------------------ */
 #define GRIDGCN_MAX_STAGES 8
 
 typedef struct {
     int n_feat_stages;                         /* len(pt_mlp_lst), 1..GRIDGCN_MAX_STAGES-2     */
     int attfdim;                               /* 10 (seg flavour) or 4 (dist, dxyz) or 0       */
-    int feat_in;                               /* 3 (geo) when Cin==0, else Cin                 */
-    int widths[GRIDGCN_MAX_STAGES];            /* out width of feat stages, then C/4, C for att */
+    int feat_in;                               /* 3 (geo) when Cin==0, else Cin (+3 if localfdim)*/
+    int widths[GRIDGCN_MAX_STAGES];            /* out width of feat stages, then of att stages  */
     const float *weight[GRIDGCN_MAX_STAGES];   /* device, (C_out, C_in) row-major, BN folded    */
     const float *bias[GRIDGCN_MAX_STAGES];     /* device, (C_out), BN folded                    */
     int pre_relu;                              /* configs["relu"], gcn_module_g_att.py:31-32    */
+    int n_att_stages;                          /* 0 = 2 (segmentation block: C/4, C)            */
+    int localfdim;                             /* 0, or 3: [geo_vec | features] as MLP input    */
+    int att_full;                              /* GRIDGCN_ATT_FULL_*                            */
 } gridgcn_mlp_t;
+
+#define GRIDGCN_ATT_FULL_OFF  0
+#define GRIDGCN_ATT_FULL_NEXT 1  /* attention stages >= 1 read [att_0 | feature MLP output]     */
+#define GRIDGCN_ATT_FULL_LAST 2  /* attention stages >= 1 read [att_0 | feature MLP input]      */
 
 #define GRIDGCN_PRECISION_FP32   0  /* CUDA-core fp32 FMA                                      */
 #define GRIDGCN_PRECISION_TF32   1  /* tcgen05 kind::tf32, fp32 accumulate                     */
@@ -173,6 +187,9 @@ size_t gridgcn_gridconv_packed_bytes(const gridgcn_mlp_t *mlp_host, int Cin);
 int gridgcn_gridconv_pack(const gridgcn_mlp_t *mlp_host, int Cin, void *packed, size_t packed_bytes,
                           void *stream);
 size_t gridgcn_gridconv_workspace_bytes(const gridgcn_mlp_t *mlp_host, int B, int Nprev, int Cin);
+/* GRIDGCN_PRECISION_FP32 keeps a tile's activations in shared memory; layers too wide for that (the
+ * classification block's 256/512-channel layers) need this much `workspace` instead (0 otherwise). */
+size_t gridgcn_gridconv_fp32_scratch_bytes(const gridgcn_mlp_t *mlp_host, int Cin, int K);
 
 /* packed / workspace may be NULL for GRIDGCN_PRECISION_FP32. */
 int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const float *cent,

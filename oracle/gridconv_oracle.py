@@ -67,12 +67,35 @@ def gridconv_layer(table, nebidx, cent, centmsk, layer, pre_relu=True):
         att_vec = np.concatenate([geo_dist, geo_vec, centers_expand, nloc], axis=1)
     else:
         raise NotImplementedError("attfdim %d" % attfdim)
-    feats = neighbors[:, 4:] if has_feats else geo_vec  # localfdim == 0 (seg config)
+    # neighbour features: the geo vector when the layer has no input features; with localfdim != 0 (the
+    # classification config, classification/models/gcn_module_g.py:165-171,186-191) the geo features are
+    # concatenated in front of the gathered ones; localfdim == 0 is the seg config
+    localfdim = int(layer.get("localfdim", 0))
+    if localfdim > 3:
+        raise NotImplementedError("localfdim %d" % localfdim)
+    if not has_feats:
+        feats = geo_vec
+    elif localfdim != 0:
+        feats = np.concatenate([geo_vec, neighbors[:, 4:]], axis=1)
+    else:
+        feats = neighbors[:, 4:]
+    ori_feats = feats
     for st in layer["feat"]:
         feats = _conv_bn_relu(feats, st)
     if attfdim > 0:
-        a = att_vec
-        for st in layer["att"]:
+        # verts_pair_func: first attention stage alone ("update_att_mlp2d_frst"), optional concat with the
+        # MLP output (att_full "next") or its input ("last"), remaining stages ("update_att_mlp2d_scnd")
+        # -- classification/models/gcn_module_g.py:83-97; the seg module (gcn_module_g_att.py:141-152)
+        # is the two-stage special case without concat
+        att_full = layer.get("att_full", "") or ""
+        a = _conv_bn_relu(att_vec, layer["att"][0])
+        if att_full == "last":
+            a = np.concatenate([a, ori_feats], axis=1)
+        elif att_full == "next":
+            a = np.concatenate([a, feats], axis=1)
+        elif att_full not in ("", "off"):
+            raise NotImplementedError("att_full %r" % att_full)
+        for st in layer["att"][1:]:
             a = _conv_bn_relu(a, st)
         pair = (a * feats).astype(F)
     else:

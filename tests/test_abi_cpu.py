@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(gg):
     for s in _declared_symbols():
         assert hasattr(lib, s), "libgridgcn_b200.so does not export %s" % s
     assert set(gg._lib.SIGNATURES) == set(_declared_symbols())
-    assert gg._lib.lib().gridgcn_abi_version() == 1
+    assert gg._lib.lib().gridgcn_abi_version() == 2
 
 
 def test_library_is_sm100a_native(gg):
@@ -86,3 +86,32 @@ def test_missing_library_fails_loudly(gg, monkeypatch):
     monkeypatch.setattr(gg._lib, "LIB_PATH", "/nonexistent/libgridgcn_b200.so")
     with pytest.raises(gg._lib.GridGcnError):
         gg._lib.lib()
+
+
+def test_mlp_description_validation_without_gpu(gg):
+    """gridgcn_mlp_t: the classification-block fields are validated on the host; the tensor-core packing
+    refuses them, the fp32 path reports the activation scratch the wide layers need."""
+    import ctypes
+    L = gg._lib.lib()
+
+    def desc(pt, att, cin, localfdim=0, att_full=0, attfdim=4):
+        d = gg._lib.MlpDesc()
+        d.n_feat_stages, d.attfdim, d.pre_relu = len(pt), attfdim, 1
+        d.n_att_stages, d.localfdim, d.att_full = len(att), localfdim, att_full
+        d.feat_in = 3 if cin == 0 else cin + localfdim
+        for i, w in enumerate(list(pt) + list(att)):
+            d.widths[i] = w
+            d.weight[i] = 16  # never dereferenced: nothing is launched here
+            d.bias[i] = 16
+        return d
+
+    seg = desc([64, 64, 128], [32, 128], 64, attfdim=10)
+    assert L.gridgcn_gridconv_packed_bytes(ctypes.byref(seg), 64) > 0
+    assert L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(seg), 64, 64) == 0
+    cls = desc([128, 128, 256], [128, 256, 256], 128, localfdim=3, att_full=1)
+    assert L.gridgcn_gridconv_packed_bytes(ctypes.byref(cls), 128) == 0          # tensor cores: seg block only
+    assert L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(cls), 128, 64) > 0  # too wide for shared memory
+    assert L.gridgcn_gridconv_pack(ctypes.byref(cls), 128, 16, 1 << 30, None) == -2
+    bad = desc([64, 128], [32, 64], 16, att_full=1)  # last attention width must equal the feature width
+    assert L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(bad), 16, 8) == 0
+    assert L.gridgcn_gridconv_fwd(16, 16, 16, 16, 1, 8, 16, 4, 8, ctypes.byref(bad), 0, None, None, 0, 16, None) == -1

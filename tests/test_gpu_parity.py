@@ -254,6 +254,74 @@ def test_gridconv_matches_oracle(gg, cuda_dev, oracle_mod, name, B, N, O, K, Cin
     assert np.abs(want[..., 4:]).max() > 0  # the comparison is not vacuous
 
 
+CLS_CASES = [
+    # name, B, N, O, K, Cin, pt_mlp, att_ele, att_full, localfdim, attfdim
+    ("cls_l0", 2, 1024, 200, 64, 0, [64, 64, 128], [64, 128, 128], "next", 3, 4),
+    ("cls_l1_wide_scratch", 2, 256, 64, 64, 128, [128, 128, 256], [128, 256, 256], "next", 3, 4),
+    ("cls_l2_one_voxel_K128", 2, 128, 1, 128, 256, [256, 256, 512], [256, 512, 512], "next", 3, 4),
+    ("att_full_last", 2, 256, 40, 16, 16, [16, 32], [8, 24, 32], "last", 3, 10),
+    ("explicit_att_no_concat", 2, 256, 40, 8, 16, [32], [8, 16, 32], "", 0, 4),
+    ("four_att_stages", 1, 256, 30, 8, 8, [16, 32], [8, 16, 24, 32], "next", 3, 4),
+]
+
+
+@pytest.mark.parametrize("case", CLS_CASES, ids=[c[0] for c in CLS_CASES])
+def test_gridconv_classification_block(gg, cuda_dev, oracle_mod, case):
+    """The classification flavour of the block (classification/models/gcn_module_g.py: geo vector in front
+    of the gathered features, explicit attention widths, att_full concat) -- fp32 CUDA-core kernel."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import gridconv
+    name, B, N, O, K, Cin, pt, att, att_full, localfdim, attfdim = case
+    rng = np.random.default_rng(8)
+    data, npts = synth.make_batch(B, N, seed0=70, voxels=(0.25,))
+    if O == 1:   # group-all layer of the cls ladder: one voxel, kernel 1
+        kw = dict(max_p_grid=K, max_o_grid=1, kernel_size=1, loc=1, coord_shift=(1, 1, 1),
+                  voxel_size=(2.0,) * 3, grid_size=(1,) * 3)
+    else:
+        kw = dict(max_p_grid=K, max_o_grid=O, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
+                  voxel_size=(0.25,) * 3, grid_size=(8,) * 3)
+    nebidx, _, cent, centmsk, _ = oracle_mod.gridify(data, npts, **kw)
+    table = data if Cin == 0 else np.concatenate(
+        [data, rng.uniform(0, 1, size=(B, N, Cin)).astype(np.float32)], axis=2)
+    layer = gridconv.init_layer(np.random.default_rng(29), Cin, pt, attfdim, att_ele_lst=att,
+                                att_full=att_full, localfdim=localfdim)
+    want = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, layer)
+    conv = gg.GridConv(layer, cuda_dev, precision="fp32")
+    got = conv(_t(table, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(centmsk, cuda_dev)).cpu().numpy()
+    assert np.array_equal(got[..., :4], want[..., :4])
+    err = _rel_err(got[..., 4:], want[..., 4:])
+    assert err <= 1e-3, "%s: rel err %.3g" % (name, err)
+    assert np.abs(want[..., 4:]).max() > 0
+    if att_full or localfdim:  # the tensor-core kernels implement the segmentation block only: loud refusal
+        with pytest.raises(gg._lib.GridGcnError):
+            gg.GridConv(layer, cuda_dev, precision="tf32x3")
+
+
+def test_classification_stack_matches_oracle(gg, cuda_dev, oracle_mod):
+    """The shipped ModelNet40 ladder (classification/configs/configs.yaml:44-68: kernel 7/3/1, O 1024/128/1,
+    P 64/64/128, attfdim 4, localfdim 3, att_full next) end to end: Gridify indices bit-exact per layer,
+    features within 1e-3."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import stack
+    cfg = stack.cls1024_shipped()
+    params = stack.init_params(cfg, seed=4)
+    data, npts = synth.make_batch(2, cfg.num_points, seed0=210, voxels=cfg.voxels)
+    enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision="fp32")
+    out = enc(_t(data, cuda_dev), _t(npts, cuda_dev), keep_trace=True)
+    table, loc, num = data, data, npts
+    for i, (l, p) in enumerate(zip(cfg.layers, params)):
+        want = oracle_mod.gridify(loc, num, max_p_grid=l.max_p_grid, max_o_grid=l.max_o_grid,
+                                  kernel_size=l.kernel_size, loc=cfg.loc, coord_shift=cfg.coord_shift,
+                                  voxel_size=(l.voxel_size,) * 3, grid_size=(l.grid_size,) * 3)
+        tr = enc.trace[i]
+        _check5([tr[n] for n in NAMES], want, "cls1024_shipped layer %d" % i)
+        table = gridconv_oracle.gridconv_layer(table, want[0], want[2], want[3], p, pre_relu=cfg.pre_relu)
+        err = _rel_err(tr["table"].cpu().numpy()[..., 4:], table[..., 4:])
+        assert err <= 1e-3, "cls1024_shipped layer %d: rel err %.3g" % (i, err)
+        loc, num = want[2], want[4]
+    assert out.shape == (2, 1, 4 + 512)
+
+
 def test_gridconv_attention_variants_and_ball_misses(gg, cuda_dev, oracle_mod):
     from oracle import gridconv_oracle
     from gridgcn_b200 import gridconv
