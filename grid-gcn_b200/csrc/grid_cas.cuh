@@ -51,19 +51,6 @@ __host__ inline size_t cas_smem_bytes(long long Gp, int O, bool cover_in_smem) {
     return b;
 }
 
-// curand_init(seed, 0, 0) followed by one curand_uniform (curand_kernel.h:772-798, 863-874).
-__device__ __forceinline__ float xorwow_first_uniform(unsigned long long seed) {
-    unsigned s0 = (unsigned)seed ^ 0xaad26b49u;
-    unsigned s1 = (unsigned)(seed >> 32) ^ 0xf7dcefddu;
-    unsigned t0 = 1099087573u * s0, t1 = 2591861531u * s1;
-    unsigned d = 6615241u + t1 + t0;
-    unsigned v0 = 123456789u + t0, v4 = 5783321u + t0;
-    unsigned t = v0 ^ (v0 >> 2);
-    v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
-    d += 362437u;
-    return __fmaf_rn((float)(v4 + d), 2.3283064e-10f, 2.3283064e-10f / 2.0f);
-}
-
 template <bool COVER_SMEM>
 __global__ void __launch_bounds__(kCasThreads)
 cas_sampling_kernel(GridParams g, int *__restrict__ ws_base, WsLayout L, CasLayout C,

@@ -87,16 +87,25 @@ __device__ __forceinline__ void decode_lin(int lin, const GridParams &g, int &c2
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gridify query (A.3): first min(P, total) ids in raster order d -> h -> w, keep-first beyond P.
+// Gridify query (A.3): first min(P, total) ids in raster order d -> h -> w; beyond P the canonical rule
+// keeps the first ones.  GRIDGCN_FLAG_STRICT_RESERVOIR instead reproduces the reference's reservoir over
+// the later candidates (gridify.cu:259-270): its seed, index_P * size + grid_pntidx, does not depend on the
+// schedule, so this part of the reference IS deterministic.  Candidate c (0-based, c >= P) draws
+// insrtidx = ceilf(uniform(XORWOW(seed)) * (c + 1)) - 1 and replaces slot insrtidx if it is < P; the
+// reference walks the candidates in order, so a slot ends up with the LAST candidate that drew it: the
+// draws are independent of each other, hence one pass records the highest c per slot (shared-memory
+// atomicMax) and a second one stores the winners' ids.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kQueryWarps * 32)
 gridify_query_kernel(const float4 *__restrict__ data, GridParams g, const int *__restrict__ ws_base,
                      WsLayout L, const int *__restrict__ centnum, int *__restrict__ nebidx,
                      float *__restrict__ nebmsk, float4 *__restrict__ cent) {
     __shared__ int rows[kQueryWarps][kMaxP];
+    __shared__ int wins[kQueryWarps][kMaxP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int *row = rows[warp];
+    int *row = rows[warp], *win = wins[warp];
     const int P = g.P, O = g.O, ks = g.ks, S = ks * ks * ks, r = (ks - 1) / 2;
+    const bool strict = (g.flags & GRIDGCN_FLAG_STRICT_RESERVOIR) != 0;
     const long long total_centers = (long long)g.B * O;
     for (long long ci = (long long)blockIdx.x * kQueryWarps + warp; ci < total_centers;
          ci += (long long)gridDim.x * kQueryWarps) {
@@ -115,8 +124,16 @@ gridify_query_kernel(const float4 *__restrict__ data, GridParams g, const int *_
         const float4 *pts = data + (size_t)b * g.N;
         int c2, c1, c0;
         decode_lin(t.cent_lin[o], g, c2, c1, c0);
+        // seed of candidate c: (int)(index_P * size + c + 1), evaluated in 32-bit int, widened (gridify.cu:260)
+        const unsigned seed0 = (unsigned)ci * (unsigned)P * (unsigned)S;
+        auto draw = [&](int c) {  // slot the reservoir assigns to candidate c >= P (may be >= P: dropped)
+            const long long sd = (long long)(int)(seed0 + (unsigned)(c + 1));
+            return (int)ceilf(__fmul_rn(xorwow_first_uniform((unsigned long long)sd), (float)(c + 1))) - 1;
+        };
+        if (strict)
+            for (int s = lane; s < P; s += 32) win[s] = -1;
         int filled = 0;
-        for (int t0 = 0; t0 < S && filled < P; t0 += 32) {
+        for (int t0 = 0; t0 < S && (strict || filled < P); t0 += 32) {
             int tt = t0 + lane, s = 0, e = 0;
             if (tt < S)
                 voxel_segment(t, g, tt / (ks * ks) - r + c2, (tt % (ks * ks)) / ks - r + c1,
@@ -124,16 +141,49 @@ gridify_query_kernel(const float4 *__restrict__ data, GridParams g, const int *_
             int amount = min(P, e - s);  // gridify.cu:249
             int incl = warp_incl_scan(amount, lane);
             int slot = filled + incl - amount;
-            for (int j = 0; j < amount && slot + j < P; j++) row[slot + j] = t.sorted[s + j];
+            for (int j = 0; j < amount; j++) {
+                const int c = slot + j;
+                if (c < P) {
+                    row[c] = t.sorted[s + j];
+                } else if (strict) {
+                    const int ins = draw(c);
+                    if (ins < P) atomicMax(&win[ins], c);
+                } else {
+                    break;
+                }
+            }
             filled += __shfl_sync(kFull, incl, 31);
         }
         __syncwarp();
+        if (strict && filled > P) {  // second pass: the winners' ids
+            int seen = 0;
+            for (int t0 = 0; t0 < S; t0 += 32) {
+                int tt = t0 + lane, s = 0, e = 0;
+                if (tt < S)
+                    voxel_segment(t, g, tt / (ks * ks) - r + c2, (tt % (ks * ks)) / ks - r + c1,
+                                  tt % ks - r + c0, s, e);
+                int amount = min(P, e - s);
+                int incl = warp_incl_scan(amount, lane);
+                int slot = seen + incl - amount;
+                for (int j = max(0, P - slot); j < amount; j++) {
+                    const int c = slot + j, ins = draw(c);
+                    if (ins < P && win[ins] == c) row[ins] = t.sorted[s + j];
+                }
+                seen += __shfl_sync(kFull, incl, 31);
+            }
+            __syncwarp();
+        }
         const int n = min(filled, P);
         const int pad = row[0];  // initID (gridify.cu:253, :275-279); n >= 1 always
+        // NOTE (strict mode): initID is the FIRST candidate, which the reservoir may have replaced in
+        // slot 0 -- but rows that overflow have no padding, so `pad` is only read when n < P (no overflow)
         for (int s = lane; s < P; s += 32) {
             out_idx[s] = s < n ? row[s] : pad;
             out_msk[s] = s < n ? 1.f : 0.f;
         }
+        // cent.w: the reference updates it as += (int)w_new - w_old per replacement (:266-269), which for the
+        // integer-valued weights of the pipeline (1.0 inputs, counts afterwards) equals the sum over the
+        // final row
         float wsum = weight_sum(pts, row, n, lane);
         if (lane == 0) cent[ci] = center_row(t, o, g.loc, wsum);
         __syncwarp();

@@ -75,13 +75,17 @@ def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_siz
 
 
 def Gridify(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_size=0, stride=0, loc=0,
-            coord_shift=(), voxel_size=(), grid_size=()):
+            coord_shift=(), voxel_size=(), grid_size=(), strict_reservoir=False):
     """Voxel hash + centre sampling + first-P neighbour gather (canonical RVS, keep-first).
 
     Returns ``(nebidx i32 [B,O,P], nebidxmsk f32 [B,O,P], cent f32 [B,O,4], centmsk f32 [B,O],
-    actual_centnum i32 [B,1])`` exactly as gridify-inl.h:190-196,207-212 infer them."""
+    actual_centnum i32 [B,1])`` exactly as gridify-inl.h:190-196,207-212 infer them.
+    ``strict_reservoir`` (extension): when a neighbourhood holds more than max_p_grid candidates, reproduce
+    the reference's reservoir over the later ones (gridify.cu:259-270, deterministic seed) instead of
+    keeping the first max_p_grid in raster order."""
     return _gridify("gridgcn_gridify_fwd", data, actual_numpoints, max_p_grid, max_o_grid,
-                    kernel_size, stride, loc, coord_shift, voxel_size, grid_size, 0)
+                    kernel_size, stride, loc, coord_shift, voxel_size, grid_size,
+                    4 if strict_reservoir else 0)
 
 
 def GridifyKNN(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_size=0, stride=0,
@@ -96,13 +100,13 @@ def GridifyKNN(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_siz
 
 def Gridify_occaware(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_size=0, stride=0,
                      loc=0, coord_shift=(), voxel_size=(), grid_size=(), seed=0, knn_query=False,
-                     dist_fma=False):
+                     dist_fma=False, strict_reservoir=False):
     """Gridify with Coverage-Aware Sampling of the centre voxels (paper s3.2).  The reference
     registers this operator from gridifyop/additional.so but ships its kernels only as cubins
     (SURVEY.md F3); same inputs, attributes and five outputs as Gridify.  ``seed`` replaces the
     reference's wall-clock seed (challenger i draws from XORWOW(seed + i)); ``knn_query`` (extension)
     runs the GridifyKNN query on the sampled centres.  Parity unpinned, see DESIGN.md."""
-    flags = (2 if knn_query else 0) | (1 if dist_fma else 0)
+    flags = (2 if knn_query else 0) | (1 if dist_fma else 0) | (4 if strict_reservoir and not knn_query else 0)
     return _gridify("gridgcn_gridify_occaware_fwd", data, actual_numpoints, max_p_grid, max_o_grid,
                     kernel_size, stride, loc, coord_shift, voxel_size, grid_size, flags, seed=seed)
 

@@ -47,6 +47,12 @@ extern "C" {
 #define GRIDGCN_FLAG_KNN_QUERY 2  /* gridgcn_gridify_occaware_fwd only: run the GridifyKNN query
                                      (K4) on the sampled centres instead of the Gridify one (K2) */
 
+#define GRIDGCN_FLAG_STRICT_RESERVOIR 4  /* Gridify / Gridify_occaware (K2 query): reproduce the reference's
+                                     reservoir over the candidates beyond max_p_grid (gridify.cu:259-270;
+                                     its seed index_P*size+grid_pntidx is schedule independent) instead of
+                                     the canonical keep-first rule.  cent.w is exact for integer-valued
+                                     weights (the pipeline's: 1.0 inputs, neighbour counts afterwards).  */
+
 int gridgcn_abi_version(void);
 
 /* Human-readable text for a return code of this library (static storage). */

@@ -66,6 +66,33 @@ def test_gridify_and_knn_match_oracle(gg, cuda_dev, oracle_mod, name, B, N, kind
             oracle_mod.gridify_knn(data, npts, dist_fma=True, **kw), name + "/GridifyKNN fma")
 
 
+STRICT_CASES = [c for c in GRID_CASES if c[0] in ("cfg1_P64_k3", "seg8192_L0", "seg8192_L1", "overflow",
+                                                 "P128_k7_cls", "loc0_aniso", "big_cloud_global_path")] + [
+    ("tiny_P4_heavy_overflow", 3, 900, "ball",
+     dict(max_p_grid=4, max_o_grid=40, kernel_size=3, loc=1, voxel_size=(0.5,) * 3, grid_size=(4,) * 3)),
+]
+
+
+@pytest.mark.parametrize("name,B,N,kind,kw", STRICT_CASES, ids=[c[0] for c in STRICT_CASES])
+def test_gridify_strict_reservoir_matches_oracle(gg, cuda_dev, oracle_mod, name, B, N, kind, kw):
+    """The reference's K2 reservoir (gridify.cu:259-270) has a schedule-independent seed: reproduced exactly
+    (XORWOW, insertion index, last writer wins), against the oracle's sequential replay."""
+    data, npts = synth.make_batch(B, N, seed0=400, kind=kind, voxels=(kw["voxel_size"][0],))
+    npts[-1, 0] = N - N // 5
+    kw = dict(kw, coord_shift=(1.0, 1.0, 1.0))
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    want = oracle_mod.gridify(data, npts, strict_reservoir=True, **kw)
+    _check5(gg.Gridify(d, n, stride=1, strict_reservoir=True, **kw), want, name + "/Gridify strict")
+    keep_first = oracle_mod.gridify(data, npts, **kw)
+    if name not in ("cfg1_P64_k3", "P128_k7_cls"):  # the others overflow: the two rules really differ
+        assert not np.array_equal(want[0], keep_first[0])
+    # integer-valued weights other than 1 (what later layers see: neighbour counts)
+    data[..., 3] = np.random.default_rng(1).integers(1, 40, size=data.shape[:2]).astype(np.float32)
+    d = _t(data, cuda_dev)
+    _check5(gg.Gridify(d, n, stride=1, strict_reservoir=True, **kw),
+            oracle_mod.gridify(data, npts, strict_reservoir=True, **kw), name + "/Gridify strict, weights")
+
+
 def test_edge_cases(gg, cuda_dev, oracle_mod):
     data, npts = synth.make_batch(3, 64, seed0=1)
     npts[0, 0] = 0
