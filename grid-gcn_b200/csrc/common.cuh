@@ -3,7 +3,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace gg {
+
+// "Already configured on the current device?" for kernel attributes (cudaFuncSetAttribute is per device and
+// the library may serve several devices and host threads of one process).  A lost race only repeats an
+// idempotent call.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    __host__ bool done(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+    __host__ void set(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

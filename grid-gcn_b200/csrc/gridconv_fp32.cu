@@ -285,18 +285,18 @@ static int launch_gridconv_fp32(const ConvParams &p, cudaStream_t st) {
     size_t smem = (size_t)s.total * sizeof(float);
     if (smem > kFp32SmemLimit) return GRIDGCN_ELIMIT;
     if (s.act_global && !p.scratch) return GRIDGCN_EWORKSPACE;
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(gridconv_fp32_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFp32SmemLimit);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set.set(dev);
     }
     long long centers = (long long)p.B * p.O;
     long long tiles = (centers + s.cpt - 1) / s.cpt;
     if (tiles > 0x7fffffff) return GRIDGCN_ELIMIT;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int per_sm = (int)max((size_t)1, min((size_t)8, kFp32SmemLimit / (smem + 1024)));
     int blocks = (int)min(tiles, (long long)sms * per_sm);

@@ -1835,10 +1835,12 @@ constexpr size_t kSmemCap = 224 * 1024;  // dynamic part; static barriers/index 
 
 static void launch_first64(const TcParams &p, int blocks, size_t smem, cudaStream_t st, int tiles, int cpt,
                            int hid, int stash_lo) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done(dev)) {
         cudaFuncSetAttribute(edge_first64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
-        attr_set = true;
+        attr_set.set(dev);
     }
     edge_first64_kernel<3><<<blocks, kTcThreads, smem, st>>>(p, tiles, cpt, hid, stash_lo);
 }
@@ -1849,8 +1851,8 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(point_mlp_tc_kernel<NSPLIT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
         if (e == cudaSuccess)
@@ -1866,7 +1868,7 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
             e = cudaFuncSetAttribute(edge_wide_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemCap);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set.set(dev);
     }
     if (p.na > 0) {  // kernel A
         int chunks = 0, kmax = 0, npmax = 0;
