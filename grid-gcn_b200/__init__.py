@@ -11,7 +11,7 @@ from . import _lib  # noqa: F401  ctypes binding (loads the library lazily)
 from .ops import Gridify, GridifyKNN, GridifyUp, Gridify_occaware, GridifyOccaware, contrib  # noqa: F401
 from .gridconv import (GridConv, GridConvUp, SegHead, sub_g_update, fold_bn, init_layer,  # noqa: F401
                        init_up_layer, features_nco, rowmlp)
-from . import stack, shard  # noqa: F401
+from . import stack, shard, train  # noqa: F401
 from .build import build  # noqa: F401
 
 __all__ = ["Gridify", "GridifyKNN", "GridifyUp", "Gridify_occaware", "GridifyOccaware", "contrib", "GridConv", "sub_g_update", "fold_bn",

@@ -1,0 +1,160 @@
+"""Training-mode GridConv block and the data-parallel training step.
+
+What this is: the block of segmentation/models/gcn_module_g_att.py:172-287 (and the classification
+variants of classification/models/gcn_module_g.py) with BatchNorm in TRAINING mode -- batch statistics
+over all B*O*P edges between consecutive 1x1 convs (utils/ops.py:149-158, `use_global_stats: False`,
+segmentation/configs/configs.yaml:27), moving statistics updated with momentum bn_decay -- written
+op by op on the reference's (B, C, O, P) layout with PyTorch tensor ops, so that autograd provides the
+backward of gather / MLP / attention product / max-pool.  The index operators in front of it
+(Gridify, GridifyKNN, Gridify_occaware, BallKNN) are this library's CUDA kernels; like the reference's
+(gridify-inl.h:227-231) they have no gradient.  One step = forward, backward, ONE all-reduce of the
+flattened gradient bucket (shard.allreduce_gradients; the north star's only collective), optimiser update.
+
+What this is NOT: a fused training kernel.  The fused sm_100a kernels of this repository implement the
+inference form (BatchNorm folded into the convs); the training-mode math here runs on PyTorch's library
+kernels.  `GridConvTrain.export_layer()` hands the trained parameters to the fused kernels, and the
+eval-mode forward of this module is held to the same oracle as they are (tests), which is what ties the
+two together.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import gridconv, shard
+
+BN_EPS = gridconv.BN_EPS
+
+
+class ConvBnRelu(nn.Module):
+    """mlp2d_c stage: Convolution(kernel 1x1) -> BatchNorm(axis=1, fix_gamma=False, momentum=bn_decay)
+    -> relu (utils/ops.py:149-158).  MXNet's `momentum` weighs the OLD moving value; torch's the new one."""
+
+    def __init__(self, stage, bn_decay=0.9):
+        super().__init__()
+        w = torch.as_tensor(np.asarray(stage["weight"], np.float32))
+        self.weight = nn.Parameter(w.reshape(w.shape[0], -1).clone())
+        self.bias = nn.Parameter(torch.as_tensor(np.asarray(stage["bias"], np.float32)).clone())
+        self.bn = nn.BatchNorm2d(w.shape[0], eps=BN_EPS, momentum=1.0 - bn_decay)
+        with torch.no_grad():
+            self.bn.weight.copy_(torch.as_tensor(stage["gamma"]))
+            self.bn.bias.copy_(torch.as_tensor(stage["beta"]))
+            self.bn.running_mean.copy_(torch.as_tensor(stage["moving_mean"]))
+            self.bn.running_var.copy_(torch.as_tensor(stage["moving_var"]))
+
+    def forward(self, x):  # (B, Cin, O, P)
+        y = torch.einsum("oc,bcnp->bonp", self.weight, x) + self.bias[None, :, None, None]
+        return F.relu(self.bn(y))
+
+    def export(self):
+        g = lambda t: t.detach().cpu().numpy().astype(np.float32)  # noqa: E731
+        return dict(weight=g(self.weight), bias=g(self.bias), gamma=g(self.bn.weight), beta=g(self.bn.bias),
+                    moving_mean=g(self.bn.running_mean), moving_var=g(self.bn.running_var))
+
+
+class GridConvTrain(nn.Module):
+    """One GridConv layer with trainable parameters.  ``forward(table, nebidx, cent, centmsk)`` has the
+    fused layer's signature: table (B,Nprev,4+Cin), nebidx (B,O,K) int, cent (B,O,4), centmsk (B,O) ->
+    (B,O,4+Cout) = concat(cent, feats) (ggcn_models_g.py:186)."""
+
+    def __init__(self, layer, pre_relu=True, bn_decay=0.9):
+        super().__init__()
+        self.cin, self.attfdim = int(layer["cin"]), int(layer["attfdim"])
+        self.localfdim = int(layer.get("localfdim", 0))
+        self.att_full = layer.get("att_full", "") or ""
+        self.pre_relu = bool(pre_relu)
+        self.feat = nn.ModuleList([ConvBnRelu(st, bn_decay) for st in layer["feat"]])
+        self.att = nn.ModuleList([ConvBnRelu(st, bn_decay) for st in layer["att"]])
+
+    def forward(self, table, nebidx, cent, centmsk):
+        B, Nprev, W = table.shape
+        _, O, P = nebidx.shape
+        # batch_take_g: take with mode "clip" AFTER the per-batch offset (utils/ops.py:90-92)
+        gi = nebidx.long() + (torch.arange(B, device=table.device) * Nprev)[:, None, None]
+        gi = gi.clamp_(0, B * Nprev - 1)
+        nb = table.reshape(B * Nprev, W)[gi].permute(0, 3, 1, 2)       # (B, 4+C, O, P)
+        cxyz = cent[:, :, :3].permute(0, 2, 1)[:, :, :, None].expand(B, 3, O, P)
+        nloc = nb[:, 0:3]
+        geo = nloc - cxyz
+        dist = geo.square().sum(1, keepdim=True).sqrt()
+        if self.attfdim <= 3:
+            att_vec = geo
+        elif self.attfdim == 4:
+            att_vec = torch.cat([dist, geo], 1)
+        else:
+            att_vec = torch.cat([dist, geo, cxyz, nloc], 1)
+        if self.cin == 0:
+            feats = geo
+        elif self.localfdim:
+            feats = torch.cat([geo, nb[:, 4:]], 1)
+        else:
+            feats = nb[:, 4:]
+        ori = feats
+        for st in self.feat:
+            feats = st(feats)
+        if len(self.att):
+            a = self.att[0](att_vec)
+            if self.att_full == "next":
+                a = torch.cat([a, feats], 1)
+            elif self.att_full == "last":
+                a = torch.cat([a, ori], 1)
+            for st in self.att[1:]:
+                a = st(a)
+            feats = a * feats                                         # gcn_module_g_att.py:167
+        agg = feats.amax(dim=3)                                       # max pooling over P (:57-59)
+        if self.pre_relu:
+            agg = F.relu(agg)
+        agg = agg * centmsk[:, None, :]
+        return torch.cat([cent, agg.permute(0, 2, 1)], 2)
+
+    def export_layer(self):
+        """Parameter dict for the fused inference kernels (gridconv.GridConv folds the BatchNorms)."""
+        return dict(feat=[st.export() for st in self.feat], att=[st.export() for st in self.att],
+                    attfdim=self.attfdim, cin=self.cin, att_full=self.att_full, localfdim=self.localfdim)
+
+
+class GridGcnClassifier(nn.Module):
+    """Encoder ladder (index operator -> GridConvTrain per layer) + global max pool + linear head: the shape
+    of get_symbol_cls_ggcn (classification/models/ggcn_models_g.py:37-111) reduced to what a training step
+    needs.  ``query(data_loc, num, layer_cfg) -> (nebidx, nebidxmsk, cent, centmsk, num)`` supplies the
+    indices: the CUDA operators on a GPU (default), anything with the same outputs in CPU tests."""
+
+    def __init__(self, cfg, params, num_classes=40, query=None, bn_decay=0.9):
+        super().__init__()
+        self.cfg = cfg
+        self.layers = nn.ModuleList([GridConvTrain(p, cfg.pre_relu, bn_decay) for p in params])
+        self.head = nn.Linear(cfg.layers[-1].pt_mlp_lst[-1], num_classes)
+        self._query = query
+
+    def _default_query(self, loc, num, l):
+        from . import stack
+        fn = stack.query_fn(self.cfg)
+        return fn(loc, num, max_o_grid=l.max_o_grid, max_p_grid=l.max_p_grid, kernel_size=l.kernel_size,
+                  stride=l.stride, coord_shift=self.cfg.coord_shift, voxel_size=[l.voxel_size] * 3,
+                  grid_size=[l.grid_size] * 3, loc=self.cfg.loc)
+
+    def forward(self, data, actual_numpoints):
+        q = self._query or self._default_query
+        table, loc, num = data, data, actual_numpoints
+        for l, conv in zip(self.cfg.layers, self.layers):
+            with torch.no_grad():  # index operators: no gradient (gridify-inl.h:227-231)
+                nebidx, _, cent, centmsk, num = q(loc, num, l)
+            table = conv(table, nebidx, cent, centmsk)
+            loc = cent
+        feats = table[:, :, 4:]
+        mask = table.new_ones(feats.shape[:2]) if centmsk is None else centmsk
+        pooled = (feats - (1.0 - mask[:, :, None]) * 1e30).amax(dim=1)  # masked global max pool
+        return self.head(pooled)
+
+
+def train_step(model, optimizer, data, actual_numpoints, labels):
+    """forward -> cross entropy -> backward -> ONE flat gradient all-reduce (mean over ranks) -> update.
+    Returns the local loss (python float).  With equal shard sizes the averaged gradient is the gradient of
+    the global mean loss; BatchNorm statistics stay per rank (the reference has no SyncBN either)."""
+    model.train()
+    optimizer.zero_grad(set_to_none=True)
+    loss = F.cross_entropy(model(data, actual_numpoints), labels)
+    loss.backward()
+    shard.allreduce_gradients([p for p in model.parameters()])
+    optimizer.step()
+    return float(loss.detach())
