@@ -96,7 +96,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
         if not self.samples:
@@ -170,7 +170,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=192, help="clouds per GPU per step")
+    ap.add_argument("--batch", type=int, default=296,
+                    help="clouds per GPU per step (default: two per SM of a 148-SM B200; measured 192 -> 4.19e8, "
+                         "296 -> 4.41e8, 444 -> 4.45e8, 592 -> 4.47e8 points/s)")
     ap.add_argument("--K", type=int, default=64)
     ap.add_argument("--query", default="gridifyknn", choices=["gridifyknn", "gridify", "occaware", "occaware_knn"],
                     help="centre sampling + neighbour query operator (occaware = coverage-aware sampling)")
