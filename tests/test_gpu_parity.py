@@ -103,6 +103,12 @@ def test_edge_cases(gg, cuda_dev, oracle_mod):
     d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
     _check5(gg.Gridify(d, n, **kw), oracle_mod.gridify(data, npts, **kw), "edge/Gridify")
     _check5(gg.GridifyKNN(d, n, **kw), oracle_mod.gridify_knn(data, npts, **kw), "edge/GridifyKNN")
+    _check5(gg.Gridify(d, n, strict_reservoir=True, **kw), oracle_mod.gridify(data, npts, strict_reservoir=True, **kw),
+            "edge/Gridify strict")
+    for ks in (1, 3):  # empty cloud, cloud outside the grid, duplicates; kernel 1: a voxel only covers itself
+        kc = dict(kw, kernel_size=ks, max_o_grid=3)
+        _check5(gg.Gridify_occaware(d, n, seed=3, **kc), oracle_mod.gridify_occaware(data, npts, seed=3, **kc),
+                "edge/occaware k%d" % ks)
     # B = 0 is a no-op
     out = gg.Gridify(d[:0], n[:0], **kw)
     assert out[0].shape == (0, 8, 4)
