@@ -1483,7 +1483,9 @@ edge_first64_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt, 
 // the four-warp version leaves the SM latency bound (issue slots ~20 % busy); here two threads share an
 // edge row in the gather phase (each computes half of the attention stage-0 channels) and two warps share
 // a TMEM lane quadrant in the epilogue (columns [0,64) / [64,128); K | 64 so no centre straddles the
-// split).  Shared-memory layout and ring protocol are those of edge_tc_kernel (kernel_b_base).
+// split).  Every 128-channel chunk has its own TMEM region and "retired" barrier: the MMAs of all chunks of
+// a tile are issued back to back and the epilogue of chunk j overlaps the tensor-core work on the later
+// chunks.  Shared-memory layout and ring protocol are those of edge_tc_kernel (kernel_b_base).
 // ------------------------------------------------------------------------------------------------
 constexpr int kWideThreads = 288;  // warps 0-7: workers; warp 8: TMA + MMA issue
 
@@ -1491,8 +1493,9 @@ template <int NSPLIT>
 __global__ void __launch_bounds__(kWideThreads, 1)
 edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bars[2 * kMaxRing + 1];
-    __shared__ uint32_t seq_off_s[kMaxSeq], seq_bytes_s[kMaxSeq];
+    constexpr int kWideSeq = 32, kWideChunks = 4;       // slices per tile (<= 4 chunks x <= 8 slices), chunks
+    __shared__ uint64_t bars[2 * kMaxRing + kWideChunks];  // ring full / empty, one "MMAs retired" barrier per chunk
+    __shared__ uint32_t seq_off_s[kWideSeq], seq_bytes_s[kWideSeq];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t rowoff_s[kTileRows];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1535,13 +1538,16 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
     } else {
         for (int i = 0; i < kMaxRing; i++) ring.off[i] = (uint32_t)i * kSlotBytes;
     }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
+    // One TMEM region per channel chunk (<= 4 x 128 columns = all of TMEM, one CTA per SM): the MMAs of EVERY
+    // chunk of a tile are issued up-front, back to back, and the epilogue of chunk j runs while the tensor
+    // core works on chunks j+1..  (the per-chunk lock step left the SM idle two thirds of the time).
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, (uint32_t)(Cp / 128 <= 1 ? 128 : (Cp / 128 == 2 ? 256 : 512)));
     if (tid == 0) {
         for (int i = 0; i < ring.nslots; i++) {
             tc::mbar_init(&ring.full[i], 1);
             tc::mbar_init(&ring.empty[i], 1);
         }
-        tc::mbar_init(bar_mma, 1);
+        for (int j = 0; j < kWideChunks; j++) tc::mbar_init(&bar_mma[j], 1);
         tc::mbar_init_fence();
     }
     for (int i = tid; i < kh * 8; i += kWideThreads)  // folded rows, see att0_folded_weight
@@ -1632,15 +1638,17 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
         __syncthreads();
         tc::fence_after_sync();
 
-        for (int j = 0; j < nchunk; j++) {
-            if (warp == 8) {
-                if (lane == 0) {
+        if (warp == 8) {  // every chunk's MMAs, back to back; chunk j signals bar_mma[j]
+            if (lane == 0) {
+                for (int j = 0; j < nchunk; j++) {
                     run_transposed_stage<NSPLIT>(p.a1.Kp, 1, ring, sticky, tc::smem_u32(xa_hi),
-                                                 tc::smem_u32(xa_lo), LBO, 128, tmem, 0);
-                    tc::mma_commit(bar_mma);
+                                                 tc::smem_u32(xa_lo), LBO, 128, tmem + (uint32_t)(j * 128), 0);
+                    tc::mma_commit(&bar_mma[j]);
                 }
-                __syncwarp();
             }
+            __syncwarp();
+        }
+        for (int j = 0; j < nchunk; j++) {
             // ---- epilogue: thread = channel (TMEM lane of quadrant warp & 3), columns [64 * half, +64) ----
             const int ch = j * 128 + (warp & 3) * 32 + lane;
             const bool chv = ch < C;
@@ -1654,12 +1662,11 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             };
             if (warp_on) gather16(fA, col0);
             if (j == 0 && warp < 8) fetch_row();
-            wait_bar(bar_mma, mma_phase);
-            mma_phase ^= 1;
+            if (warp < 8) wait_bar(&bar_mma[j], mma_phase);
             tc::fence_after_sync();
             if (warp_on) {
                 const float ba = bias_a1_s[chv ? ch : 0];
-                const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+                const uint32_t lane_addr = tmem + (uint32_t)(j * 128) + ((uint32_t)((warp & 3) * 32) << 16);
                 float *out_ch = c.out + 4 + ch;
                 float m = -3.402823466e+38f;
                 int pos = 0, cl = col0 / K;
@@ -1713,10 +1720,8 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                     tc::tmem_ld_wait();
                 }
             }
-            tc::fence_before_sync();
-            __syncthreads();
-            tc::fence_after_sync();
         }
+        mma_phase ^= 1;  // every chunk barrier completed once for this tile
         if (warp < 8) {
             for (int i = tid; i < cpt * 4; i += 256) {
                 const long long center = c_base + i / 4;
@@ -1724,9 +1729,13 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                     c.out[center * out_w + (i & 3)] = __ldg(reinterpret_cast<const float *>(c.cent + center) + (i & 3));
             }
         }
+        // the next tile rewrites the operand image and the accumulators: every epilogue read must be done
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
     }
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)(Cp / 128 <= 1 ? 128 : (Cp / 128 == 2 ? 256 : 512)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1972,7 +1981,8 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         int blocks = (int)min(tiles, (long long)sms * per_sm);
         if (p.has_ff)
             edge_tc_kernel<NSPLIT, true><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
-        else if (per_sm == 1 && p.has_att && p.dbg == nullptr && 64 % c.K == 0 && (p.a1.Kp & 7) == 0)
+        else if (per_sm == 1 && p.has_att && p.dbg == nullptr && 64 % c.K == 0 && (p.a1.Kp & 7) == 0 &&
+                 n_slices <= 32 && pad_to(c.Cout, 128) / 128 <= 4)  // slice table / one TMEM region per chunk
             edge_wide_kernel<NSPLIT><<<blocks, kWideThreads, smem, st>>>(p, (int)tiles, cpt);  // 8 worker warps
         else
             edge_tc_kernel<NSPLIT, false><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
