@@ -1655,12 +1655,20 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
             const bool warp_on = warp < 8 && (j * 128 + (warp & 3) * 32) < C;
             const int col0 = 64 * half;
             const float *fbase = p.ftab + (chv ? ch : 0);
-            uint32_t gA[16], fA[16], gB[16], fB[16];
+            // All 64 feature values of this thread's columns are requested before the wait on the chunk's MMAs
+            // (they only depend on the row offsets): 64 loads in flight per thread instead of 16 -- with eight
+            // warps per SM the L2 latency of these gathers is what the epilogue waits for.
+            uint32_t gA[16], gB[16], f0[16], f1[16], f2[16], f3[16];
             auto gather16 = [&](uint32_t (&f)[16], int e0) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) f[i] = __float_as_uint(__ldg(fbase + rowoff_s[e0 + i]));
             };
-            if (warp_on) gather16(fA, col0);
+            if (warp_on) {
+                gather16(f0, col0);
+                gather16(f1, col0 + 16);
+                gather16(f2, col0 + 32);
+                gather16(f3, col0 + 48);
+            }
             if (j == 0 && warp < 8) fetch_row();
             if (warp < 8) wait_bar(&bar_mma[j], mma_phase);
             tc::fence_after_sync();
@@ -1706,19 +1714,16 @@ edge_wide_kernel(const __grid_constant__ TcParams p, int num_tiles, int cpt) {
                 };
                 tc::tmem_ld16(lane_addr + col0, gA);
                 tc::tmem_ld_wait();
-#pragma unroll 1
-                for (int e0 = col0; e0 < col0 + 64; e0 += 32) {
-                    tc::tmem_ld16(lane_addr + e0 + 16, gB);
-                    gather16(fB, e0 + 16);
-                    reduce16(gA, fA);
-                    tc::tmem_ld_wait();
-                    if (e0 + 32 < col0 + 64) {
-                        tc::tmem_ld16(lane_addr + e0 + 32, gA);
-                        gather16(fA, e0 + 32);
-                    }
-                    reduce16(gB, fB);
-                    tc::tmem_ld_wait();
-                }
+                tc::tmem_ld16(lane_addr + col0 + 16, gB);
+                reduce16(gA, f0);
+                tc::tmem_ld_wait();
+                tc::tmem_ld16(lane_addr + col0 + 32, gA);
+                reduce16(gB, f1);
+                tc::tmem_ld_wait();
+                tc::tmem_ld16(lane_addr + col0 + 48, gB);
+                reduce16(gA, f2);
+                tc::tmem_ld_wait();
+                reduce16(gB, f3);
             }
         }
         mma_phase ^= 1;  // every chunk barrier completed once for this tile
