@@ -43,6 +43,9 @@ constexpr int kTileRows = 128;
 #ifndef GG_SLICE_K
 #define GG_SLICE_K 32   // k extent of one streamed weight slice (tools/build_variant.py -DGG_SLICE_K=16)
 #endif
+#ifndef GG_WIDE_ALWAYS
+#define GG_WIDE_ALWAYS 0  // 1: the 8-warp wide kernel also where three 5-warp CTAs per SM would fit (layer 1)
+#endif
 #ifndef GG_RING_CAP
 #define GG_RING_CAP 4   // most ring slots the row-major kernel A / kernel B take (transposed kernel A: + 2)
 #endif
@@ -1986,9 +1989,12 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         int blocks = (int)min(tiles, (long long)sms * per_sm);
         if (p.has_ff)
             edge_tc_kernel<NSPLIT, true><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
-        else if (per_sm == 1 && p.has_att && p.dbg == nullptr && 64 % c.K == 0 && (p.a1.Kp & 7) == 0 &&
-                 n_slices <= 32 && pad_to(c.Cout, 128) / 128 <= 4)  // slice table / one TMEM region per chunk
-            edge_wide_kernel<NSPLIT><<<blocks, kWideThreads, smem, st>>>(p, (int)tiles, cpt);  // 8 worker warps
+        else if ((per_sm == 1 || GG_WIDE_ALWAYS) && p.has_att && p.dbg == nullptr && 64 % c.K == 0 &&
+                 (p.a1.Kp & 7) == 0 && n_slices <= 32 &&
+                 pad_to(c.Cout, 128) / 128 <= 4) {  // slice table / one TMEM region per chunk
+            // 288 threads x ~160 registers: one CTA per SM whatever shared memory would allow
+            edge_wide_kernel<NSPLIT><<<(int)min(tiles, (long long)sms), kWideThreads, smem, st>>>(p, (int)tiles, cpt);
+        }
         else
             edge_tc_kernel<NSPLIT, false><<<blocks, kTcThreads, smem, st>>>(p, (int)tiles, cpt);
         return (int)cudaGetLastError();
