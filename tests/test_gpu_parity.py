@@ -426,6 +426,15 @@ def test_golden_fixtures_on_gpu(gg, cuda_dev):
         got = gg.GridConv(layer, cuda_dev)(_t(z["table"], cuda_dev), _t(z["nebidx"], cuda_dev),
                                            _t(z["cent"], cuda_dev), _t(z["centmsk"], cuda_dev))
         assert _rel_err(got.cpu().numpy()[..., 4:], z["out"][..., 4:]) <= 1e-3, case
+    z = np.load(os.path.join(GOLDEN, "gridify_strict.npz"))
+    _check5(gg.Gridify(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), strict_reservoir=True, **kwo),
+            [z[n] for n in NAMES], "golden strict reservoir")
+    z = np.load(os.path.join(GOLDEN, "gridconv_cls.npz"))
+    layer = gridconv.init_layer(np.random.default_rng(31), 16, [16, 16, 32], 4, att_ele_lst=[16, 32, 32],
+                                att_full="next", localfdim=3)
+    got = gg.GridConv(layer, cuda_dev, precision="fp32")(_t(z["table"], cuda_dev), _t(z["nebidx"], cuda_dev),
+                                                         _t(z["cent"], cuda_dev), _t(z["centmsk"], cuda_dev))
+    assert _rel_err(got.cpu().numpy()[..., 4:], z["out"][..., 4:]) <= 1e-3, "golden cls block"
 
 
 @pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
