@@ -41,6 +41,20 @@ def test_library_is_sm100a_native(gg):
     assert "sm_100a" in out, out
 
 
+def test_library_uses_blackwell_tensor_and_copy_engines(gg):
+    """SASS evidence (B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, bulk copies ->
+    UBLKCP): the GridConv kernels really are tcgen05 / TMEM / TMA-engine code, not mma.sync recompiles."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", gg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass and "WGMMA" not in sass
+
+
 def test_argument_validation_without_gpu(gg):
     """Rejected arguments never reach a launch, so these calls are safe on a CPU-only box."""
     L = gg._lib.lib()
