@@ -47,6 +47,7 @@ SIGNATURES = {
     "gridgcn_rowmlp_fwd": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp,
                                 ctypes.c_longlong, _vp]),
     "gridgcn_debug_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "gridgcn_debug_curand_first_uniform": (_i, [_vp, _i, _vp, _vp, _vp]),
     "gridgcn_debug_phase_buffer": (None, [_vp]),
     "gridgcn_gridconv_packed_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i]),
     "gridgcn_gridconv_pack": (_i, [ctypes.POINTER(MlpDesc), _i, _vp, _sz, _vp]),

@@ -222,6 +222,12 @@ int gridgcn_rowmlp_fwd(const float *in1, int ld1, int c1, const float *in2, int 
 int gridgcn_debug_tc_gemm(const float *A, const float *B, float *D, int N, int K, int nsplit,
                           void *stream);
 
+/* Debug / self-test: for each of n 64-bit seeds, the first uniform of this library's XORWOW (`ours`) and of
+ * the device cuRAND the reference calls, curand_init(seed, 0, 0) + curand_uniform (`theirs`).  Not part of
+ * the operator ABI. */
+int gridgcn_debug_curand_first_uniform(const unsigned long long *seeds, int n, float *ours, float *theirs,
+                                       void *stream);
+
 /* Debug: see csrc/gridconv_fp32.cu.  8 x u64 device buffer of per-phase cycles, NULL = off. */
 void gridgcn_debug_phase_buffer(unsigned long long *dev_buf);
 

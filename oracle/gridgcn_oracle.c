@@ -79,6 +79,14 @@ static float xorwow_uniform(xorwow_t *s) {
     return fmaf((float)xorwow_next(s), 2.3283064e-10f, 2.3283064e-10f / 2.0f);
 }
 
+/* Probe for the tests: the first uniform after xorwow_init(seed) -- compared on the GPU box with the
+ * device cuRAND the reference calls (tests/test_gpu_tc.py::test_xorwow_matches_device_curand).       */
+float gridgcn_oracle_xorwow_first_uniform(unsigned long long seed) {
+    xorwow_t s;
+    xorwow_init(&s, (uint64_t)seed);
+    return xorwow_uniform(&s);
+}
+
 /* ---------------------------------------------------------------------------------- */
 /* Shared pieces                                                                        */
 /* ---------------------------------------------------------------------------------- */

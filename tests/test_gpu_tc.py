@@ -48,3 +48,31 @@ def test_tf32_operands_are_truncated(gg, cuda_dev):
     exact = A.astype(np.float64) @ B.astype(np.float64).T
     assert np.abs(got - want).max() < 1e-5
     assert np.abs(got - exact).max() > 1e-4  # i.e. it really is tf32, not fp32
+
+
+def test_xorwow_matches_device_curand(gg, cuda_dev):
+    """The strict K2 reservoir and the coverage-aware sampling draw from the library's own XORWOW; the reference
+    draws from cuRAND (curand_init(seed, 0, 0) + curand_uniform, gridify.cu:260-261).  Bit equality of the first
+    uniform for small, large, negative-int-widened and random 64-bit seeds -- and of the CPU oracle's XORWOW."""
+    import ctypes
+    from oracle import oracle
+    rng = np.random.default_rng(0)
+    seeds = np.concatenate([np.arange(0, 4096, dtype=np.uint64),
+                            np.array([2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1, 2 ** 32, 2 ** 63, 2 ** 64 - 1], np.uint64),
+                            (np.arange(-2000, 0, dtype=np.int64)).astype(np.uint64),  # (long long)(int) seeds < 0
+                            rng.integers(0, 2 ** 63, size=20000, dtype=np.uint64) * np.uint64(2) + np.uint64(1)])
+    s = torch.from_numpy(seeds.view(np.int64)).to(cuda_dev)
+    ours = torch.empty(len(seeds), dtype=torch.float32, device=cuda_dev)
+    theirs = torch.empty_like(ours)
+    rc = gg._lib.lib().gridgcn_debug_curand_first_uniform(s.data_ptr(), len(seeds), ours.data_ptr(),
+                                                          theirs.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(ours, theirs)
+    assert float(theirs.min()) > 0.0 and float(theirs.max()) <= 1.0
+    # the CPU oracle's XORWOW (gridgcn_oracle.c) through its exported probe
+    L = oracle.lib()
+    L.gridgcn_oracle_xorwow_first_uniform.restype = ctypes.c_float
+    L.gridgcn_oracle_xorwow_first_uniform.argtypes = [ctypes.c_ulonglong]
+    host = np.array([L.gridgcn_oracle_xorwow_first_uniform(int(x)) for x in seeds[:6200]], np.float32)
+    assert np.array_equal(host, theirs.cpu().numpy()[:6200])
