@@ -8,15 +8,25 @@
  * That is a legal schedule of the reference kernels, hence a legal reference output,
  * and it is the one the sm_100a kernels in grid-gcn_b200/csrc are compared against.
  *
- * PARITY STATUS: "parity unpinned" at the reference level.  The reference ships no
- * tests, golden vectors or known-answer values for these operators, its
- * Gridify/GridifyKNN/GridifyUp CPU specialisations are LOG(FATAL) stubs
- * (gridifyop/gridify.cc:30-39, gridifyknn.cc:30-39, gridify_up.cc:29-38) and MXNet is
- * not installable here, so the restatement below cannot be checked against a run of the
- * reference.  It is pinned instead by (i) the 27-point lattice sanity vector of
- * utils/ops.py:282-299, (ii) a second, independently written numpy twin
- * (oracle/np_twin.py) and (iii) for KNN / BallKNN only, the reference's own kernel bodies
- * compiled from /root/reference through a shim (oracle/ref_shim, `make ref`).
+ * PARITY STATUS.  The reference ships no tests, golden vectors or known-answer values for these
+ * operators, its Gridify/GridifyKNN/GridifyUp CPU specialisations are LOG(FATAL)
+ * stubs (gridifyop/gridify.cc:30-39, gridifyknn.cc:30-39, gridify_up.cc:29-38) and MXNet is not
+ * installable here, so the reference cannot be RUN as shipped.  The restatement is pinned instead by
+ *  (i)   the reference's OWN kernel bodies: `make ref` compiles the `__global__` functions of
+ *        gridify.cu:102-291, gridifyknn.cu:115-333, gridify_up.cu:102-225 and k_nn-inl.h /
+ *        ball_k_nn-inl.h from where they lie under /root/reference (ref_shim/: CUDA threads run one
+ *        after the other in ascending index = the canonical schedule) into oracle/_ref/*.so;
+ *        tests/test_ref_gridify.py and tests/test_ref_knn.py demand bit equality with this file --
+ *        and, on the GPU box, with the CUDA kernels -- for everything the reference does
+ *        deterministically: voxel hash, centre numbering, bucket order, K2's raster walk and its
+ *        schedule-independent reservoir (strict mode below), K4's shell-expanding insertion sort,
+ *        K5/K6, KNN, BallKNN;
+ *  (ii)  the device cuRAND the reference calls, for the XORWOW used here (GPU test);
+ *  (iii) the 27-point lattice sanity vector of utils/ops.py:282-299 and an independently written
+ *        numpy twin (oracle/np_twin.py).
+ * What stays "parity unpinned": the time-seeded reservoirs of K1 / K5 (not reproducible by
+ * construction: the canonical rule is keep-first), the slots the reference fills from uninitialised
+ * locals (defined here, SURVEY s8c rule 8), and coverage-aware sampling (no source in the tree).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * may load this library.  Nothing under grid-gcn_b200/ imports it.

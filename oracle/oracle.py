@@ -34,7 +34,7 @@ def build_ref():
     """Compile oracle/_ref from the reference sources (only where /root/reference exists)."""
     if not os.path.isdir("/root/reference/gridifyop"):
         return None
-    subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])  # libknn_ref.so and libgridify_ref.so
     return os.path.join(_HERE, "_ref", "libknn_ref.so")
 
 

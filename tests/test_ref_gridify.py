@@ -1,0 +1,189 @@
+"""The restatement (and, on the GPU box, the CUDA kernels) against the REFERENCE's own Gridify / GridifyKNN /
+GridifyUp kernel BODIES -- gridify.cu:102-291, gridifyknn.cu:115-333, gridify_up.cu:102-225 -- compiled from where
+they lie into oracle/_ref/libgridify_ref.so (`make -C oracle ref`; ref_shim/cuda_seq.h runs the CUDA threads one
+after the other in ascending index: the canonical schedule of SURVEY.md s8c, which is a legal schedule of those
+kernels).  This is what pins the oracle for these operators: everything deterministic in the reference -- the
+voxel hash, centre numbering, bucket order, K2's raster walk AND its schedule-independent reservoir, K4's
+shell-expanding insertion sort, K5/K6 -- is compared bit for bit.  Not compared: the time-seeded reservoirs of
+K1 / K5 (the cases below stay within max_p_grid points per voxel and max_o_grid occupied voxels) and the slots
+the reference fills from uninitialised locals (rows with fewer than P candidates: their cent.w).
+Skipped when the library has not been built (it travels to the GPU box with the snapshot)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from gridgcn_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libgridify_ref.so")
+NAMES = ("nebidx", "nebidxmsk", "cent", "centmsk", "actual_centnum")
+_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+
+def _ref():
+    if not os.path.exists(REF):
+        from oracle import oracle
+        try:
+            oracle.build_ref()
+        except Exception:
+            pass
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/libgridify_ref.so not built (needs /root/reference)")
+    L = ctypes.CDLL(REF)
+    sig = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 7 + [ctypes.c_void_p] * 3 + [ctypes.c_ulong] + [ctypes.c_void_p] * 5
+    L.ref_gridify.argtypes = sig
+    L.ref_gridify_knn.argtypes = sig
+    L.ref_gridify_up.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 3 + \
+        [ctypes.c_ulong] + [ctypes.c_void_p] * 2
+    return L
+
+
+def _run(fn, data, npts, kw, seconds=123456):
+    B, N, _ = data.shape
+    O, P = kw["max_o_grid"], kw["max_p_grid"]
+    shift = np.asarray(kw["coord_shift"], np.float32)
+    voxel = np.asarray(kw["voxel_size"], np.float32)
+    grid = np.asarray(kw["grid_size"], np.int32)
+    out = (np.empty((B, O, P), np.int32), np.empty((B, O, P), np.float32), np.empty((B, O, 4), np.float32),
+           np.empty((B, O), np.float32), np.empty((B, 1), np.int32))
+    data = np.ascontiguousarray(data, np.float32)
+    npts = np.ascontiguousarray(npts, np.int32)
+    fn(_p(data), _p(npts), B, N, O, P, kw["kernel_size"], 1, kw["loc"], _p(shift), _p(voxel), _p(grid), seconds,
+       *[_p(o) for o in out])
+    return out
+
+
+def _no_k1_overflow(data, npts, kw):
+    """True when no voxel holds more than P points and at most O voxels are occupied: none of the reference's
+    time-seeded reservoirs (gridify.cu:148-153,181-186) can fire."""
+    shift, voxel = np.asarray(kw["coord_shift"], np.float32), np.asarray(kw["voxel_size"], np.float32)
+    grid = np.asarray(kw["grid_size"])
+    for b in range(len(data)):
+        pts = data[b, :int(npts[b, 0]), :3]
+        c = np.floor(((pts + shift).astype(np.float32) / voxel).astype(np.float32)).astype(np.int64)
+        ok = np.all((c >= 0) & (c < grid), axis=1)
+        lin = (c[ok, 2] * grid[1] + c[ok, 1]) * grid[0] + c[ok, 0]
+        _, counts = np.unique(lin, return_counts=True)
+        if len(counts) > kw["max_o_grid"] or (len(counts) and counts.max() > kw["max_p_grid"]):
+            return False
+    return True
+
+
+# (name, B, N, kind, kwargs): K2 overflow (more candidates than slots in a neighbourhood) is welcome -- its
+# reservoir is deterministic -- K1 overflow is not
+CASES = [
+    ("cfg1_like", 2, 1024, "surface", dict(max_p_grid=64, max_o_grid=1024, kernel_size=3, loc=1,
+                                           voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("k2_overflow", 2, 3000, "surface", dict(max_p_grid=16, max_o_grid=3000, kernel_size=3, loc=1,
+                                             voxel_size=(0.05,) * 3, grid_size=(40,) * 3)),
+    ("kernel5_aniso_loc0", 2, 700, "surface", dict(max_p_grid=48, max_o_grid=100, kernel_size=5, loc=0,
+                                                   voxel_size=(0.2, 0.25, 0.5), grid_size=(10, 8, 4))),
+    ("coarse_heavy_k2_overflow", 3, 400, "ball", dict(max_p_grid=32, max_o_grid=64, kernel_size=3, loc=1,
+                                                      voxel_size=(0.5,) * 3, grid_size=(4,) * 3)),
+]
+
+
+def _inputs(name, B, N, kind, kw):
+    data, npts = synth.make_batch(B, N, seed0=500, kind=kind, voxels=(kw["voxel_size"][0],))
+    npts[-1, 0] = N - N // 6
+    data[0, :, 3] = np.random.default_rng(2).integers(1, 9, size=N).astype(np.float32)  # integer weights != 1
+    kw = dict(kw, coord_shift=(1.0, 1.0, 1.0))
+    assert _no_k1_overflow(data, npts, kw), name
+    return data, npts, kw
+
+
+@pytest.mark.parametrize("name,B,N,kind,kw", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_reference_gridify_bodies(oracle_mod, name, B, N, kind, kw):
+    L = _ref()
+    data, npts, kw = _inputs(name, B, N, kind, kw)
+    # Gridify: the reference's K2 always runs its reservoir => the oracle's strict mode is the comparison
+    ref = _run(L.ref_gridify, data, npts, kw)
+    want = oracle_mod.gridify(data, npts, strict_reservoir=True, **kw)
+    for r, w, n in zip(ref, want, NAMES):
+        assert np.array_equal(r, w), (name, "Gridify", n)
+    # ... and it is independent of the wall-clock seed as long as K1 does not overflow
+    again = _run(L.ref_gridify, data, npts, kw, seconds=987)
+    assert all(np.array_equal(a, b) for a, b in zip(ref, again))
+    # GridifyKNN (P <= 64: best[64..127] is never initialised, gridifyknn.cu:259-261)
+    if kw["max_p_grid"] <= 64:
+        ref = _run(L.ref_gridify_knn, data, npts, kw)
+        want = oracle_mod.gridify_knn(data, npts, **kw)
+        for r, w, n in zip(ref, want, NAMES):
+            if n == "cent":  # cent.w of short rows sums uninitialised besti[] in the reference (:309-313)
+                full = np.array([[len(set(row)) == len(row) for row in cloud] for cloud in want[0]])
+                assert np.array_equal(r[..., :3], w[..., :3]), (name, "GridifyKNN cent xyz")
+                assert np.array_equal(r[..., 3][full], w[..., 3][full]), (name, "GridifyKNN cent.w")
+            else:
+                assert np.array_equal(r, w), (name, "GridifyKNN", n)
+
+
+def _run_up(L, down, up, dn, un, O, P, vox, grid, seconds=4242):
+    shift, voxel, g = np.ones(3, np.float32), np.full(3, vox, np.float32), np.full(3, grid, np.int32)
+    nebidx, msk = np.empty((len(down), O, P), np.int32), np.empty((len(down), O, P), np.float32)
+    L.ref_gridify_up(_p(down), _p(up), _p(dn), _p(un), len(down), down.shape[1], O, P, 3, _p(shift), _p(voxel),
+                     _p(g), seconds, _p(nebidx), _p(msk))
+    return nebidx, msk
+
+
+UP_CASES = ((256, 1024, 5, 0.133333, 15), (24, 256, 5, 0.4, 5), (1024, 2048, 5, 0.05, 40))  # decoder stages, P = 5
+
+
+def _up_inputs(seed, Nd, O, vox):
+    down, dn = synth.make_batch(2, Nd, seed0=600 + seed, voxels=(vox,))
+    up, un = synth.make_batch(2, O, seed0=700 + seed, voxels=(vox,))
+    dn[1, 0], un[1, 0] = Nd - Nd // 5, O - O // 7
+    return down, up, dn, un
+
+
+def test_oracle_matches_reference_gridify_up_bodies(oracle_mod):
+    """K5 splats every down point into its kernel^3 neighbour buckets; a bucket that receives more than P points
+    fires a time-seeded reservoir (gridify_up.cu:160-166).  With P = 128 nothing overflows: full equality.  With
+    the decoder's P = 5, rows whose bucket holds at most 5 points (known from the P = 128 run) must be equal and
+    the others must still agree on the mask."""
+    L = _ref()
+    for seed, (Nd, O, P, vox, grid) in enumerate(UP_CASES):
+        down, up, dn, un = _up_inputs(seed, Nd, O, vox)
+        kw = dict(max_o_grid=O, kernel_size=3, coord_shift=(1, 1, 1), voxel_size=(vox,) * 3, grid_size=(grid,) * 3)
+        big_ref = _run_up(L, down, up, dn, un, O, 128, vox, grid)
+        big = oracle_mod.gridify_up(down, up, dn, un, max_p_grid=128, **kw)
+        assert np.array_equal(big_ref[0], big[0]) and np.array_equal(big_ref[1], big[1]), seed
+        count = big[1].sum(axis=2)
+        assert count.max() < 128
+        ref = _run_up(L, down, up, dn, un, O, P, vox, grid)
+        want = oracle_mod.gridify_up(down, up, dn, un, max_p_grid=P, **kw)
+        assert np.array_equal(ref[1], want[1]), seed
+        fits = count <= P
+        assert fits.any() and np.array_equal(ref[0][fits], want[0][fits]), seed
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_gridify_bodies(gg, cuda_dev):
+    """The CUDA kernels against the reference's own kernel bodies directly (no oracle in between)."""
+    import torch
+    L = _ref()
+    for name, B, N, kind, kw in CASES:
+        data, npts, kw = _inputs(name, B, N, kind, kw)
+        d, n = torch.from_numpy(data).to(cuda_dev), torch.from_numpy(npts).to(cuda_dev)
+        ref = _run(L.ref_gridify, data, npts, kw)
+        got = gg.Gridify(d, n, stride=1, strict_reservoir=True, **kw)
+        for r, g, nm in zip(ref, got, NAMES):
+            assert np.array_equal(r, g.cpu().numpy()), (name, "Gridify", nm)
+        if kw["max_p_grid"] <= 64:
+            ref = _run(L.ref_gridify_knn, data, npts, kw)
+            got = gg.GridifyKNN(d, n, stride=1, **kw)
+            for r, g, nm in zip(ref, got, NAMES):
+                if nm != "cent":
+                    assert np.array_equal(r, g.cpu().numpy()), (name, "GridifyKNN", nm)
+                else:
+                    assert np.array_equal(r[..., :3], g.cpu().numpy()[..., :3]), (name, "GridifyKNN cent xyz")
+    for seed, (Nd, O, P, vox, grid) in enumerate(UP_CASES):  # GridifyUp at the decoder's P: rows whose bucket fits
+        down, up, dn, un = _up_inputs(seed, Nd, O, vox)
+        fits = _run_up(L, down, up, dn, un, O, 128, vox, grid)[1].sum(axis=2) <= P
+        ref = _run_up(L, down, up, dn, un, O, P, vox, grid)
+        got = gg.GridifyUp(*[torch.from_numpy(a).to(cuda_dev) for a in (down, up, dn, un)], max_p_grid=P,
+                           max_o_grid=O, kernel_size=3, coord_shift=(1, 1, 1), voxel_size=(vox,) * 3,
+                           grid_size=(grid,) * 3)
+        assert np.array_equal(ref[1], got[1].cpu().numpy()), seed
+        assert fits.any() and np.array_equal(ref[0][fits], got[0].cpu().numpy()[fits]), seed
