@@ -15,7 +15,7 @@
  *  (i)   the reference's OWN kernel bodies: `make ref` compiles the `__global__` functions of
  *        gridify.cu:102-291, gridifyknn.cu:115-333, gridify_up.cu:102-225 and k_nn-inl.h /
  *        ball_k_nn-inl.h from where they lie under /root/reference (ref_shim/: CUDA threads run one
- *        after the other in ascending index = the canonical schedule) into oracle/_ref/*.so;
+ *        after the other in ascending index = the canonical schedule) into the libraries under oracle/_ref;
  *        tests/test_ref_gridify.py and tests/test_ref_knn.py demand bit equality with this file --
  *        and, on the GPU box, with the CUDA kernels -- for everything the reference does
  *        deterministically: voxel hash, centre numbering, bucket order, K2's raster walk and its

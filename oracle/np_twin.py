@@ -3,8 +3,8 @@
 Written against SURVEY.md Appendix A, *not* as a transliteration of gridgcn_oracle.c: it uses
 the sorted / CSR formulation (stable sort by voxel key, first-occurrence ranking, k-way merge,
 stable sort by distance) that the sm_100a kernels use, so agreement between the two pins both
-the literal restatement and the reformulation.  Parity status: "parity unpinned" at the
-reference level (see gridgcn_oracle.c).
+the literal restatement and the reformulation.  Parity status: see the header of
+gridgcn_oracle.c (pinned against the reference's own kernel bodies; CAS unpinned).
 
 Reference lines followed: gridify.cu:126-190,218-290; gridifyknn.cu:231-332;
 gridify_up.cu:121-169,190-224 (paths relative to /root/reference/gridifyop/).

@@ -1,8 +1,9 @@
 """ctypes front-end of the CPU oracle (oracle/gridgcn_oracle.c).
 
 TEST INFRASTRUCTURE -- only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
-``--impl reference`` leg may import this module.  Parity status: "parity unpinned" at the
-reference level (see the header of gridgcn_oracle.c).
+``--impl reference`` leg may import this module.  Parity status: see the header of gridgcn_oracle.c
+(the grid operators are pinned against the reference's own kernel bodies, oracle/_ref; coverage-aware sampling
+and the numpy GridConv block are unpinned).
 
 All functions take and return numpy arrays and mirror the reference operators' argument
 names (gridifyop/gridify-inl.h:58-87,146-152; gridify_up-inl.h:58-81,137-143;
