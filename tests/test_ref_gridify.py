@@ -119,6 +119,37 @@ def test_oracle_matches_reference_gridify_bodies(oracle_mod, name, B, N, kind, k
                 assert np.array_equal(r, w), (name, "GridifyKNN", n)
 
 
+def test_baseline_config0_against_reference_bodies(oracle_mod):
+    """BASELINE.json configs[0]: a single synthetic 1024-point cloud, one Gridify + one GridifyKNN, CPU reference,
+    index tensors bit-exact.  The CPU reference here IS the reference's kernel source (sequential canonical
+    schedule); the golden fixtures gridify_cfg1 / gridifyknn_cfg1 hold the same inputs for the GPU box."""
+    L = _ref()
+    data, npts = synth.make_batch(1, 1024, seed0=0)
+    base = dict(max_o_grid=1024, loc=1, coord_shift=(1.0, 1.0, 1.0), voxel_size=(0.05,) * 3, grid_size=(40,) * 3)
+    kg, kk = dict(base, max_p_grid=64, kernel_size=3), dict(base, max_p_grid=32, kernel_size=5)
+    assert _no_k1_overflow(data, npts, kg)
+    for r, w, n in zip(_run(L.ref_gridify, data, npts, kg), oracle_mod.gridify(data, npts, strict_reservoir=True, **kg),
+                       NAMES):
+        assert np.array_equal(r, w), ("Gridify", n)
+    # no neighbourhood of this cloud overflows 64 slots: the canonical keep-first output is the same tensor
+    for a, b in zip(oracle_mod.gridify(data, npts, **kg), oracle_mod.gridify(data, npts, strict_reservoir=True, **kg)):
+        assert np.array_equal(a, b)
+    ref, want = _run(L.ref_gridify_knn, data, npts, kk), oracle_mod.gridify_knn(data, npts, **kk)
+    for r, w, n in zip(ref, want, NAMES):
+        if n != "cent":
+            assert np.array_equal(r, w), ("GridifyKNN", n)
+    assert np.array_equal(ref[2][..., :3], want[2][..., :3])
+    # the committed golden fixtures of this configuration (what the GPU box checks) are these very tensors
+    zg = np.load(os.path.join(ROOT, "tests", "golden", "gridify_cfg1.npz"))
+    zk = np.load(os.path.join(ROOT, "tests", "golden", "gridifyknn_cfg1.npz"))
+    assert np.array_equal(zg["data"], data) and np.array_equal(zk["data"], data)
+    for n, r in zip(NAMES, _run(L.ref_gridify, data, npts, kg)):
+        assert np.array_equal(zg[n], r), ("golden Gridify", n)
+    for n, r in zip(NAMES, ref):
+        if n != "cent":
+            assert np.array_equal(zk[n], r), ("golden GridifyKNN", n)
+
+
 def _run_up(L, down, up, dn, un, O, P, vox, grid, seconds=4242):
     shift, voxel, g = np.ones(3, np.float32), np.full(3, vox, np.float32), np.full(3, grid, np.int32)
     nebidx, msk = np.empty((len(down), O, P), np.int32), np.empty((len(down), O, P), np.float32)
