@@ -298,6 +298,13 @@ static void occaware_sampling_cloud(int O, const float *gridf, gridify_scratch_t
     }
 }
 
+/* K1's reservoirs (gridify.cu:148-153, :181-186) are seeded with index + tv_usec: irreproducible on a GPU, and
+ * the canonical rule is keep-first (g_k1_seconds < 0).  For the comparison with the reference's own kernel
+ * bodies (oracle/_ref, run sequentially with a GIVEN `seconds`) they can be replayed literally: a test-only
+ * switch, set through gridgcn_oracle_set_k1_seconds().                                                    */
+static long long g_k1_seconds = -1;
+void gridgcn_oracle_set_k1_seconds(long long seconds) { g_k1_seconds = seconds; }
+
 /* K1 = K3: gridify_kernel_build_index, gridify.cu:126-190 (== gridifyknn.cu:139-203),
  * one cloud, threads i_pt = 0..npts-1 executed in ascending order.
  * Canonical overflow rule (SURVEY s8c rule 7): keep-first, i.e. the time-seeded reservoir
@@ -305,8 +312,9 @@ static void occaware_sampling_cloud(int O, const float *gridf, gridify_scratch_t
 static void build_index_cloud(const float *data, int npts, int O, int P, int loc,
                               const float *shift, const float *voxel, const float *gridf,
                               gridify_scratch_t *s, float *centmsk, int *centcount,
-                              const occaware_t *oa) {
+                              const occaware_t *oa, long long index0) {
     int ncent = 0;
+    const long long k1 = oa ? -1 : g_k1_seconds; /* index0 = b * N: global index of this cloud's thread 0 */
     for (int i_pt = 0; i_pt < npts; i_pt++) {
         const float *p_pt = data + (size_t)i_pt * DATA_NDIM;
         int coor[3];
@@ -315,6 +323,11 @@ static void build_index_cloud(const float *data, int npts, int O, int P, int loc
         int grid_pntidx = s->coor_counter[coor_indx]++;             /* :145 atomicAdd */
         if (grid_pntidx < P) {
             s->coor_to_pntidx[(size_t)coor_indx * P + grid_pntidx] = i_pt; /* :147 */
+        } else if (k1 >= 0) { /* :148-153, literal replay with a given tv_usec */
+            xorwow_t st;
+            xorwow_init(&st, (uint64_t)(index0 + i_pt) + (uint64_t)k1);
+            int insrtidx = (int)(ceilf(xorwow_uniform(&st) * (float)(grid_pntidx + 1)) - 1.0f);
+            if (insrtidx < P) s->coor_to_pntidx[(size_t)coor_indx * P + insrtidx] = i_pt;
         } /* else: keep-first */
         if (loc == 1) { /* :155-162, product rounded, then added */
             float *acc = s->coor_to_locxyzw + (size_t)coor_indx * DATA_NDIM;
@@ -335,6 +348,11 @@ static void build_index_cloud(const float *data, int npts, int O, int P, int loc
                 s->voxelidx_to_coor[tmp] = coor_indx; /* :178 */
                 centmsk[tmp] = 1.0f;                  /* :179 */
                 if (oa) occaware_cover_add(oa, coor, gridf, +1); /* K9: coverage counts */
+            } else if (k1 >= 0) { /* :180-186, literal replay */
+                xorwow_t st;
+                xorwow_init(&st, (uint64_t)(index0 + i_pt) + 2u * (uint64_t)k1);
+                int insrtidx = (int)(ceilf(xorwow_uniform(&st) * (float)(tmp + 1)) - 1.0f);
+                if (insrtidx < O) s->voxelidx_to_coor[insrtidx] = coor_indx;
             } /* else: keep-first (Gridify) / challenger of the sampling kernel (occaware) */
         }
     }
@@ -494,6 +512,7 @@ static void set_gridf(const int grid[3], float gridf[3]) {
 
 static int g_num_threads = 1;
 
+
 void gridgcn_oracle_set_threads(int n) { g_num_threads = n > 0 ? n : 1; }
 
 int gridgcn_oracle_max_threads(void) {
@@ -541,7 +560,7 @@ static int gridify_common(int knn, const float *data, const int *npts, int B, in
             init_outputs(nb, nm, ce, cm, cn, O, P);
             scratch_reset(&s, (int)G);
             int ncent = 0;
-            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &ncent, NULL);
+            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &ncent, NULL, (long long)b * N);
             if (knn)
                 query_knn_cloud(d, O, P, ks, loc, voxel, gridf, &s, ncent, mode, nb, nm, ce, cn,
                                 best, besti);
@@ -615,7 +634,7 @@ int gridgcn_oracle_gridify_occaware(const float *data, const int *npts, int B, i
             scratch_reset(&s, (int)G);
             memset(oa.cover, 0, sizeof(int) * (size_t)G);
             int nocc = 0;
-            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &nocc, &oa);
+            build_index_cloud(d, n, O, P, loc, shift, voxel, gridf, &s, cm, &nocc, &oa, (long long)b * N);
             occaware_sampling_cloud(O, gridf, &s, &oa, nocc, (uint64_t)seed);
             if (knn_query)
                 query_knn_cloud(d, O, P, ks, loc, voxel, gridf, &s, nocc, dist_fma, nb, nm, ce, cn,

@@ -49,6 +49,14 @@ def lib():
     return _lib
 
 
+def set_k1_seconds(seconds):
+    """Test-only: replay K1's time-seeded reservoirs literally with this `tv_usec` (None / negative: the
+    canonical keep-first rule).  Used to compare with the reference's own kernel bodies in the overflow regime."""
+    L = lib()
+    L.gridgcn_oracle_set_k1_seconds.argtypes = [ctypes.c_longlong]
+    L.gridgcn_oracle_set_k1_seconds(-1 if seconds is None else int(seconds))
+
+
 def set_threads(n):
     lib().gridgcn_oracle_set_threads(int(n))
 

@@ -150,6 +150,37 @@ def test_baseline_config0_against_reference_bodies(oracle_mod):
             assert np.array_equal(zk[n], r), ("golden GridifyKNN", n)
 
 
+def test_k1_reservoirs_replayed_with_a_given_seed(oracle_mod):
+    """The overflow regime (more than P points in a voxel, more than O occupied voxels): the reference seeds K1's
+    reservoirs with index + tv_usec.  Given the same `seconds`, the restatement replays them literally and stays
+    bit-equal to the reference bodies (Gridify incl. the K2 reservoir, GridifyKNN); the canonical keep-first
+    output differs from both, as it must."""
+    L = _ref()
+    data, npts = synth.make_batch(2, 1500, seed0=7, kind="ball", voxels=(0.25,))
+    npts[1, 0] = 1400
+    kw = dict(max_p_grid=8, max_o_grid=100, kernel_size=3, loc=1, coord_shift=(1.0, 1.0, 1.0),
+              voxel_size=(0.25,) * 3, grid_size=(8,) * 3)
+    assert not _no_k1_overflow(data, npts, kw)
+    keep_first = oracle_mod.gridify(data, npts, strict_reservoir=True, **kw)
+    try:
+        for seconds in (0, 31337, 999999):
+            oracle_mod.set_k1_seconds(seconds)
+            ref = _run(L.ref_gridify, data, npts, kw, seconds=seconds)
+            want = oracle_mod.gridify(data, npts, strict_reservoir=True, **kw)
+            for r, w, n in zip(ref, want, NAMES):
+                assert np.array_equal(r, w), (seconds, "Gridify", n)
+            assert not np.array_equal(want[0], keep_first[0])
+            ref = _run(L.ref_gridify_knn, data, npts, kw, seconds=seconds)
+            want = oracle_mod.gridify_knn(data, npts, **kw)
+            for r, w, n in zip(ref, want, NAMES):
+                if n != "cent":
+                    assert np.array_equal(r, w), (seconds, "GridifyKNN", n)
+    finally:
+        oracle_mod.set_k1_seconds(None)
+    for a, b in zip(oracle_mod.gridify(data, npts, strict_reservoir=True, **kw), keep_first):
+        assert np.array_equal(a, b)
+
+
 def _run_up(L, down, up, dn, un, O, P, vox, grid, seconds=4242):
     shift, voxel, g = np.ones(3, np.float32), np.full(3, vox, np.float32), np.full(3, grid, np.int32)
     nebidx, msk = np.empty((len(down), O, P), np.int32), np.empty((len(down), O, P), np.float32)
