@@ -698,7 +698,15 @@ int gridgcn_oracle_gridify_up(const float *downdata, const float *updata, const 
                     if (!in_grid(d, h, w, gridf)) continue;
                     int v = linear_index3(d, h, w, gridf);
                     int slot = counter[v]++; /* :157 atomicAdd */
-                    if (slot < P) bucket[(size_t)v * P + slot] = i_pt;
+                    if (slot < P) {
+                        bucket[(size_t)v * P + slot] = i_pt;
+                    } else if (g_k1_seconds >= 0) { /* :160-166, literal replay with a given tv_usec */
+                        xorwow_t st;
+                        uint64_t threadindex = ((uint64_t)b * (uint64_t)N + (uint64_t)i_pt) * (uint64_t)size + (uint64_t)t;
+                        xorwow_init(&st, (uint64_t)g_k1_seconds + threadindex);
+                        int insrtidx = (int)(ceilf(xorwow_uniform(&st) * (float)(slot + 1)) - 1.0f);
+                        if (insrtidx < P) bucket[(size_t)v * P + insrtidx] = i_pt;
+                    } /* else: keep-first */
                 }
             }
             const float *ud = updata + (size_t)b * O * DATA_NDIM;

@@ -218,6 +218,14 @@ def test_oracle_matches_reference_gridify_up_bodies(oracle_mod):
         assert np.array_equal(ref[1], want[1]), seed
         fits = count <= P
         assert fits.any() and np.array_equal(ref[0][fits], want[0][fits]), seed
+        # ... and with K5's reservoir replayed for the same tv_usec, every row
+        try:
+            oracle_mod.set_k1_seconds(4242)
+            replay = oracle_mod.gridify_up(down, up, dn, un, max_p_grid=P, **kw)
+        finally:
+            oracle_mod.set_k1_seconds(None)
+        assert np.array_equal(ref[0], replay[0]) and np.array_equal(ref[1], replay[1]), seed
+        assert (~fits).any() and not np.array_equal(replay[0], want[0]), seed
 
 
 @pytest.mark.gpu
