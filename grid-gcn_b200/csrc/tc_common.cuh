@@ -98,11 +98,41 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// plain arrive (count 1) by the calling thread
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// non-blocking phase test (polling loops that watch several barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// try_wait with a suspend-time hint: the warp SLEEPS in hardware until the phase completes (or ~1 ms pass)
+// instead of spinning -- r02b profile: with the default (short) time limit the waiting warps of a
+// warp-specialised kernel executed ~4000 polling instructions per 128-edge unit and starved the others.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a wrong descriptor must fail the launch (trap), never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 26); i++)
-        if (mbar_try_wait(bar, parity)) return;
-    __trap();
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+#pragma unroll 1
+    while (!mbar_try_wait_sleep(bar, parity))
+        if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s
 }
 
 // 1-D bulk copy global -> shared, completion counted on an mbarrier (TMA engine, SASS UBLKCP)
