@@ -24,8 +24,9 @@
 //       EF   warps 12-15  final epilogue (thread = channel x half): relu(F + b) * relu(G + b), max over K, store
 //       MS / MH / MA / MF0 / MF1   warps 16-20: one thread each issues the MMAs of stage 0 / the hidden stage /
 //            attention stage 1 / the last feature stage (one warp per 64-edge half) and commits their mbarriers
-//     Every hand-over is an mbarrier (thread arrivals from the epilogue warps, tcgen05.commit from the MMA
-//     threads); every resource has its own barrier ring (a wait on a barrier of a ring of a DIFFERENT depth can
+//     Every hand-over is an mbarrier (ONE arrival per epilogue warp -- every arrival wakes the warps sleeping on
+//     any barrier, r02f: 128 thread arrivals per hand-over made half of all executed instructions re-polls --,
+//     tcgen05.commit from the MMA threads); every resource has its own barrier ring (a wait on a barrier of a ring of a DIFFERENT depth can
 //     alias phases and deadlock).
 //   * Last stages transposed with M = 64: D^T[ch, edge]; the 64 edges [64h, 64h+64) of a unit go to TMEM lanes
 //     32q+16h .. +15 (cta_group::1 M = 64 layout, tools/m64_probe.cu; A and D must use the same lane half),
@@ -154,11 +155,11 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[kDX + 4 * kDA + 2 * kDI + 3 * kDF];
     __shared__ uint32_t tmem_base_s;
-    uint64_t *x0_full = bars;                                                    // G -> MS (128)
-    uint64_t *s0_done = x0_full + kDX, *e0_done = s0_done + kDA;                 // MS -> E0, G (1); E0 -> MH (128)
-    uint64_t *h_done = e0_done + kDA, *acc_free = h_done + kDA;                  // MH -> EH (1); EH -> MS (128)
-    uint64_t *eh_done = acc_free + kDA, *img_free = eh_done + kDI;               // EH -> MA, MF0, MF1 (128); MA + MF0 + MF1 -> E0 (3)
-    uint64_t *f_full = img_free + kDI, *g_full = f_full + kDF, *fg_free = g_full + kDF;  // MF0 + MF1 -> EF (2); MA -> EF (1); EF -> MA, MF (128)
+    uint64_t *x0_full = bars;                                                    // G -> MS (4: one arrival per warp)
+    uint64_t *s0_done = x0_full + kDX, *e0_done = s0_done + kDA;                 // MS -> E0, G (1); E0 -> MH (4: one arrival per warp)
+    uint64_t *h_done = e0_done + kDA, *acc_free = h_done + kDA;                  // MH -> EH (1); EH -> MS (4: one arrival per warp)
+    uint64_t *eh_done = acc_free + kDA, *img_free = eh_done + kDI;               // EH -> MA, MF0, MF1 (4: one arrival per warp); MA + MF0 + MF1 -> E0 (3)
+    uint64_t *f_full = img_free + kDI, *g_full = f_full + kDF, *fg_free = g_full + kDF;  // MF0 + MF1 -> EF (2); MA -> EF (1); EF -> MA, MF (4: one arrival per warp)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const ConvParams &c = p.c;
     const int C = c.Cout;
@@ -167,21 +168,21 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
     // ---- one-time set-up: TMEM, barriers, resident weight images ----
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 32) {
-        for (int i = 0; i < kDX; i++) tc::mbar_init(&x0_full[i], 128);
+        for (int i = 0; i < kDX; i++) tc::mbar_init(&x0_full[i], 4);
         for (int i = 0; i < kDA; i++) {
             tc::mbar_init(&s0_done[i], 1);
-            tc::mbar_init(&e0_done[i], 128);
+            tc::mbar_init(&e0_done[i], 4);
             tc::mbar_init(&h_done[i], 1);
-            tc::mbar_init(&acc_free[i], 128);
+            tc::mbar_init(&acc_free[i], 4);
         }
         for (int i = 0; i < kDI; i++) {
-            tc::mbar_init(&eh_done[i], 128);
+            tc::mbar_init(&eh_done[i], 4);
             tc::mbar_init(&img_free[i], 3);
         }
         for (int i = 0; i < kDF; i++) {
             tc::mbar_init(&f_full[i], 2);
             tc::mbar_init(&g_full[i], 1);
-            tc::mbar_init(&fg_free[i], 128);
+            tc::mbar_init(&fg_free[i], 4);
         }
         tc::mbar_init_fence();
     }
@@ -326,7 +327,8 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             *reinterpret_cast<float4 *>(x0 + 2 * kPanel) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<float4 *>(x0 + 3 * kPanel) = make_float4(lo[4], lo[5], lo[6], lo[7]);
             tc::fence_async_smem();
-            tc::mbar_arrive(&x0_full[x]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&x0_full[x]);
             // centre columns of the output rows
             if (r < cpt * 4) {
                 const unsigned center = (unsigned)(blockIdx.x + i * gridDim.x) * (unsigned)cpt + (unsigned)(r >> 2);
@@ -376,7 +378,8 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             tc::tmem_st_wait();
             tc::fence_async_smem();
             tc::fence_before_sync();
-            tc::mbar_arrive(&e0_done[a.slot]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&e0_done[a.slot]);
             a.next();
             d.next();
         }
@@ -396,14 +399,16 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             for (int c0 = 0; c0 < H1L; c0 += 16) tc::tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(v + c0));
             tc::tmem_ld_wait();
             tc::fence_before_sync();
-            tc::mbar_arrive(&acc_free[a.slot]);  // the whole front slot (xf and both accumulators) is dead now
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_free[a.slot]);  // the whole front slot (xf and both accumulators) is dead now
 #pragma unroll
             for (int cc = 0; cc < H1P; cc += 4) {
                 uint8_t *dst = img + (uint32_t)(cc >> 2) * kPanel;
                 relu_split_store4(v + cc, *reinterpret_cast<const float4 *>(bias_h + cc), dst, dst + L.xf_lo);
             }
             tc::fence_async_smem();
-            tc::mbar_arrive(&eh_done[d.slot]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&eh_done[d.slot]);
             a.next();
             d.next();
         }
@@ -460,7 +465,8 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
                     tc::tmem_ld16(taddr + 96u, ga);
                 } else {  // every TMEM read of this unit is done: the slot may be overwritten
                     tc::fence_before_sync();
-                    tc::mbar_arrive(&fg_free[f.slot]);
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&fg_free[f.slot]);
                 }
                 reduce16(fb, gb, c0 + 16);
                 tc::tmem_ld_wait();
