@@ -27,7 +27,7 @@ static int check_grid_args(int B, int N, int O, int P, int ks, const float *shif
     if (B < 0 || N < 0 || O < 1 || P < 1 || ks < 1 || !shift || !voxel || !grid)
         return GRIDGCN_EINVAL;
     if ((ks & 1) == 0) return GRIDGCN_EINVAL;  // even kernel: coor_indx_b_origin unset, gridify.cu:248
-    if (P > kMaxP || N >= (1 << 24)) return GRIDGCN_ELIMIT;
+    if (P > kMaxP || N >= (1 << 24) || (long long)B * O >= (1LL << 31)) return GRIDGCN_ELIMIT;  // 32-bit row arithmetic in the query kernels
     long long G = 1;
     for (int j = 0; j < 3; j++) {
         if (grid[j] < 1 || !(voxel[j] > 0.f)) return GRIDGCN_EINVAL;

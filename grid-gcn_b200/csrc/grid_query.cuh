@@ -79,12 +79,28 @@ __device__ __forceinline__ float4 center_row(const CloudTable &t, int o, int loc
     return c;
 }
 
-__device__ __forceinline__ void decode_lin(int lin, const GridParams &g, int &c2, int &c1, int &c0) {
-    int gxy = g.grid[0] * g.grid[1];
-    c2 = lin / gxy;
-    c1 = (lin - c2 * gxy) / g.grid[0];
-    c0 = lin - c2 * gxy - c1 * g.grid[0];
-}
+// Division by a loop-invariant divisor: m = ceil(2^32 / d) (d >= 2), umulhi over-estimates by at most one.
+struct FastDiv {
+    int d;
+    unsigned m;
+    __device__ __forceinline__ explicit FastDiv(int d_) : d(d_), m(d_ > 1 ? 0xFFFFFFFFu / (unsigned)d_ + 1u : 0u) {}
+    __device__ __forceinline__ int div(int n) const {  // 0 <= n < 2^31
+        if (d <= 1) return n;
+        int q = (int)__umulhi((unsigned)n, m);
+        if (q * d > n) q--;
+        return q;
+    }
+};
+struct LinDecoder {  // linear voxel index -> (c2, c1, c0), two divisions by grid constants
+    FastDiv gxy, gx;
+    __device__ __forceinline__ explicit LinDecoder(const GridParams &g) : gxy(g.grid[0] * g.grid[1]), gx(g.grid[0]) {}
+    __device__ __forceinline__ void operator()(int lin, int &c2, int &c1, int &c0) const {
+        c2 = gxy.div(lin);
+        const int rem = lin - c2 * gxy.d;
+        c1 = gx.div(rem);
+        c0 = rem - c1 * gx.d;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Gridify query (A.3): first min(P, total) ids in raster order d -> h -> w; beyond P the canonical rule
@@ -107,9 +123,11 @@ gridify_query_kernel(const float4 *__restrict__ data, GridParams g, const int *_
     const int P = g.P, O = g.O, ks = g.ks, S = ks * ks * ks, r = (ks - 1) / 2;
     const bool strict = (g.flags & GRIDGCN_FLAG_STRICT_RESERVOIR) != 0;
     const long long total_centers = (long long)g.B * O;
+    const FastDiv odiv(O);
+    const LinDecoder decode(g);
     for (long long ci = (long long)blockIdx.x * kQueryWarps + warp; ci < total_centers;
          ci += (long long)gridDim.x * kQueryWarps) {
-        const int b = (int)(ci / O), o = (int)(ci % O);
+        const int b = odiv.div((int)ci), o = (int)ci - b * O;  // B * O < 2^31 (host-checked)
         int *out_idx = nebidx + ci * P;
         float *out_msk = nebmsk + ci * P;
         if (o >= centnum[b]) {  // rows beyond actual_centnum keep the init values
@@ -123,7 +141,7 @@ gridify_query_kernel(const float4 *__restrict__ data, GridParams g, const int *_
         const CloudTable t = cloud_table(ws_base, L, b);
         const float4 *pts = data + (size_t)b * g.N;
         int c2, c1, c0;
-        decode_lin(t.cent_lin[o], g, c2, c1, c0);
+        decode(t.cent_lin[o], c2, c1, c0);
         // seed of candidate c: (int)(index_P * size + c + 1), evaluated in 32-bit int, widened (gridify.cu:260)
         const unsigned seed0 = (unsigned)ci * (unsigned)P * (unsigned)S;
         auto draw = [&](int c) {  // slot the reservoir assigns to candidate c >= P (may be >= P: dropped)
@@ -344,6 +362,114 @@ __device__ __forceinline__ void append_batch(TopP<CAP> &tp, const int *sorted, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast path of the GridifyKNN query (r02): shells 0 + 1 (the 27 voxels around the centre) hold at most CAP
+// candidates and no further shell is needed -- the common case (layer 0 of the seg8192 ladder: ~80 candidates
+// for P = 64).  The candidates are numbered in arrival order (centre voxel first, then the 26 others in loop
+// order, ascending ids inside a voxel) and sorted as 32-bit keys
+//        [ d^2 float bits, low log2(CAP) bits dropped | arrival number ]
+// through a bitonic network held in REGISTERS (element e = r * 32 + lane: strides >= 32 are register moves,
+// strides < 32 one SHFL + one predicated min/max) -- ~260 instructions instead of ~700 for the 64-bit keys in
+// shared memory.  The key orders exactly like (d^2, arrival number) -- the stable order of the reference's
+// strict-< insertion (gridifyknn.cu:288-298) -- unless two candidates agree in all the kept bits of d^2; such
+// a near tie is detected after the sort (adjacent keys with equal high bits) and the centre is handed to the
+// general path, which compares the full 64-bit keys.  Bit-exact by construction.
+// ------------------------------------------------------------------------------------------------
+template <int RR, int R>
+__device__ __forceinline__ void bitonic_regs(unsigned (&v)[R], int lane) {
+    constexpr int N = 32 * RR;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {  // partner in the same lane (k >= 64: the direction depends on the register only)
+#pragma unroll
+                for (int r = 0; r < RR; r++) {
+                    const int rp = r ^ (j >> 5);
+                    if (rp > r) {
+                        const bool asc = ((r * 32) & k) == 0;
+                        const unsigned lo = min(v[r], v[rp]), hi = max(v[r], v[rp]);
+                        v[r] = asc ? lo : hi;
+                        v[rp] = asc ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RR; r++) {
+                    const unsigned o = __shfl_xor_sync(kFull, v[r], j);
+                    const int e = r * 32 + lane;
+                    const bool keep_min = ((e & j) == 0) == ((e & k) == 0);
+                    v[r] = keep_min ? min(v[r], o) : max(v[r], o);
+                }
+            }
+        }
+    }
+}
+
+// Returns false when the centre needs the general path.  On success buf[0, found) holds the neighbour ids in
+// output order.  buf: 2 * CAP ints of this warp.
+template <int CAP>
+__device__ __forceinline__ bool knn_shell01_fast(const CloudTable &t, const GridParams &g, const float4 *pts, int c2,
+                                                 int c1, int c0, float ux, float uy, float uz, int fma, int P, int ks,
+                                                 int lane, int *buf, int &found) {
+    constexpr int R = CAP / 32;
+    constexpr unsigned SEQM = (unsigned)CAP - 1u;
+    // lane l looks up voxel tt: the centre voxel (shell 0, tt = 13) first, then the 26 of shell 1 in loop order
+    const int tt = lane == 0 ? 13 : (lane <= 13 ? lane - 1 : lane);
+    int s = 0, e = 0;
+    if (lane < 27) voxel_segment(t, g, tt % 3 - 1 + c2, (tt / 3) % 3 - 1 + c1, tt / 9 - 1 + c0, s, e);
+    int amount = min(P, e - s);
+    if (__shfl_sync(kFull, amount, 0) >= P && lane != 0) amount = 0;  // shell 0 alone fills the row (:304-305)
+    const int incl = warp_incl_scan(amount, lane);
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (total > CAP || (total < P && ks > 3)) return false;  // too many candidates / further shells needed
+    unsigned key[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        key[r] = 0xFFFFFFFFu;
+        if (r * 32 < total) {  // warp-uniform
+            const int f = r * 32 + lane;  // candidate f: register r of lane f % 32
+            int v = 0;                    // its voxel: the first lane whose inclusive prefix exceeds f
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int tpre = __shfl_sync(kFull, incl, v + st - 1);
+                if (tpre <= f) v += st;
+            }
+            v = min(v, 31);
+            const int v_incl = __shfl_sync(kFull, incl, v), v_amount = __shfl_sync(kFull, amount, v);
+            const int v_s = __shfl_sync(kFull, s, v);
+            if (f < total) {
+                const int id = t.sorted[v_s + (f - (v_incl - v_amount))];
+                const float4 q = __ldg(pts + id);
+                const float dst = dist2(ux, uy, uz, q.x, q.y, q.z, fma);
+                key[r] = (__float_as_uint(dst) & ~SEQM) | (unsigned)f;
+                buf[CAP + f] = id;
+            }
+        }
+    }
+    if (total <= 32) bitonic_regs<1>(key, lane);
+    else if (R >= 2 && total <= 64) bitonic_regs<(R >= 2 ? 2 : 1)>(key, lane);
+    else if (R >= 4 && total <= 128) bitonic_regs<(R >= 4 ? 4 : 1)>(key, lane);
+    else bitonic_regs<R>(key, lane);
+    // near ties: adjacent keys that agree in every kept bit of d^2
+    bool tie = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const unsigned nxt_reg = __shfl_sync(kFull, r + 1 < R ? key[r + 1 < R ? r + 1 : r] : 0xFFFFFFFFu, 0);
+        unsigned nk = __shfl_down_sync(kFull, key[r], 1);
+        if (lane == 31) nk = nxt_reg;
+        if (r * 32 + lane + 1 < total && ((key[r] ^ nk) & ~SEQM) == 0u) tie = true;
+    }
+    if (__any_sync(kFull, tie)) return false;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        if (r * 32 + lane < total) buf[r * 32 + lane] = buf[CAP + (key[r] & SEQM)];
+    __syncwarp();
+    found = min(total, P);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // GridifyKNN query (A.4): Chebyshev shells around the centre voxel, candidates = first min(P,cnt)
 // ids of every voxel in loop order w -> h -> d, stable sort by squared distance to the voxel
 // centre in the shifted frame, stop after the first shell with cumulative candidates >= P.
@@ -368,9 +494,11 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
     const int idbits = 32 - vbits;
     const int fma = (g.flags & GRIDGCN_FLAG_DIST_FMA) ? 1 : 0;
     const long long total_centers = (long long)g.B * O;
+    const FastDiv odiv(O);
+    const LinDecoder decode(g);
     for (long long ci = (long long)blockIdx.x * kQueryWarps + warp; ci < total_centers;
          ci += (long long)gridDim.x * kQueryWarps) {
-        const int b = (int)(ci / O), o = (int)(ci % O);
+        const int b = odiv.div((int)ci), o = (int)ci - b * O;  // B * O < 2^31 (host-checked)
         int *out_idx = nebidx + ci * P;
         float *out_msk = nebmsk + ci * P;
         if (o >= centnum[b]) {
@@ -384,11 +512,15 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
         const CloudTable t = cloud_table(ws_base, L, b);
         const float4 *pts = data + (size_t)b * g.N;
         int c2, c1, c0;
-        decode_lin(t.cent_lin[o], g, c2, c1, c0);
+        decode(t.cent_lin[o], c2, c1, c0);
         // gridifyknn.cu:253-255: (int + 0.5) * voxel evaluated in double, rounded to float
         const float ux = (float)(((double)c0 + 0.5) * (double)g.voxel[0]);
         const float uy = (float)(((double)c1 + 0.5) * (double)g.voxel[1]);
         const float uz = (float)(((double)c2 + 0.5) * (double)g.voxel[2]);
+        int found = 0;
+        int *ids = reinterpret_cast<int *>(s_keys[warp]);  // CAP 64-bit keys == 2 * CAP ints
+        if (!(ks >= 3 && knn_shell01_fast<CAP>(t, g, pts, c2, c1, c0, ux, uy, uz, fma, P, ks, lane, ids, found))) {
+        __syncwarp();
         TopP<CAP> tp{s_keys[warp], 0, (1u << idbits) - 1u, 0, false};
         int seq = 0, vbase = 0;
         auto key_of = [&](int id, int vorder) {
@@ -429,9 +561,8 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
         }
         tp.flush(P, lane);
         __syncwarp();
-        const int found = tp.fill;  // >= 1: the centre voxel is never empty
+        found = tp.fill;  // >= 1: the centre voxel is never empty
         // unpack the ids in place (low word of every key) so that weight_sum can index them
-        int *ids = reinterpret_cast<int *>(tp.keys);
         {
             int v0 = lane < found ? tp.id_of(lane) : 0, v1 = lane + 32 < found ? tp.id_of(lane + 32) : 0;
             int v2 = lane + 64 < found ? tp.id_of(lane + 64) : 0, v3 = lane + 96 < found ? tp.id_of(lane + 96) : 0;
@@ -442,6 +573,7 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
             if (lane + 96 < found) ids[lane + 96] = v3;
             __syncwarp();
         }
+        }  // general path
         const int pad = ids[0];
         for (int s = lane; s < P; s += 32) {
             out_idx[s] = s < found ? ids[s] : pad;  // :308-310, :317-321
@@ -469,9 +601,11 @@ gridify_up_query_kernel(const float4 *__restrict__ updata, const int *__restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = g.P, O = g.O, ks = g.ks, S = ks * ks * ks, r = (ks - 1) / 2;
     const long long total_rows = (long long)g.B * O;
+    const FastDiv odiv(O);
+    const LinDecoder decode(g);
     for (long long ci = (long long)blockIdx.x * kQueryWarps + warp; ci < total_rows;
          ci += (long long)gridDim.x * kQueryWarps) {
-        const int b = (int)(ci / O), o = (int)(ci % O);
+        const int b = odiv.div((int)ci), o = (int)ci - b * O;  // B * O < 2^31 (host-checked)
         int *out_idx = nebidx + ci * P;
         float *out_msk = nebmsk + ci * P;
         int lin = -1;
@@ -484,7 +618,7 @@ gridify_up_query_kernel(const float4 *__restrict__ updata, const int *__restrict
         if (lin >= 0) {
             const CloudTable t = cloud_table(ws_base, L, b);
             int c2, c1, c0;
-            decode_lin(lin, g, c2, c1, c0);
+            decode(lin, c2, c1, c0);
             int seq = 0;
             auto key_of = [&](int id, int) { return (unsigned long long)(unsigned)id; };
             for (int t0 = 0; t0 < S; t0 += 32) {
