@@ -164,6 +164,145 @@ def time_cpu(cfg, params, clouds, steps, warmup):
     return clouds * cfg.num_points / dt, dt, workers
 
 
+def _timed(torch, flush, fn, steps):
+    """Mean device time (ms) of fn over `steps` calls, L2 flushed before each, CUDA events on the current stream."""
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    return sum(s.elapsed_time(e) for s, e in evs) / max(steps, 1)
+
+
+def measure_encoder(torch, flush, peaks, cfg, B, precision, steps=5, graph=False, seed=0):
+    """One BASELINE configuration measured the way the headline is: device-resident points/s of the encoder
+    ladder, per-operator times (query = voxel-hash build + neighbour gather; gridconv = the per-edge MLP
+    kernels) and the two roofline fractions."""
+    from gridgcn_b200 import stack, synth
+    params = stack.init_params(cfg, seed=seed)
+    dev = flush.device
+    pool = min(B, 8)
+    base, _ = synth.make_batch(pool, cfg.num_points, seed0=1000, voxels=cfg.voxels)
+    data = torch.from_numpy(np.tile(base, ((B + pool - 1) // pool, 1, 1))[:B].copy()).to(dev)
+    npts = torch.full((B, 1), cfg.num_points, dtype=torch.int32, device=dev)
+    enc = stack.GridGcnEncoder(cfg, params, dev, precision=precision)
+    for _ in range(3):
+        enc(data, npts)
+    out = {"clouds": B, "points_per_cloud": cfg.num_points, "layers": len(cfg.layers),
+           "K": [l.max_p_grid for l in cfg.layers], "O": [l.max_o_grid for l in cfg.layers],
+           "query": cfg.query, "precision": precision}
+    ms = _timed(torch, flush, lambda: enc(data, npts), steps)
+    out["ms_per_step"] = ms
+    out["points_per_s"] = B * cfg.num_points / (ms * 1e-3)
+    if graph:
+        replay = stack.capture_graph(enc, data, npts)
+        replay()
+        gms = _timed(torch, flush, replay, steps)
+        out["cuda_graph"] = {"ms_per_step": gms, "points_per_s": B * cfg.num_points / (gms * 1e-3)}
+    enc(data, npts, keep_trace=True)
+    tr = enc.trace
+    qf = stack.query_fn(cfg)
+    q_ms, c_ms = [], []
+    for i, (l, conv) in enumerate(zip(cfg.layers, enc.convs)):
+        loc_in = data if i == 0 else tr[i - 1]["cent"]
+        num_in = npts if i == 0 else tr[i - 1]["actual_centnum"]
+        tin = data if i == 0 else tr[i - 1]["table"]
+        kwl = dict(max_o_grid=l.max_o_grid, max_p_grid=l.max_p_grid, kernel_size=l.kernel_size, stride=1,
+                   coord_shift=cfg.coord_shift, voxel_size=[l.voxel_size] * 3, grid_size=[l.grid_size] * 3, loc=cfg.loc)
+        fq = lambda: qf(loc_in, num_in, **kwl)  # noqa: E731
+        fc = lambda: conv(tin, tr[i]["nebidx"], tr[i]["cent"], tr[i]["centmsk"])  # noqa: E731
+        for _ in range(2):
+            fq(); fc()
+        q_ms.append(_timed(torch, flush, fq, steps))
+        c_ms.append(_timed(torch, flush, fc, steps))
+    macs = layer_macs(params)
+    flops = [2 * l.max_o_grid * l.max_p_grid * m for l, m in zip(cfg.layers, macs)]
+    l0 = cfg.layers[0]
+    q_gbs = B * gridify_bytes(cfg.num_points, l0.max_o_grid, l0.max_p_grid) / (q_ms[0] * 1e-3) / 1e9
+    dom = int(np.argmax(c_ms))
+    tf = B * flops[dom] / (c_ms[dom] * 1e-3) / 1e12
+    tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    out["breakdown_ms"] = {"gather": q_ms, "mlp": c_ms, "gather_total": sum(q_ms), "mlp_total": sum(c_ms),
+                           "gather_share": sum(q_ms) / (sum(q_ms) + sum(c_ms))}
+    out["roofline_hbm"] = {"kernel": "%s layer 0 (build + query)" % cfg.query, "achieved_gbs": q_gbs,
+                           "frac": q_gbs / peaks["hbm_gbs"]}
+    out["roofline_tensor"] = {"kernel": "gridconv layer %d" % dom, "algorithmic_tflops": tf, "frac": tf / tensor_peak}
+    return out
+
+
+def measure_seg_graph(torch, flush, B, precision, steps=5):
+    """BASELINE config 3: the shipped ScanNet-8192 graph (3 Gridify + GridConv encoder layers, 3 BallKNN + GridConv
+    decoder layers, head) through stack.GridGcnSeg at the shipped batch."""
+    from gridgcn_b200 import stack, synth
+    cfg, up = stack.seg8192_shipped(), stack.UpCfg()
+    params = stack.init_seg_params(cfg, up, seed=0)
+    dev = flush.device
+    pool = min(B, 8)
+    base, _ = synth.make_batch(pool, cfg.num_points, seed0=2000, voxels=cfg.voxels)
+    data = torch.from_numpy(np.tile(base, ((B + pool - 1) // pool, 1, 1))[:B].copy()).to(dev)
+    npts = torch.full((B, 1), cfg.num_points, dtype=torch.int32, device=dev)
+    net = stack.GridGcnSeg(cfg, up, params, dev, precision=precision)
+    for _ in range(3):
+        net(data, npts)
+    ms = _timed(torch, flush, lambda: net(data, npts), steps)
+    enc_ms = _timed(torch, flush, lambda: net.enc(data, npts), steps)
+    replay = stack.capture_graph(net, data, npts)
+    replay()
+    gms = _timed(torch, flush, replay, steps)
+    return {"clouds": B, "points_per_cloud": cfg.num_points, "graph": "encoder (Gridify, strict reservoir) + decoder "
+            "(BallKNN k=5) + head, 21 classes", "precision": precision, "ms_per_step": ms,
+            "points_per_s": B * cfg.num_points / (ms * 1e-3), "encoder_ms": enc_ms, "decoder_head_ms": ms - enc_ms,
+            "cuda_graph": {"ms_per_step": gms, "points_per_s": B * cfg.num_points / (gms * 1e-3)}}
+
+
+def measure_train_step(torch, dist, dev, world, B=3, steps=4):
+    """BASELINE config 4: one data-parallel TRAINING step of the seg81920 ladder, B clouds per GPU: forward
+    (index operators = this library's kernels; training-mode block on torch ops, train.py), backward, ONE flat
+    NCCL all-reduce of the gradient bucket, update.  Every rank takes part; times are MAX over ranks."""
+    from gridgcn_b200 import stack, synth, train, shard
+    cfg = stack.seg81920_shipped("gridify")
+    params = stack.init_params(cfg, seed=0)
+    model = train.GridGcnClassifier(cfg, params, num_classes=21).to(dev)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    base, _ = synth.make_batch(1, cfg.num_points, seed0=3000 + (dist.get_rank() if world > 1 else 0), voxels=cfg.voxels)
+    data = torch.from_numpy(np.tile(base, (B, 1, 1)).copy()).to(dev)
+    npts = torch.full((B, 1), cfg.num_points, dtype=torch.int32, device=dev)
+    labels = torch.arange(B, device=dev) % 21
+    plist = [p for p in model.parameters()]
+    grad_bytes = sum(p.numel() for p in plist) * 4
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    t_step, t_ar = [], []
+    for it in range(steps + 2):
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        loss = torch.nn.functional.cross_entropy(model(data, npts), labels)
+        loss.backward()
+        e1.record()
+        shard.allreduce_gradients(plist)
+        e2.record()
+        opt.step()
+        e3.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            t_step.append(e0.elapsed_time(e3))
+            t_ar.append(e1.elapsed_time(e2))
+    step_ms, ar_ms = shard.max_over_ranks([sum(t_step) / len(t_step), sum(t_ar) / len(t_ar)], device=dev)
+    return {"workload": "seg81920 ladder, %d clouds per GPU, training step (torch autograd block behind the CUDA index "
+                        "operators)" % B, "n_gpus": world, "step_ms": step_ms, "allreduce_ms": ar_ms,
+            "allreduce_share": ar_ms / step_ms, "gradient_bytes": grad_bytes,
+            "points_per_s": world * B * cfg.num_points / (step_ms * 1e-3),
+            "collective": "one flat NCCL all-reduce (SUM, then / world)" if world > 1 else "none (single rank)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,6 +325,8 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay the forward as ONE CUDA graph (stack.capture_graph) for the device-resident `value`; "
                          "pays off when the step is launch bound (small batches)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the `configs` block (the other BASELINE configurations measured in the same run)")
     ap.add_argument("--cpu-clouds", type=int, default=0,
                     help="clouds per CPU-baseline step (default: one per host core, at most 64)")
     args = ap.parse_args()
@@ -228,12 +369,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        # every step is a bounded sample of the workload (cpu_clouds clouds, ~0.5 s of CPU work at 3e5 points/s), so
+        # the driver's K and W are honoured as given
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
         val, dt, cores = time_cpu(cfg, params, args.cpu_clouds, steps, warmup)
+        ref_config = dict(config, clouds_per_gpu=args.cpu_clouds, precision="fp32 (C / numpy port of the reference algorithm)",
+                          cuda_graph=False, parallelism="host threads, one cloud each",
+                          l2="n/a (CPU)", sample_of="the b200 arm's workload at clouds_per_gpu=%d, precision=%s"
+                                                    % (args.batch, args.precision))
         line = {"impl": "reference", "metric": metric_name,
                 "value": val, "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": ref_config,
                 "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
                                  "sample": "%d clouds of %d points per step, %d steps (oracle C port: OpenMP over "
                                            "clouds for the grid ops, one thread per cloud for the numpy GridConv); "
@@ -356,6 +503,15 @@ def main():
     value = points_job * args.steps / (ms_total * 1e-3)
     e2e_value = points_job * args.steps / (ms_e2e * 1e-3)
 
+    # BASELINE config 4 (training step with the gradient all-reduce): every rank takes part
+    train_cfg = None
+    if not args.no_configs and args.workload == "seg8192":
+        try:
+            train_cfg = measure_train_step(torch, dist, dev, world)
+        except Exception as e:  # never lose the headline line to a side measurement
+            train_cfg = {"error": "%s: %s" % (type(e).__name__, e)}
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -442,6 +598,29 @@ def main():
                     "ms_per_launch": q_ms,
                     "algorithmic_bytes": q_bytes, "peak_source": peaks["_source"]}
 
+    # ------------------------------------------------------------------ the other BASELINE configurations
+    configs_block = None
+    if not args.no_configs and args.workload == "seg8192" and args.K == 64 and args.query == "gridifyknn":
+        configs_block = {}
+        def side(name, fn):
+            try:
+                configs_block[name] = fn()
+            except Exception as e:
+                configs_block[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
+        side("config2_cls1024_B32_K32", lambda: measure_encoder(torch, flush, peaks, stack.cls1024_4layer(32), 32,
+                                                                 args.precision, graph=True))
+        side("config3_seg8192_shipped_graph_B12", lambda: measure_seg_graph(torch, flush, 12, args.precision))
+        side("config4_seg81920_B3", lambda: measure_encoder(torch, flush, peaks, stack.seg81920_shipped("gridify"), 3,
+                                                             args.precision, graph=True))
+        for k in (16, 32, 128):
+            side("config5_seg8192_K%d_B%d" % (k, B), lambda k=k: measure_encoder(torch, flush, peaks, stack.seg8192_4layer(k),
+                                                                                 B, args.precision, steps=3))
+        configs_block["config5_seg8192_K64_B%d" % B] = {
+            "note": "the headline line itself", "ms_per_step": ms_total / args.steps, "points_per_s": value,
+            "breakdown_ms": {"gather": query_ms, "mlp": conv_ms, "gather_total": sum(query_ms), "mlp_total": sum(conv_ms),
+                             "gather_share": sum(query_ms) / (sum(query_ms) + sum(conv_ms))}}
+        configs_block["config4_train_step"] = train_cfg
     cpu_val, cpu_dt, cores = time_cpu(cfg, params, args.cpu_clouds, 2, 1)
     line = {"metric": metric_name,
             "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
@@ -462,6 +641,8 @@ def main():
             "breakdown_ms": {"query": query_ms, "gridconv": conv_ms,
                              "note": "each operator timed alone, L2 flushed before every call"},
             "clocks": sampler.summary()}
+    if configs_block is not None:
+        line["configs"] = configs_block
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

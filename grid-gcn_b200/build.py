@@ -36,7 +36,7 @@ def _stale():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) + \
         [os.path.join(_HERE, "..", "include", "gridgcn_b200.h")]
     return any(os.path.getmtime(p) > t for p in deps)
 

@@ -11,13 +11,15 @@ namespace gg {
 constexpr int kMaxGridVoxels = 262144;
 constexpr size_t kBuildSmemLimit = 200 * 1024;
 
-static int sm_count() {
-    static int n = 0;
+static int sm_count() {  // of the CURRENT device (the library may serve several devices of one process)
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cached = dev >= 0 && dev < 64;
+    int n = cached ? cache[dev].load(std::memory_order_relaxed) : 0;
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (cached) cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
 }

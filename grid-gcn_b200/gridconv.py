@@ -179,6 +179,9 @@ class GridConv:
         return out
 
 
+_SHIM_CACHE = {}  # sub_g_update(): (id(layer), device, pre_relu, precision) -> (layer, GridConv)
+
+
 def features_nco(out_table):
     """(B, O, 4+C) [cent | feats] -> (B, C, O), the layout sub_g_update returns (BN=True path)."""
     return out_table[:, :, 4:].transpose(1, 2)
@@ -208,8 +211,12 @@ def sub_g_update(centers_xyz, center_den, neighbors, has_feats, center_masks, ne
     cent = torch.cat([centers_xyz.transpose(1, 2), center_den.transpose(1, 2)], dim=2).contiguous()
     if center_masks is None:
         center_masks = torch.ones((B, O), dtype=torch.float32, device=neighbors.device)
-    conv = GridConv(layer, neighbors.device, pre_relu=pre_relu, precision=precision)
-    return features_nco(conv(table, idx, cent, center_masks))
+    key = (id(layer), str(neighbors.device), bool(pre_relu), precision)
+    conv = _SHIM_CACHE.get(key)
+    if conv is None or conv[0] is not layer:  # BN folding + weight packing happen once per layer, not per call
+        conv = (layer, GridConv(layer, neighbors.device, pre_relu=pre_relu, precision=precision))
+        _SHIM_CACHE[key] = conv
+    return features_nco(conv[1](table, idx, cent, center_masks))
 
 
 def init_up_layer(rng, cd, cu, pt_mlp_lst, attfdim, center_dim, out_dim):
@@ -301,3 +308,20 @@ class SegHead:
     def __call__(self, feats):
         x = rowmlp(feats, None, *self.l1)
         return rowmlp(x, None, *self.l2, relu_out=False)
+
+
+class ClsHead:
+    """get_cls_head up to the class scores (classification/models/ggcn_models_g.py:25-35, eval mode: BatchNorm
+    folded, Dropout = identity): FC 512 -> BN -> ReLU -> FC 256 -> BN -> ReLU -> FC num_classes; ``probs=True``
+    adds the softmax SoftmaxOutput applies at inference.  Runs on the row-MLP kernel (gridgcn_rowmlp_fwd)."""
+
+    def __init__(self, head, device):
+        self.l1 = _folded(head[0], device)
+        self.l2 = _folded(head[1], device)
+        self.l3 = _folded(head[2], device, bn=False)
+
+    def __call__(self, feats, probs=False):
+        x = rowmlp(feats, None, *self.l1)
+        x = rowmlp(x, None, *self.l2)
+        x = rowmlp(x, None, *self.l3, relu_out=False)
+        return torch.softmax(x, dim=-1) if probs else x

@@ -75,14 +75,15 @@ def _gridify(fn_name, data, actual_numpoints, max_p_grid, max_o_grid, kernel_siz
 
 
 def Gridify(data, actual_numpoints, *, max_p_grid=0, max_o_grid=0, kernel_size=0, stride=0, loc=0,
-            coord_shift=(), voxel_size=(), grid_size=(), strict_reservoir=False):
-    """Voxel hash + centre sampling + first-P neighbour gather (canonical RVS, keep-first).
+            coord_shift=(), voxel_size=(), grid_size=(), strict_reservoir=True):
+    """Voxel hash + centre sampling + neighbour gather of the kernel^3 voxels around every centre.
 
     Returns ``(nebidx i32 [B,O,P], nebidxmsk f32 [B,O,P], cent f32 [B,O,4], centmsk f32 [B,O],
     actual_centnum i32 [B,1])`` exactly as gridify-inl.h:190-196,207-212 infer them.
-    ``strict_reservoir`` (extension): when a neighbourhood holds more than max_p_grid candidates, reproduce
-    the reference's reservoir over the later ones (gridify.cu:259-270, deterministic seed) instead of
-    keeping the first max_p_grid in raster order."""
+    When a neighbourhood holds more than max_p_grid candidates the reference keeps a reservoir sample of them
+    whose seed does not depend on the schedule (gridify.cu:259-270); ``strict_reservoir=True`` (the default:
+    what the reference outputs) reproduces it exactly, ``strict_reservoir=False`` is the faster keep-first rule
+    (the first max_p_grid candidates in raster order; biased against the +z side of the neighbourhood)."""
     return _gridify("gridgcn_gridify_fwd", data, actual_numpoints, max_p_grid, max_o_grid,
                     kernel_size, stride, loc, coord_shift, voxel_size, grid_size,
                     4 if strict_reservoir else 0)

@@ -42,9 +42,15 @@ def max_over_ranks(values, device=None):
 
 def allreduce_gradients(params):
     """Training-time collective: ONE all-reduce over a flat bucket of every gradient (mean)."""
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    params = list(params)
+    if not params or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
+    # the bucket layout must be the same on every rank: a parameter without a gradient on THIS rank (unused
+    # branch, zero_grad(set_to_none=True)) contributes zeros instead of being skipped
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat /= dist.get_world_size()

@@ -204,7 +204,13 @@ class UpCfg:
     center_dim: Sequence[int] = (128,)        # up_center_dim
     out_dim: Sequence[int] = (128,)           # up_gcn_outDim
     attfdim: int = 10                         # up_attfdim
-    neigh_fetch: str = "ballknn"              # up_neigh_fetch: True -> BallKNN; "gridifyup" -> GridifyUp
+    neigh_fetch: str = "ballknn"              # up_neigh_fetch: True -> BallKNN ("knn" when real_knn is set:
+                                              # contrib.KNN, ggcn_models_g.py:74-83); False -> "gridifyup"
+    # per decoder level (ggcn_models_g.py:204-210 index these with the decoder step i); () = the encoder ladder
+    # reversed, which is what the shipped configs contain (configs.yaml:99-102)
+    voxel_size_lst: Sequence[float] = ()      # up_voxel_size_lst (BallKNN radius = voxel * kernel * 1.7 / 2)
+    grid_size_lst: Sequence[int] = ()         # up_grid_size_lst  (GridifyUp)
+    max_o_grid_lst: Sequence[int] = ()        # up_max_o_grid_lst (GridifyUp; must equal the up level's row count)
 
 
 def init_seg_params(cfg: StackCfg, up: UpCfg, seed=0, num_classes=21):
@@ -254,16 +260,26 @@ class GridGcnSeg:
         for i, dec in enumerate(self.dec):
             lvl_dn, lvl_up = nl - i, nl - i - 1
             down, centers = cents[lvl_dn], cents[lvl_up]
-            l = cfg.layers[lvl_up]  # the up level's own grid: up_voxel_size_lst is the encoder ladder reversed
+            l = cfg.layers[lvl_up]  # default ladder: up_voxel_size_lst is the encoder ladder reversed
+            voxel = float(up.voxel_size_lst[i]) if len(up.voxel_size_lst) else l.voxel_size
+            grid = int(up.grid_size_lst[i]) if len(up.grid_size_lst) else l.grid_size
+            if len(up.max_o_grid_lst) and int(up.max_o_grid_lst[i]) != centers.shape[1]:
+                raise ValueError("up_max_o_grid_lst[%d] = %d but the up level has %d rows"
+                                 % (i, up.max_o_grid_lst[i], centers.shape[1]))
             if up.neigh_fetch == "ballknn":
-                radius = l.voxel_size * up.kernel_size * 1.7 / 2
+                radius = voxel * up.kernel_size * 1.7 / 2  # ggcn_models_g.py:204
                 nebidx = ops.contrib.BallKNN(centers[:, :, :3].contiguous(), down[:, :, :3].contiguous(),
                                              nums[lvl_dn], nums[lvl_up], k=up.max_p_grid, radius=radius)
-            else:
+            elif up.neigh_fetch == "knn":  # real_knn (:74-83); ThreeNN (k == 3) is the same exact search
+                nebidx = ops.contrib.KNN(centers[:, :, :3].contiguous(), down[:, :, :3].contiguous(),
+                                         nums[lvl_dn], nums[lvl_up], k=up.max_p_grid)
+            elif up.neigh_fetch == "gridifyup":
                 nebidx, _ = ops.GridifyUp(down, centers, nums[lvl_dn], nums[lvl_up],
                                           max_p_grid=up.max_p_grid, max_o_grid=centers.shape[1],
                                           kernel_size=up.kernel_size, coord_shift=cfg.coord_shift,
-                                          voxel_size=[l.voxel_size] * 3, grid_size=[l.grid_size] * 3)
+                                          voxel_size=[voxel] * 3, grid_size=[grid] * 3)
+            else:
+                raise ValueError("UpCfg.neigh_fetch must be ballknn, knn or gridifyup, not %r" % (up.neigh_fetch,))
             mask = masks[lvl_up] if i != len(self.dec) - 1 else None  # ggcn_models_g.py:224
             f_last = dec(f_last, nebidx, centers, tables[lvl_up], mask)
             if keep_trace:
@@ -274,6 +290,38 @@ class GridGcnSeg:
 
 
 # ---------------------------------------------------------------------------------------------------
+# Classification graph (get_symbol_cls_ggcn, classification/models/ggcn_models_g.py:37-111) + head (:25-35)
+# ---------------------------------------------------------------------------------------------------
+def init_cls_params(cfg: StackCfg, seed=0, num_classes=40):
+    """Encoder layers of ``cfg`` (the classification flavour when cfg.localfdim / att_full say so) and the
+    FC 512 - 256 - num_classes head on the flattened features of the last layer."""
+    rng = np.random.default_rng(seed)
+    enc = init_params(cfg, seed)
+    width = cfg.layers[-1].pt_mlp_lst[-1] * cfg.layers[-1].max_o_grid  # fully_connected(flatten=True)
+    head = [gridconv.init_stage(rng, width, 512), gridconv.init_stage(rng, 512, 256),
+            gridconv.init_stage(rng, 256, num_classes)]
+    return dict(enc=enc, head=head)
+
+
+class GridGcnCls:
+    """``scores = net(data, actual_numpoints)``: (B,N,4) -> (B,num_classes).  The encoder loop of
+    get_symbol_cls_ggcn (Gridify -> batch_take_g -> sub_g_update per layer, :66-106; group_all False as
+    shipped) and get_cls_head (:25-35) in eval mode.  ``probs=True`` returns what SoftmaxOutput does."""
+
+    def __init__(self, cfg: StackCfg, params, device, precision="fp32"):
+        self.cfg = cfg
+        self.enc = GridGcnEncoder(cfg, params["enc"], device, precision=precision)
+        self.head = gridconv.ClsHead(params["head"], device)
+
+    def __call__(self, data, actual_numpoints, probs=False, keep_trace=False):
+        table = self.enc(data, actual_numpoints, keep_trace=keep_trace)
+        B, O, _ = table.shape
+        feats = table[:, :, 4:]                      # (B, O, C); the reference flattens (B, C, O)
+        feats = feats.reshape(B, -1) if O == 1 else feats.transpose(1, 2).reshape(B, -1)
+        return self.head(feats.contiguous(), probs=probs)
+
+
+# ---------------------------------------------------------------------------------------------------
 # Reference-compatible configuration: the keys of segmentation/configs/configs.yaml
 # ---------------------------------------------------------------------------------------------------
 def from_reference_config(conf, query="gridify"):
@@ -281,30 +329,41 @@ def from_reference_config(conf, query="gridify"):
     (segmentation/configs/configs.yaml:54-111): voxel_size_lst, grid_size_lst, max_p_grid_lst,
     max_o_grid_lst, kernel_size_lst, stride_lst, pt_ele_dim, lidar_coord, loc_within, attfdim, relu,
     num_points, up_max_p_grid_lst, up_kernel_size_lst, up_pt_ele_dim, up_center_dim, up_gcn_outDim,
-    up_attfdim, up_neigh_fetch.  Only what the fused kernels implement is accepted (cubic voxels/grids,
-    aggtype gcn, max pooling, localfdim 0, no context MLP, empty gcn_outDim, concat centre integration)."""
+    up_attfdim, up_neigh_fetch, real_knn, up_voxel_size_lst, up_grid_size_lst, up_max_o_grid_lst; and the
+    classification keys att_ele_dim, att_full, localfdim (classification/configs/configs.yaml:44-68).  Only what the
+    fused kernels implement is accepted -- cubic voxels/grids, aggtype gcn, max pooling, no context MLP, empty
+    gcn_outDim / elevation, concat centre integration, use_bn t -- everything else raises NotImplementedError
+    instead of being ignored."""
     def cubic(v):
         v = list(v)
         if len(set(v)) != 1:
             raise NotImplementedError("anisotropic voxel / grid sizes are not supported by StackCfg: %r" % (v,))
         return v[0]
     for key, ok in (("aggtype", ("gcn",)), ("agg", ("max_pooling", "max")), ("up_aggtype", ("gcn",)),
-                    ("up_agg", ("max_pooling", "max")), ("up_center_inte", ("concat",))):
+                    ("up_agg", ("max_pooling", "max")), ("up_center_inte", ("concat",)), ("use_bn", ("t", True))):
         if conf.get(key, ok[0]) not in ok:
             raise NotImplementedError("%s=%r is not supported" % (key, conf.get(key)))
-    if conf.get("localfdim", 0) != 0 or conf.get("cntxt_mlp_lst") or conf.get("att_full"):
-        raise NotImplementedError("localfdim / cntxt_mlp_lst / att_full variants are not supported")
-    if any(len(d) for d in conf.get("gcn_outDim", [])):
-        raise NotImplementedError("encoder gcn_outDim MLPs are not supported")
+    def empty(v):  # None, [], [[], [], []]
+        return not v or all(not x for x in v)
+    for key in ("cntxt_mlp_lst", "up_cntxt_mlp_lst", "elevation", "gcn_outDim"):
+        if not empty(conf.get(key)):
+            raise NotImplementedError("%s=%r is not supported by the fused kernels" % (key, conf.get(key)))
+    if conf.get("up_att_full") or conf.get("group_all") or conf.get("fps") or conf.get("reverse_index"):
+        raise NotImplementedError("up_att_full / group_all / fps / reverse_index are not supported")
+    cls_block = bool(conf.get("att_ele_dim")) or bool(conf.get("att_full")) or conf.get("localfdim", 0) != 0
+    if cls_block and conf.get("up_max_p_grid_lst"):
+        raise NotImplementedError("the classification block (att_ele_dim / att_full / localfdim) has no decoder")
     n = len(conf["max_o_grid_lst"])
+    att = conf.get("att_ele_dim") or [()] * n
     layers = [LayerCfg(float(cubic(conf["voxel_size_lst"][i])), int(cubic(conf["grid_size_lst"][i])),
                        int(conf["max_o_grid_lst"][i]), int(conf["max_p_grid_lst"][i]),
                        int(conf["kernel_size_lst"][i]), list(conf["pt_ele_dim"][i]),
-                       int(conf.get("stride_lst", [1] * n)[i])) for i in range(n)]
+                       int(conf.get("stride_lst", [1] * n)[i]), att_ele_lst=tuple(att[i])) for i in range(n)]
     cfg = StackCfg(str(conf.get("save_model_prefix", "reference_config")), int(conf["num_points"]), layers,
                    coord_shift=tuple(float(x) for x in conf.get("lidar_coord", (1.0, 1.0, 1.0))),
                    loc=1 if conf.get("loc_within", True) else 0, attfdim=int(conf.get("attfdim", 10)),
-                   pre_relu=bool(conf.get("relu", True)), query=query)
+                   pre_relu=bool(conf.get("relu", True)), query=query,
+                   att_full=str(conf.get("att_full") or ""), localfdim=int(conf.get("localfdim", 0)))
     up = None
     if conf.get("up_max_p_grid_lst"):
         def same(key):
@@ -312,10 +371,21 @@ def from_reference_config(conf, query="gridify"):
             if any(list(x) != list(v[0]) for x in v) if isinstance(v[0], (list, tuple)) else len(set(v)) != 1:
                 raise NotImplementedError("%s must be the same on every decoder level" % key)
             return v[0]
+        nu = len(conf["up_max_p_grid_lst"])
+        if nu != n:
+            raise NotImplementedError("one decoder level per encoder level is expected (%d vs %d)" % (nu, n))
+        fetch = "gridifyup" if not conf.get("up_neigh_fetch", True) else ("knn" if conf.get("real_knn") else "ballknn")
+        levels = [conf["num_points"]] + [int(o) for o in conf["max_o_grid_lst"]]  # rows of level 0 .. n
+        up_o = [int(o) for o in conf.get("up_max_o_grid_lst", [])]
+        if up_o and up_o != [levels[n - 1 - i] for i in range(n)]:
+            raise NotImplementedError("up_max_o_grid_lst %r does not match the encoder levels %r" % (up_o, levels))
         up = UpCfg(max_p_grid=int(same("up_max_p_grid_lst")), kernel_size=int(same("up_kernel_size_lst")),
                    pt_mlp_lst=tuple(same("up_pt_ele_dim")), center_dim=tuple(same("up_center_dim")),
                    out_dim=tuple(same("up_gcn_outDim")), attfdim=int(conf.get("up_attfdim", 10)),
-                   neigh_fetch="ballknn" if conf.get("up_neigh_fetch", True) else "gridifyup")
+                   neigh_fetch=fetch,
+                   voxel_size_lst=tuple(float(cubic(v)) for v in conf.get("up_voxel_size_lst", [])),
+                   grid_size_lst=tuple(int(cubic(v)) for v in conf.get("up_grid_size_lst", [])),
+                   max_o_grid_lst=tuple(up_o))
     return cfg, up
 
 

@@ -107,9 +107,11 @@ def _gridify(fn, data, actual_numpoints, max_p_grid, max_o_grid, kernel_size, lo
 
 def gridify(data, actual_numpoints, *, max_p_grid, max_o_grid, kernel_size, stride=1, loc=0,
             coord_shift=(0, 0, 0), voxel_size=(1, 1, 1), grid_size=(1, 1, 1),
-            strict_reservoir=False):
+            strict_reservoir=True):
     """Gridify (gridify-inl.h:99-128, gridify.cu:102-291).  ``stride`` is accepted and ignored,
-    as in the reference (gridify.cu:112, never read)."""
+    as in the reference (gridify.cu:112, never read).  ``strict_reservoir`` (default, like the product
+    operator): K2's schedule-independent reservoir over the candidates beyond max_p_grid (gridify.cu:259-270);
+    False = the canonical keep-first rule."""
     fn = lib().gridgcn_oracle_gridify
     fn.restype = ctypes.c_int
     return _gridify(fn, data, actual_numpoints, max_p_grid, max_o_grid, kernel_size, loc,

@@ -83,7 +83,7 @@ def test_gridify_strict_reservoir_matches_oracle(gg, cuda_dev, oracle_mod, name,
     d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
     want = oracle_mod.gridify(data, npts, strict_reservoir=True, **kw)
     _check5(gg.Gridify(d, n, stride=1, strict_reservoir=True, **kw), want, name + "/Gridify strict")
-    keep_first = oracle_mod.gridify(data, npts, **kw)
+    keep_first = oracle_mod.gridify(data, npts, strict_reservoir=False, **kw)
     if name not in ("cfg1_P64_k3", "P128_k7_cls"):  # the others overflow: the two rules really differ
         assert not np.array_equal(want[0], keep_first[0])
     # integer-valued weights other than 1 (what later layers see: neighbour counts)
@@ -242,6 +242,26 @@ def _rel_err(got, want):
     return float(np.max(np.abs(got - want) / (np.abs(want) + rms)))
 
 
+def _strict_err(got, want):
+    """The elementwise reading of "1e-3 rel fp32" (VERDICT r01 item 7): relative error wherever
+    |want| >= 1e-2 rms(want), absolute error in units of rms below that.  Returns (rel_big, abs_small_over_rms)."""
+    got, want = got.astype(np.float64), want.astype(np.float64)
+    rms = float(np.sqrt(np.mean(want ** 2))) + 1e-30
+    big = np.abs(want) >= 1e-2 * rms
+    d = np.abs(got - want)
+    rel_big = float(np.max(d[big] / np.abs(want[big]))) if big.any() else 0.0
+    abs_small = float(np.max(d[~big])) / rms if (~big).any() else 0.0
+    return rel_big, abs_small
+
+
+def _assert_feats(got, want, what):
+    """Both tolerances, both numbers in the message: rms-floored 1e-3 and the strict elementwise one."""
+    loose = _rel_err(got, want)
+    rel_big, abs_small = _strict_err(got, want)
+    assert loose <= 1e-3 and rel_big <= 1e-3 and abs_small <= 1e-3, \
+        "%s: rms-floored %.3g, strict relative %.3g, small-entry absolute/rms %.3g" % (what, loose, rel_big, abs_small)
+
+
 CONV_CASES = [
     # name, B, N, O, K, Cin, mlp
     ("l0_K8", 2, 256, 32, 8, 0, [16, 32]),
@@ -282,8 +302,7 @@ def test_gridconv_matches_oracle(gg, cuda_dev, oracle_mod, name, B, N, O, K, Cin
     got = conv(_t(table, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(centmsk, cuda_dev))
     got = got.cpu().numpy()
     assert np.array_equal(got[..., :4], want[..., :4])  # centre columns are copied
-    err = _rel_err(got[..., 4:], want[..., 4:])
-    assert err <= 1e-3, "%s/%s: rel err %.3g" % (name, precision, err)  # north_star: 1e-3 rel fp32
+    _assert_feats(got[..., 4:], want[..., 4:], "%s/%s" % (name, precision))  # north_star: 1e-3 rel fp32
     assert np.abs(want[..., 4:]).max() > 0  # the comparison is not vacuous
 
 
@@ -395,7 +414,7 @@ def test_golden_fixtures_on_gpu(gg, cuda_dev):
     kw1 = dict(max_p_grid=64, max_o_grid=1024, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
                voxel_size=(0.05,) * 3, grid_size=(40,) * 3)
     z = np.load(os.path.join(GOLDEN, "gridify_cfg1.npz"))
-    _check5(gg.Gridify(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), **kw1),
+    _check5(gg.Gridify(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), strict_reservoir=False, **kw1),
             [z[n] for n in NAMES], "golden gridify_cfg1")
     z = np.load(os.path.join(GOLDEN, "gridifyknn_cfg1.npz"))
     _check5(gg.GridifyKNN(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev),
@@ -404,7 +423,7 @@ def test_golden_fixtures_on_gpu(gg, cuda_dev):
     z = np.load(os.path.join(GOLDEN, "gridify_overflow.npz"))
     kwo = dict(max_p_grid=8, max_o_grid=100, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
                voxel_size=(0.25,) * 3, grid_size=(8,) * 3)
-    _check5(gg.Gridify(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), **kwo),
+    _check5(gg.Gridify(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), strict_reservoir=False, **kwo),
             [z[n] for n in NAMES], "golden overflow")
     _check5(gg.GridifyKNN(_t(z["data"], cuda_dev), _t(z["npts"], cuda_dev), **kwo),
             [z["knn_" + n] for n in NAMES], "golden overflow knn")
@@ -444,11 +463,11 @@ def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod, precision):
     from oracle import gridconv_oracle
     from gridgcn_b200 import stack
     cases = [(stack.tiny(8), 3), (stack.cls1024_4layer(32), 2), (stack.seg8192_4layer(16), 1),
-             (stack.seg8192_shipped(), 1)]
-    if precision == "tf32x3":  # the product precision also covers the headline shape, the K sweep of
-        cases += [(stack.seg8192_4layer(64), 1),             # BASELINE config 5 and the config-4 shape
-                  (stack.seg8192_4layer(32, "gridify"), 1), (stack.seg8192_4layer(128), 1),
-                  (stack.seg81920_shipped(), 1)]
+             (stack.seg8192_shipped(), 1), (stack.seg8192_4layer(64), 2)]  # the headline shape in BOTH precisions
+    if precision == "tf32x3":  # the product precision also covers BASELINE's batch of config 2 (B = 32), the K sweep
+        cases += [(stack.cls1024_4layer(32), 32),             # of config 5 and the config-4 shape (B = 3 per GPU)
+                  (stack.seg81920_shipped(), 3),
+                  (stack.seg8192_4layer(32, "gridify"), 1), (stack.seg8192_4layer(128), 1)]
         cas = stack.seg8192_4layer(32, "occaware_knn")  # coverage-aware sampling feeding the GridConv ladder
         cas.cas_seed = 11
         cases += [(cas, 2), (stack.seg8192_shipped("occaware"), 1)]
@@ -471,8 +490,7 @@ def test_full_stack_matches_oracle(gg, cuda_dev, oracle_mod, precision):
             _check5([tr[n] for n in NAMES], want, "%s layer %d" % (cfg.name, i))
             table = gridconv_oracle.gridconv_layer(table, want[0], want[2], want[3], p,
                                                    pre_relu=cfg.pre_relu)
-            err = _rel_err(tr["table"].cpu().numpy()[..., 4:], table[..., 4:])
-            assert err <= 1e-3, "%s layer %d: rel err %.3g" % (cfg.name, i, err)
+            _assert_feats(tr["table"].cpu().numpy()[..., 4:], table[..., 4:], "%s B=%d layer %d" % (cfg.name, B, i))
             loc, num = want[2], want[4]
         assert out.shape == (B, cfg.layers[-1].max_o_grid, 4 + cfg.layers[-1].pt_mlp_lst[-1])
 
@@ -578,15 +596,22 @@ def test_decoder_layer_matches_oracle(gg, cuda_dev, precision):
             assert _rel_err(got[..., 4:], want[..., 4:]) <= 1e-3, (B, Nd, O, cd, cu, mask is None)
 
 
-def test_seg_graph_encoder_decoder_head(gg, cuda_dev, oracle_mod):
+@pytest.mark.parametrize("B,fetch", [(2, "ballknn"), (12, "ballknn"), (2, "knn"), (2, "gridifyup")],
+                         ids=["B2_ballknn", "B12_baseline_batch", "B2_real_knn", "B2_gridifyup"])
+def test_seg_graph_encoder_decoder_head(gg, cuda_dev, oracle_mod, B, fetch):
     """BASELINE config 3: the shipped ScanNet-8192 graph, encoder + decoder + head, against the oracle
-    chain: BallKNN indices bit-exact at every decoder level, logits within 1e-3."""
+    chain (B = 12 is the shipped batch, configs.yaml:69): neighbour indices bit-exact at every decoder level
+    (BallKNN; KNN for real_knn, ggcn_models_g.py:74-83; GridifyUp for up_neigh_fetch False), logits within 1e-3.
+    The encoder query is Gridify in its default = the reference's reservoir."""
     from oracle import gridconv_oracle
     from gridgcn_b200 import stack
-    cfg, up = stack.seg8192_shipped(), stack.UpCfg()
+    cfg = stack.seg8192_shipped()
+    up = stack.UpCfg(neigh_fetch=fetch, voxel_size_lst=(0.4, 0.133333, 0.05), grid_size_lst=(5, 15, 40),
+                     max_o_grid_lst=(256, 1024, 8192))
     params = stack.init_seg_params(cfg, up, seed=2)
-    B = 2
     data, npts = synth.make_batch(B, cfg.num_points, seed0=400, voxels=cfg.voxels)
+    if fetch == "ballknn" and B == 2:  # duplicates: exact distance ties through the whole graph (real loaders sample with replacement)
+        data[1, 4096:] = data[1, :4096]
     net = stack.GridGcnSeg(cfg, up, params, cuda_dev)
     logits = net(_t(data, cuda_dev), _t(npts, cuda_dev), keep_trace=True).cpu().numpy()
     # oracle chain
@@ -601,17 +626,59 @@ def test_seg_graph_encoder_decoder_head(gg, cuda_dev, oracle_mod):
         tables.append(table); cents.append(cent); nums.append(num); masks.append(centmsk)
         loc = cent
     f_last, nl = tables[-1], len(cfg.layers)
+    misses = 0
     for i, p in enumerate(params["dec"]):
         dn, upl = nl - i, nl - i - 1
-        l = cfg.layers[upl]
-        radius = l.voxel_size * up.kernel_size * 1.7 / 2
-        nebidx = oracle_mod.ball_knn(cents[upl][:, :, :3], cents[dn][:, :, :3], nums[dn], nums[upl],
-                                     k=up.max_p_grid, radius=radius)
+        if fetch == "ballknn":
+            nebidx = oracle_mod.ball_knn(cents[upl][:, :, :3], cents[dn][:, :, :3], nums[dn], nums[upl],
+                                         k=up.max_p_grid, radius=up.voxel_size_lst[i] * up.kernel_size * 1.7 / 2)
+        elif fetch == "knn":
+            nebidx = oracle_mod.knn(cents[upl][:, :, :3], cents[dn][:, :, :3], nums[dn], nums[upl], k=up.max_p_grid)
+        else:
+            nebidx, _ = oracle_mod.gridify_up(cents[dn], cents[upl], nums[dn], nums[upl], max_p_grid=up.max_p_grid,
+                                              max_o_grid=cents[upl].shape[1], kernel_size=up.kernel_size,
+                                              coord_shift=cfg.coord_shift, voxel_size=(up.voxel_size_lst[i],) * 3,
+                                              grid_size=(up.grid_size_lst[i],) * 3)
+        misses += int((nebidx < 0).sum())
         assert np.array_equal(net.trace[i]["nebidx"].cpu().numpy(), nebidx), "decoder level %d indices" % i
         mask = masks[upl] if i != nl - 1 else None
         f_last = gridconv_oracle.gridconv_up_layer(f_last, nebidx, cents[upl], tables[upl], mask, p)
-        err = _rel_err(net.trace[i]["table"].cpu().numpy()[..., 4:], f_last[..., 4:])
-        assert err <= 1e-3, "decoder level %d: rel err %.3g" % (i, err)
+        _assert_feats(net.trace[i]["table"].cpu().numpy()[..., 4:], f_last[..., 4:], "decoder level %d" % i)
+    if fetch == "ballknn":
+        assert misses > 0  # the take()-clip path of BallKNN misses (-1) is exercised through the full decoder
     want = gridconv_oracle.seg_head(f_last[..., 4:], params["head"])
     assert logits.shape == (B, cfg.num_points, 21)
-    assert _rel_err(logits, want) <= 1e-3
+    _assert_feats(logits, want, "logits")
+
+
+@pytest.mark.parametrize("B", [2, 32], ids=["B2", "B32_baseline_batch"])
+def test_classification_graph_with_head(gg, cuda_dev, oracle_mod, B):
+    """BASELINE config 2's model family: the shipped ModelNet40 ladder + FC 512-256-40 head
+    (classification/models/ggcn_models_g.py:25-35, :37-111) from the reference's YAML keys, at the batch
+    BASELINE names (32) -- class scores within 1e-3 of the oracle chain."""
+    from oracle import gridconv_oracle
+    from gridgcn_b200 import stack, gridconv
+    cfg = stack.cls1024_shipped()
+    params = stack.init_cls_params(cfg, seed=6)
+    data, npts = synth.make_batch(B, cfg.num_points, seed0=500, voxels=cfg.voxels)
+    net = stack.GridGcnCls(cfg, params, cuda_dev, precision="fp32")
+    scores = net(_t(data, cuda_dev), _t(npts, cuda_dev)).cpu().numpy()
+    probs = net(_t(data, cuda_dev), _t(npts, cuda_dev), probs=True).cpu().numpy()
+    table, loc, num = data, data, npts
+    for l, p in zip(cfg.layers, params["enc"]):
+        want = oracle_mod.gridify(loc, num, max_p_grid=l.max_p_grid, max_o_grid=l.max_o_grid,
+                                  kernel_size=l.kernel_size, loc=cfg.loc, coord_shift=cfg.coord_shift,
+                                  voxel_size=(l.voxel_size,) * 3, grid_size=(l.grid_size,) * 3)
+        table = gridconv_oracle.gridconv_layer(table, want[0], want[2], want[3], p, pre_relu=cfg.pre_relu)
+        loc, num = want[2], want[4]
+    x = table[:, 0, 4:].astype(np.float32)
+    for j, st in enumerate(params["head"]):
+        if j < 2:
+            w, b = gridconv.fold_bn(st["weight"], st["bias"], st["gamma"], st["beta"], st["moving_mean"], st["moving_var"])
+            x = np.maximum(x @ w.T + b, 0).astype(np.float32)
+        else:
+            x = (x @ np.asarray(st["weight"], np.float32).reshape(len(st["bias"]), -1).T + st["bias"]).astype(np.float32)
+    assert scores.shape == (B, 40)
+    _assert_feats(scores, x, "class scores")
+    e = np.exp(x - x.max(-1, keepdims=True))
+    assert np.allclose(probs, e / e.sum(-1, keepdims=True), rtol=2e-3, atol=1e-6)

@@ -82,6 +82,44 @@ def test_reference_yaml_keys_are_understood():
         stack.from_reference_config(dict(max_o_grid_lst=[8], voxel_size_lst=[[0.1, 0.2, 0.1]],
                                          grid_size_lst=[[4, 4, 4]], max_p_grid_lst=[4], kernel_size_lst=[3],
                                          pt_ele_dim=[[8]], num_points=16))
+    # the decoder ladder is READ, not assumed: radius / GridifyUp grid come from the up_* lists
+    assert tuple(up.voxel_size_lst) == (0.4, 0.133333, 0.05) and tuple(up.grid_size_lst) == (5, 15, 40)
+    assert tuple(up.max_o_grid_lst) == (256, 1024, 8192)
+    import yaml
+    with open(os.path.join(here, "golden", "seg8192_reference_keys.yaml")) as f:
+        conf = yaml.safe_load(f)
+    knn_cfg, knn_up = stack.from_reference_config(dict(conf, real_knn=True))
+    assert knn_up.neigh_fetch == "knn"
+    assert stack.from_reference_config(dict(conf, up_neigh_fetch=False))[1].neigh_fetch == "gridifyup"
+    for bad in (dict(up_max_o_grid_lst=[256, 1024, 4096]), dict(up_att_full="next"), dict(elevation=[1]),
+                dict(up_cntxt_mlp_lst=[[8], [8], [8]]), dict(use_bn="f"), dict(up_center_inte="add"),
+                dict(aggtype="agg_gcn"), dict(gcn_outDim=[[64], [], []])):
+        with pytest.raises(NotImplementedError):  # unsupported keys are refused, never silently ignored
+            stack.from_reference_config(dict(conf, **bad))
+    # the classification keys (classification/configs/configs.yaml:44-68)
+    cls_conf = dict(num_points=1024, voxel_size_lst=[[0.05] * 3, [0.25] * 3, [2.0] * 3],
+                    grid_size_lst=[[40] * 3, [8] * 3, [1] * 3], lidar_coord=[1.0, 1.0, 1.0],
+                    max_p_grid_lst=[64, 64, 128], max_o_grid_lst=[1024, 128, 1], kernel_size_lst=[7, 3, 1],
+                    stride_lst=[1, 1, 1], aggtype="gcn", localfdim=3, attfdim=4, elevation=[],
+                    pt_ele_dim=[[64, 64, 128], [128, 128, 256], [256, 256, 512]],
+                    att_ele_dim=[[64, 128, 128], [128, 256, 256], [256, 512, 512]], cntxt_mlp_lst=[[], [], []],
+                    gcn_outDim=[[], [], []], relu=True, agg="max_pooling", att_full="next", use_bn="t",
+                    group_all=False, loc_within=True)
+    ccfg, cup = stack.from_reference_config(cls_conf)
+    ship = stack.cls1024_shipped()
+    assert cup is None and (ccfg.att_full, ccfg.localfdim, ccfg.attfdim) == ("next", 3, 4)
+    assert [(l.voxel_size, l.grid_size, l.max_o_grid, l.max_p_grid, l.kernel_size, list(l.pt_mlp_lst),
+             list(l.att_ele_lst)) for l in ccfg.layers] == \
+           [(l.voxel_size, l.grid_size, l.max_o_grid, l.max_p_grid, l.kernel_size, list(l.pt_mlp_lst),
+             list(l.att_ele_lst)) for l in ship.layers]
+    cref = "/root/reference/classification/configs/configs.yaml"
+    if os.path.exists(cref):
+        with open(cref) as f:
+            rc = yaml.safe_load(f)
+        rc.setdefault("num_points", 1024)
+        assert [l.max_o_grid for l in stack.from_reference_config(rc)[0].layers] == [1024, 128, 1]
+    head = stack.init_cls_params(ccfg, seed=0)["head"]
+    assert [st["weight"].shape[0] for st in head] == [512, 256, 40] and head[0]["weight"].reshape(512, -1).shape[1] == 512
 
 
 def test_cas_state_table_is_current():

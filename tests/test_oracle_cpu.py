@@ -39,7 +39,7 @@ def test_gridify_oracle_vs_twin(oracle_mod, name, N, B, kind, kw):
     data, npts = synth.make_batch(B, N, seed0=11, kind=kind, voxels=(kw["voxel_size"][0],))
     npts[-1, 0] = N - 37  # ragged: the last cloud has fewer valid points
     kw = dict(kw, coord_shift=(1.0, 1.0, 1.0))
-    _same(oracle_mod.gridify(data, npts, **kw), np_twin.gridify(data, npts, **kw), name + "/gridify")
+    _same(oracle_mod.gridify(data, npts, strict_reservoir=False, **kw), np_twin.gridify(data, npts, **kw), name + "/gridify")  # the twin implements the keep-first rule
     _same(oracle_mod.gridify_knn(data, npts, **kw), np_twin.gridify_knn(data, npts, **kw), name + "/knn")
 
 
@@ -87,13 +87,13 @@ def test_strict_reservoir_is_a_reservoir(oracle_mod):
     data, npts = synth.make_batch(1, 2048, seed0=2, kind="ball", voxels=(0.25,))
     kw = dict(max_p_grid=16, max_o_grid=64, kernel_size=3, loc=1, coord_shift=(1, 1, 1),
               voxel_size=(0.25,) * 3, grid_size=(8,) * 3)
-    keep = oracle_mod.gridify(data, npts, **kw)
+    keep = oracle_mod.gridify(data, npts, strict_reservoir=False, **kw)
     strict = oracle_mod.gridify(data, npts, strict_reservoir=True, **kw)
     for k in (1, 3, 4):
         assert np.array_equal(keep[k], strict[k])
     assert not np.array_equal(keep[0], strict[0])  # overflow regime: the reservoir replaced ids
     big = dict(kw, max_p_grid=128)
-    k2 = oracle_mod.gridify(data[:, :200], np.full((1, 1), 200, np.int32), **big)
+    k2 = oracle_mod.gridify(data[:, :200], np.full((1, 1), 200, np.int32), strict_reservoir=False, **big)
     s2 = oracle_mod.gridify(data[:, :200], np.full((1, 1), 200, np.int32), strict_reservoir=True, **big)
     if (k2[1].sum(-1) < 128).all():
         _same(k2, s2, "no overflow")
@@ -258,3 +258,77 @@ def test_occaware_golden(oracle_mod):
     got = oracle_mod.gridify_occaware(z["data"], z["npts"], seed=2026, **CAS_KW)
     for g, n in zip(got, ("nebidx", "nebidxmsk", "cent", "centmsk", "actual_centnum")):
         assert np.array_equal(g, z[n]), n
+
+
+# ------------------------------------------------------------------------------------------------
+# Third-party-algorithm pin of the GridConv oracle's building blocks.  MXNet 1.5 cannot be installed here,
+# so Convolution(1x1) / BatchNorm(eval, eps 1e-3, fix_gamma False) / Pooling(max) / take(mode clip) -- the MXNet
+# operators utils/ops.py:78-93,149-158 and gcn_module_g_att.py:57-59 call -- are checked against another
+# vendor's LIBRARY implementation of the same published operators (torch.nn.functional), not against a second
+# hand-written restatement.
+# ------------------------------------------------------------------------------------------------
+def test_gridconv_oracle_blocks_against_torch_library_ops():
+    import torch
+    import torch.nn.functional as TF
+    from oracle import gridconv_oracle as go
+    from gridgcn_b200 import gridconv
+    rng = np.random.default_rng(12)
+    B, Cin, Cout, O, P = 3, 10, 16, 7, 5
+    st = gridconv.init_stage(rng, Cin, Cout)
+    x = rng.normal(size=(B, Cin, O, P)).astype(np.float32)
+    got = go._conv_bn_relu(x, st)
+    w = torch.from_numpy(np.asarray(st["weight"], np.float32).reshape(Cout, Cin, 1, 1))
+    y = TF.conv2d(torch.from_numpy(x), w, torch.from_numpy(st["bias"]))
+    y = TF.batch_norm(y, torch.from_numpy(st["moving_mean"]), torch.from_numpy(st["moving_var"]),
+                      torch.from_numpy(st["gamma"]), torch.from_numpy(st["beta"]), training=False, eps=1e-3)
+    want = TF.relu(y).numpy()
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+    # the folded form the kernels consume (gridconv.fold_bn) is the same function
+    fw, fb = gridconv.fold_bn(st["weight"], st["bias"], st["gamma"], st["beta"], st["moving_mean"], st["moving_var"])
+    folded = np.maximum(np.einsum("oc,bcnp->bonp", fw, x) + fb[None, :, None, None], 0)
+    assert np.allclose(folded, want, rtol=1e-5, atol=1e-5)
+    # 1-D stage of the decoder / head (mlp1d_c, utils/ops.py:141-147,236-242)
+    st1 = gridconv.init_stage(rng, Cin, Cout)
+    x1 = rng.normal(size=(B, O, Cin)).astype(np.float32)
+    y1 = TF.conv1d(torch.from_numpy(x1).transpose(1, 2), torch.from_numpy(np.asarray(st1["weight"], np.float32).reshape(Cout, Cin, 1)),
+                   torch.from_numpy(st1["bias"]))
+    y1 = TF.relu(TF.batch_norm(y1, torch.from_numpy(st1["moving_mean"]), torch.from_numpy(st1["moving_var"]),
+                               torch.from_numpy(st1["gamma"]), torch.from_numpy(st1["beta"]), training=False, eps=1e-3))
+    assert np.allclose(go._conv1d_bn_relu(x1.transpose(0, 2, 1), st1), y1.numpy(), rtol=1e-5, atol=1e-6)  # (B, C, O) layout
+    # max pooling over the P slots (Pooling kernel (1, P), :57-59) and take(mode="clip") after the batch offset
+    pooled = TF.max_pool2d(torch.from_numpy(got), kernel_size=(1, P)).numpy()[..., 0]
+    assert np.array_equal(pooled, got.max(axis=3))
+    data = rng.normal(size=(B, 11, 6)).astype(np.float32)
+    idx = rng.integers(-1, 11, size=(B, O, P)).astype(np.int32)  # -1 = BallKNN miss
+    flat = torch.from_numpy(data.reshape(B * 11, 6))
+    gi = torch.from_numpy(idx.astype(np.int64)) + (torch.arange(B) * 11)[:, None, None]
+    want_take = flat[gi.clamp(0, B * 11 - 1)].numpy()
+    assert np.array_equal(go.batch_take_g(data, idx), want_take)
+    # one whole layer: the oracle against a torch-library composition of the same graph
+    layer = gridconv.init_layer(np.random.default_rng(3), 6, [8, 12], 10)
+    table = rng.uniform(-1, 1, size=(B, 11, 4 + 6)).astype(np.float32)
+    nidx = rng.integers(0, 11, size=(B, O, P)).astype(np.int32)
+    cent = rng.uniform(-1, 1, size=(B, O, 4)).astype(np.float32)
+    msk = (rng.uniform(size=(B, O)) > 0.3).astype(np.float32)
+    out = go.gridconv_layer(table, nidx, cent, msk, layer)
+
+    def cbr(t, stg):
+        wt = torch.from_numpy(np.asarray(stg["weight"], np.float32).reshape(len(stg["bias"]), -1, 1, 1))
+        t = TF.conv2d(t, wt, torch.from_numpy(stg["bias"]))
+        return TF.relu(TF.batch_norm(t, torch.from_numpy(stg["moving_mean"]), torch.from_numpy(stg["moving_var"]),
+                                     torch.from_numpy(stg["gamma"]), torch.from_numpy(stg["beta"]), training=False, eps=1e-3))
+    nb = torch.from_numpy(go.batch_take_g(table, nidx)).permute(0, 3, 1, 2)           # (B, 4+C, O, P)
+    cxyz = torch.from_numpy(cent[:, :, :3]).permute(0, 2, 1)[:, :, :, None].expand(B, 3, O, P)
+    geo = nb[:, :3] - cxyz
+    dist = geo.pow(2).sum(1, keepdim=True).sqrt()
+    att = torch.cat([dist, geo, cxyz, nb[:, :3]], dim=1)                              # attfdim 10 (:209-222)
+    f = nb[:, 4:]
+    for stg in layer["feat"]:
+        f = cbr(f, stg)
+    a = att
+    for stg in layer["att"]:
+        a = cbr(a, stg)
+    pooled = TF.max_pool2d(f * a, kernel_size=(1, P))[..., 0]                          # (B, C, O)
+    feats = (TF.relu(pooled) * torch.from_numpy(msk)[:, None, :]).permute(0, 2, 1).numpy()
+    assert np.array_equal(out[..., :4], cent)
+    assert np.allclose(out[..., 4:], feats, rtol=1e-4, atol=1e-5)
