@@ -46,6 +46,8 @@ SIGNATURES = {
     "gridgcn_ball_knn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "gridgcn_rowmlp_fwd": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp,
                                 ctypes.c_longlong, _vp]),
+    "gridgcn_rowmlp_tc_fwd": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp,
+                                   ctypes.c_longlong, _vp]),
     "gridgcn_debug_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "gridgcn_debug_curand_first_uniform": (_i, [_vp, _i, _vp, _vp, _vp]),
     "gridgcn_debug_phase_buffer": (None, [_vp]),

@@ -244,8 +244,9 @@ def _folded(st, device, bn=True):
     return torch.from_numpy(w).to(device).contiguous(), torch.from_numpy(b).to(device).contiguous()
 
 
-def rowmlp(in1, in2, w, b, *, relu_in=False, relu_out=True, row_scale=None, out=None, out_col=0, cent=None):
-    """out[..., out_col:out_col+Cout] = act(W act_in([in1 | in2]) + b) * row_scale   (C-ABI gridgcn_rowmlp_fwd).
+def rowmlp(in1, in2, w, b, *, relu_in=False, relu_out=True, row_scale=None, out=None, out_col=0, cent=None, tc=False):
+    """out[..., out_col:out_col+Cout] = act(W act_in([in1 | in2]) + b) * row_scale   (C-ABI gridgcn_rowmlp_fwd;
+    ``tc=True``: gridgcn_rowmlp_tc_fwd, the tf32x3 tensor-core GEMM).
     in1 / in2: (..., C) views whose last dim is contiguous and whose rows are equally strided."""
     L = _lib.lib()
     rows = int(np.prod(in1.shape[:-1]))
@@ -258,14 +259,15 @@ def rowmlp(in1, in2, w, b, *, relu_in=False, relu_out=True, row_scale=None, out=
         out = torch.empty(tuple(in1.shape[:-1]) + (out_col + cout,), dtype=torch.float32, device=in1.device)
     ldo = out.stride(-2)
     with torch.cuda.device(in1.device):
-        rc = L.gridgcn_rowmlp_fwd(in1.data_ptr(), ld1, c1, p2, ld2, c2, w.data_ptr(), b.data_ptr(), cout,
+        fn = L.gridgcn_rowmlp_tc_fwd if tc else L.gridgcn_rowmlp_fwd
+        rc = fn(in1.data_ptr(), ld1, c1, p2, ld2, c2, w.data_ptr(), b.data_ptr(), cout,
                                   1 if relu_in else 0, 1 if relu_out else 0,
                                   row_scale.data_ptr() if row_scale is not None else None,
                                   out.data_ptr() + 4 * out_col, ldo,
                                   cent.data_ptr() if cent is not None else None,
                                   out.data_ptr() if cent is not None else None, rows,
                                   torch.cuda.current_stream(in1.device).cuda_stream)
-    _lib.check(rc, "gridgcn_rowmlp_fwd")
+    _lib.check(rc, "gridgcn_rowmlp_tc_fwd" if tc else "gridgcn_rowmlp_fwd")
     return out
 
 
@@ -280,6 +282,7 @@ class GridConvUp:
         self.center = [_folded(st, self.device) for st in layer["center"]]
         self.update = [_folded(st, self.device) for st in layer["update"]]
         self.pre_relu = bool(pre_relu)
+        self.tc = precision != "fp32"  # per-centre stages on the tensor cores too (exact fp32 FMA for "fp32")
         self.cout = int(layer["update"][-1]["weight"].shape[0]) if layer["update"] else None
 
     def __call__(self, f_last, nebidx, cent_up, f_this, centmsk=None):
@@ -288,12 +291,12 @@ class GridConvUp:
         agg = self.core(f_last, nebidx, cent_up, ones)[:, :, 4:]          # (B, O, C) strided view
         cf = f_this
         for w, b in self.center:
-            cf = rowmlp(cf, None, w, b)
+            cf = rowmlp(cf, None, w, b, tc=self.tc)
         x, x2 = cf, agg
         for i, (w, b) in enumerate(self.update):
             last = i + 1 == len(self.update)
             x = rowmlp(x, x2, w, b, relu_in=self.pre_relu and i == 0, row_scale=centmsk if last else None,
-                       out_col=4 if last else 0, cent=cent_up.contiguous() if last else None)
+                       out_col=4 if last else 0, cent=cent_up.contiguous() if last else None, tc=self.tc)
             x2 = None
         return x
 
@@ -301,13 +304,14 @@ class GridConvUp:
 class SegHead:
     """get_seg_head up to the logits (ggcn_models_g.py:30-36, eval mode)."""
 
-    def __init__(self, head, device):
+    def __init__(self, head, device, precision="fp32"):
         self.l1 = _folded(head[0], device)
         self.l2 = _folded(head[1], device, bn=False)
+        self.tc = precision != "fp32"
 
     def __call__(self, feats):
-        x = rowmlp(feats, None, *self.l1)
-        return rowmlp(x, None, *self.l2, relu_out=False)
+        x = rowmlp(feats, None, *self.l1, tc=self.tc)
+        return rowmlp(x, None, *self.l2, relu_out=False, tc=self.tc)
 
 
 class ClsHead:
@@ -315,13 +319,14 @@ class ClsHead:
     folded, Dropout = identity): FC 512 -> BN -> ReLU -> FC 256 -> BN -> ReLU -> FC num_classes; ``probs=True``
     adds the softmax SoftmaxOutput applies at inference.  Runs on the row-MLP kernel (gridgcn_rowmlp_fwd)."""
 
-    def __init__(self, head, device):
+    def __init__(self, head, device, precision="fp32"):
         self.l1 = _folded(head[0], device)
         self.l2 = _folded(head[1], device)
         self.l3 = _folded(head[2], device, bn=False)
+        self.tc = precision != "fp32"
 
     def __call__(self, feats, probs=False):
-        x = rowmlp(feats, None, *self.l1)
-        x = rowmlp(x, None, *self.l2)
-        x = rowmlp(x, None, *self.l3, relu_out=False)
+        x = rowmlp(feats, None, *self.l1, tc=self.tc)
+        x = rowmlp(x, None, *self.l2, tc=self.tc)
+        x = rowmlp(x, None, *self.l3, relu_out=False, tc=self.tc)
         return torch.softmax(x, dim=-1) if probs else x

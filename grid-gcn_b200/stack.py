@@ -243,7 +243,7 @@ class GridGcnSeg:
         self.enc = GridGcnEncoder(cfg, params["enc"], device, precision=precision)
         self.dec = [gridconv.GridConvUp(p, device, pre_relu=cfg.pre_relu, precision=precision)
                     for p in params["dec"]]
-        self.head = gridconv.SegHead(params["head"], device)
+        self.head = gridconv.SegHead(params["head"], device, precision=precision)
         self.trace = []
 
     def __call__(self, data, actual_numpoints, keep_trace=False):
@@ -311,7 +311,7 @@ class GridGcnCls:
     def __init__(self, cfg: StackCfg, params, device, precision="fp32"):
         self.cfg = cfg
         self.enc = GridGcnEncoder(cfg, params["enc"], device, precision=precision)
-        self.head = gridconv.ClsHead(params["head"], device)
+        self.head = gridconv.ClsHead(params["head"], device, precision=precision)
 
     def __call__(self, data, actual_numpoints, probs=False, keep_trace=False):
         table = self.enc(data, actual_numpoints, keep_trace=keep_trace)

@@ -217,6 +217,14 @@ int gridgcn_rowmlp_fwd(const float *in1, int ld1, int c1, const float *in2, int 
                        const float *row_scale, float *out, int ld_out, const float *cent,
                        float *out_table, long long rows, void *stream);
 
+/* The same operator on the tensor cores (tcgen05 kind::tf32, 3-pass hi/lo split: fp32-class accuracy, ~1e-6),
+ * a persistent warp-specialised GEMM (csrc/rowgemm_tc.cu).  Views it cannot take (pointers / row strides / widths
+ * not multiples of 16 bytes, cout > 256) run on the CUDA-core kernel above. */
+int gridgcn_rowmlp_tc_fwd(const float *in1, int ld1, int c1, const float *in2, int ld2, int c2,
+                          const float *weight, const float *bias, int cout, int relu_in, int relu_out,
+                          const float *row_scale, float *out, int ld_out, const float *cent,
+                          float *out_table, long long rows, void *stream);
+
 /* Self-test of the tcgen05 primitives (not an operator): D[128,N] = A[128,K] * B[N,K]^T on one CTA,
  * kind::tf32, nsplit 1 (plain) or 3 (error-compensated).  N % 16 == 0, N <= 256, K % 8 == 0. */
 int gridgcn_debug_tc_gemm(const float *A, const float *B, float *D, int N, int K, int nsplit,

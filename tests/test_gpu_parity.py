@@ -626,6 +626,7 @@ def test_seg_graph_encoder_decoder_head(gg, cuda_dev, oracle_mod, B, fetch):
         tables.append(table); cents.append(cent); nums.append(num); masks.append(centmsk)
         loc = cent
     f_last, nl = tables[-1], len(cfg.layers)
+    g_tables = [data] + [t["table"].cpu().numpy() for t in net.enc.trace]  # what the GPU decoder consumed
     misses = 0
     for i, p in enumerate(params["dec"]):
         dn, upl = nl - i, nl - i - 1
@@ -642,13 +643,23 @@ def test_seg_graph_encoder_decoder_head(gg, cuda_dev, oracle_mod, B, fetch):
         misses += int((nebidx < 0).sum())
         assert np.array_equal(net.trace[i]["nebidx"].cpu().numpy(), nebidx), "decoder level %d indices" % i
         mask = masks[upl] if i != nl - 1 else None
+        got = net.trace[i]["table"].cpu().numpy()
+        # (1) the operator on IDENTICAL inputs (north_star's statement): this level of the oracle fed with the
+        #     tensors the GPU graph itself consumed -- strict elementwise tolerance;
+        g_prev = g_tables[-1] if i == 0 else net.trace[i - 1]["table"].cpu().numpy()
+        same_in = gridconv_oracle.gridconv_up_layer(g_prev, nebidx, cents[upl], g_tables[upl], mask, p)
+        _assert_feats(got[..., 4:], same_in[..., 4:], "decoder level %d (identical inputs)" % i)
+        # (2) the whole chain against the oracle chain: six layers of fp32-class rounding accumulate on both sides,
+        #     so the rms-floored form of the tolerance
         f_last = gridconv_oracle.gridconv_up_layer(f_last, nebidx, cents[upl], tables[upl], mask, p)
-        _assert_feats(net.trace[i]["table"].cpu().numpy()[..., 4:], f_last[..., 4:], "decoder level %d" % i)
+        err = _rel_err(got[..., 4:], f_last[..., 4:])
+        assert err <= 1e-3, "decoder level %d (chain): rel err %.3g" % (i, err)
     if fetch == "ballknn":
         assert misses > 0  # the take()-clip path of BallKNN misses (-1) is exercised through the full decoder
-    want = gridconv_oracle.seg_head(f_last[..., 4:], params["head"])
     assert logits.shape == (B, cfg.num_points, 21)
-    _assert_feats(logits, want, "logits")
+    _assert_feats(logits, gridconv_oracle.seg_head(net.trace[-1]["table"].cpu().numpy()[..., 4:], params["head"]),
+                  "logits (identical inputs)")
+    assert _rel_err(logits, gridconv_oracle.seg_head(f_last[..., 4:], params["head"])) <= 1e-3
 
 
 @pytest.mark.parametrize("B", [2, 32], ids=["B2", "B32_baseline_batch"])
@@ -682,3 +693,50 @@ def test_classification_graph_with_head(gg, cuda_dev, oracle_mod, B):
     _assert_feats(scores, x, "class scores")
     e = np.exp(x - x.max(-1, keepdims=True))
     assert np.allclose(probs, e / e.sum(-1, keepdims=True), rtol=2e-3, atol=1e-6)
+
+
+ROWMLP_CASES = [  # rows, c1, c2, cout, relu_in, relu_out, scale, cent
+    (1000, 132, 0, 128, False, True, False, False),   # decoder centre branch: [cent | feat] rows -> 128
+    (300, 128, 128, 128, True, True, True, True),     # update MLP: concat of two views, pre-ReLU, mask, table layout
+    (77, 128, 0, 21, False, False, False, False),     # segmentation head: 21 classes (tail columns)
+    (5, 4, 0, 128, False, True, False, False),        # level 0 of the decoder: the input points themselves
+    (260, 512, 0, 256, False, True, False, False),    # wide output (two weight rows per loader thread)
+    (33, 6, 0, 10, False, True, False, False),        # widths not a multiple of 4: CUDA-core fallback inside the tc entry
+]
+
+
+@pytest.mark.parametrize("case", ROWMLP_CASES, ids=["r%d_%d+%d_to_%d" % c[:4] for c in ROWMLP_CASES])
+def test_rowmlp_tensor_core_matches_numpy(gg, cuda_dev, case):
+    """gridgcn_rowmlp_tc_fwd (persistent tcgen05 GEMM, tf32x3) against float64 numpy, and against the CUDA-core
+    operator it replaces in the tensor-core precisions."""
+    from gridgcn_b200 import gridconv
+    rows, c1, c2, cout, relu_in, relu_out, use_scale, use_cent = case
+    rng = np.random.default_rng(rows)
+    a = rng.normal(size=(rows, 4 + c1)).astype(np.float32)       # in1 = a strided view [:, 4:]
+    b = rng.normal(size=(rows, c2 + 8)).astype(np.float32) if c2 else None
+    w = (rng.normal(size=(cout, c1 + c2)) / np.sqrt(c1 + c2)).astype(np.float32)
+    bias = rng.normal(size=cout).astype(np.float32)
+    scale = (rng.uniform(size=rows) > 0.3).astype(np.float32) if use_scale else None
+    cent = rng.normal(size=(rows, 4)).astype(np.float32) if use_cent else None
+    x = np.concatenate([a[:, 4:]] + ([b[:, :c2]] if c2 else []), axis=1).astype(np.float64)
+    if relu_in:
+        x = np.maximum(x, 0)
+    want = x @ w.astype(np.float64).T + bias
+    if relu_out:
+        want = np.maximum(want, 0)
+    if use_scale:
+        want = want * scale[:, None]
+    ta, tb = _t(a, cuda_dev), (_t(b, cuda_dev) if c2 else None)
+    outs = []
+    for tc in (True, False):
+        out = gridconv.rowmlp(ta[:, 4:], tb[:, :c2] if c2 else None, _t(w, cuda_dev), _t(bias, cuda_dev),
+                              relu_in=relu_in, relu_out=relu_out, row_scale=_t(scale, cuda_dev) if use_scale else None,
+                              out_col=4 if use_cent else 0, cent=_t(cent, cuda_dev) if use_cent else None, tc=tc)
+        out = out.cpu().numpy()
+        if use_cent:
+            assert np.array_equal(out[:, :4], cent)
+            out = out[:, 4:]
+        outs.append(out)
+        assert out.shape == want.shape
+        _assert_feats(out, want.astype(np.float32), "rowmlp tc=%s" % tc)
+    assert np.allclose(outs[0], outs[1], rtol=1e-4, atol=1e-5)
