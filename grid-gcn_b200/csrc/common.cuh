@@ -37,8 +37,9 @@ struct GridParams {
 //   sorted[N]   point ids ordered by (voxel, id)  cent_lin[O] linear voxel index of each centre
 //   cent_acc[4*O] barycentre sums (x*w, y*w, z*w, w) of each centre's voxel
 //   key[N], tmp[N]  per-point scratch used only when the cloud does not fit in shared memory
+//   firstmap[N/32], firstpfx[N/32]  first-occurrence bitmap and its prefix (grid_build_multi.cuh)
 struct WsLayout {
-    int bitmap, wordpfx, vend, sorted, cent_lin, cent_acc, key, tmp;
+    int bitmap, wordpfx, vend, sorted, cent_lin, cent_acc, key, tmp, firstmap, firstpfx;
     long long stride;  // words per cloud
 };
 
@@ -57,6 +58,8 @@ __host__ inline WsLayout make_layout(int N, int O, int G) {
     L.cent_acc = (int)off; off += round4(4LL * O);
     L.key = (int)off;      off += round4(N);
     L.tmp = (int)off;      off += round4(N);
+    L.firstmap = (int)off; off += round4((N + 31) / 32);  // first-occurrence bits / prefix: multi-kernel build only
+    L.firstpfx = (int)off; off += round4((N + 31) / 32);
     L.stride = off;
     return L;
 }

@@ -2,9 +2,13 @@
 #include "../../include/gridgcn_b200.h"
 #include "common.cuh"
 #include "grid_build.cuh"
+#include "grid_build_multi.cuh"
 #include "grid_query.cuh"
 #include "grid_cas.cuh"
 #include "knn.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace gg {
 
@@ -65,9 +69,44 @@ static cudaError_t launch_build_t(const float *data, const int *npts, const Grid
     return cudaGetLastError();
 }
 
+// Point-parallel build (grid_build_multi.cuh): nine small launches over B * N threads.
+static cudaError_t launch_build_multi(const float *data, const int *npts, const GridParams &g, int *ws,
+                                      const WsLayout &L, float *centmsk, int *centnum, int want_centers,
+                                      cudaStream_t st) {
+    const float4 *d4 = reinterpret_cast<const float4 *>(data);
+    auto blocks = [&](long long n) { return (int)std::max<long long>(1, std::min<long long>((n + kBmThreads - 1) / kBmThreads, (long long)sm_count() * 8)); };
+    const long long BN = (long long)g.B * g.N;
+    const int V = g.N < g.G ? g.N : g.G;
+    bm_clear_kernel<<<blocks((long long)g.B * (g.W + (g.N + 31) / 32)), kBmThreads, 0, st>>>(g, ws, L);
+    bm_voxelise_kernel<<<blocks(BN), kBmThreads, 0, st>>>(d4, npts, g, ws, L);
+    bm_prefix_kernel<<<g.B, 1024, 0, st>>>(g, ws, L);
+    bm_count_kernel<<<blocks(BN), kBmThreads, 0, st>>>(npts, g, ws, L);
+    bm_scan_kernel<<<g.B, 1024, 0, st>>>(ws, L);
+    bm_scatter_kernel<<<blocks(BN), kBmThreads, 0, st>>>(npts, g, ws, L);
+    bm_rank_kernel<<<blocks(BN), kBmThreads, 0, st>>>(npts, g, ws, L, want_centers);
+    if (want_centers) {
+        bm_firstpfx_kernel<<<g.B, 1024, 0, st>>>(g, ws, L, centmsk, centnum);
+        bm_centers_kernel<<<blocks((long long)g.B * V), kBmThreads, 0, st>>>(d4, g, ws, L);
+    }
+    return cudaGetLastError();
+}
+
+static bool build_multi_wanted(const GridParams &g) {
+    // clouds that do not fit one CTA's shared memory, or too few clouds to occupy the SMs one CTA each
+    static int force = -1;
+    if (force < 0) {
+        const char *e = getenv("GRIDGCN_BUILD_MULTI");
+        force = e ? (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2)) : 2;
+    }
+    if (force != 2) return force == 1;
+    const bool in_smem = build_smem_words(g.N, g.G, true) * 4 <= kBuildSmemLimit;
+    return !in_smem;
+}
+
 static cudaError_t launch_build(const float *data, const int *npts, const GridParams &g, int *ws,
                                 const WsLayout &L, float *centmsk, int *centnum, int want_centers,
                                 cudaStream_t st) {
+    if (build_multi_wanted(g)) return launch_build_multi(data, npts, g, ws, L, centmsk, centnum, want_centers, st);
     if (g.N <= 2048)
         return launch_build_t<256>(data, npts, g, ws, L, centmsk, centnum, want_centers, st);
     return launch_build_t<kBuildThreads>(data, npts, g, ws, L, centmsk, centnum, want_centers, st);

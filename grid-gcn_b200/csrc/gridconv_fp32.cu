@@ -385,7 +385,12 @@ extern "C" int gridgcn_gridconv_pack(const gridgcn_mlp_t *m, int Cin, void *pack
 extern "C" size_t gridgcn_gridconv_workspace_bytes(const gridgcn_mlp_t *m, int B, int Nprev, int Cin) {
     ConvParams p{};
     if (fill_mlp(m, Cin, p) || B < 0 || Nprev < 0 || !tc_supported(p)) return 0;
-    return Cin > 0 ? (size_t)B * Nprev * p.Cout * sizeof(float) : 0;
+    if (Cin <= 0) return 0;
+    // the transformed feature table F (rows x Cout) + two ping-pong buffers for the hidden activations of the
+    // per-point feature MLP when it runs as a chain of row GEMMs (gridconv_tc.cu, rowgemm_tc.cu)
+    int hmax = 0;
+    for (int s = 0; s + 1 < p.n_feat; s++) hmax = p.cout[s] > hmax ? p.cout[s] : hmax;
+    return (size_t)B * Nprev * ((size_t)p.Cout + 2 * (size_t)hmax) * sizeof(float);
 }
 
 extern "C" size_t gridgcn_gridconv_fp32_scratch_bytes(const gridgcn_mlp_t *m, int Cin, int K) {

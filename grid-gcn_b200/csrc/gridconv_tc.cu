@@ -36,6 +36,8 @@
 #include "gridconv_common.cuh"
 #include "gridconv_tc.cuh"
 
+#include <algorithm>
+
 namespace gg {
 
 // ------------------------------------------------------------------------------------------------
@@ -1747,6 +1749,38 @@ static void kernel_b_sequence(const TcParams &p, int &n_slices, size_t &seq_byte
 }
 
 int launch_first_ws(const TcParams &p, cudaStream_t st);  // gridconv_first_ws.cu; -1: layer does not fit
+int launch_rowgemm_tc(const float *in1, int ld1, int c1, const float *in2, int ld2, int c2, const float *W,
+                      const float *bias, int N, int relu_in, int relu_out, const float *scale, float *out, int ldo,
+                      const float *cent, float *out_table, long long rows, cudaStream_t st);  // rowgemm_tc.cu
+
+// Kernel A as a chain of row GEMMs (r02): every stage of the per-point feature MLP is one launch of the persistent
+// tensor-core GEMM of rowgemm_tc.cu (stages wider than 256 outputs: one launch per 256 columns); the hidden
+// activations ping-pong through two workspace buffers behind F.  Replaces the fused, lock-step
+// point_mlp_*_tc_kernel (13-17 % of the tensor pipe, r01 profile) whenever the views are 16-byte aligned.
+static int launch_point_mlp_chain(const TcParams &p, cudaStream_t st) {
+    const ConvParams &c = p.c;
+    if (p.nsplit != 3 || c.Cin <= 0 || (c.Cin & 3)) return -1;
+    for (int s = 0; s < c.n_feat; s++)
+        if (c.cout[s] & 3) return -1;
+    const long long rows = (long long)c.B * c.Nprev;
+    int hmax = 0;
+    for (int s = 0; s + 1 < c.n_feat; s++) hmax = std::max(hmax, c.cout[s]);
+    float *tmp[2] = {p.ftab + rows * c.Cout, p.ftab + rows * ((long long)c.Cout + hmax)};
+    const float *src = c.table + 4;
+    int ld = 4 + c.Cin, cw = c.Cin;
+    for (int s = 0; s < c.n_feat; s++) {
+        float *dst = s + 1 == c.n_feat ? p.ftab : tmp[s & 1];
+        const int N = c.cout[s];
+        for (int n0 = 0; n0 < N; n0 += 256) {
+            const int rc = launch_rowgemm_tc(src, ld, cw, nullptr, 0, 0, c.w[s] + (size_t)n0 * cw, c.bias[s] + n0,
+                                             std::min(256, N - n0), 0, 1, nullptr, dst + n0, N, nullptr, nullptr, rows, st);
+            if (rc != 0) return rc < 0 ? (s == 0 && n0 == 0 ? -1 : GRIDGCN_ELIMIT) : rc;
+        }
+        src = dst;
+        ld = cw = N;
+    }
+    return 0;
+}
 
 constexpr size_t kSmemCap = 224 * 1024;  // dynamic part; static barriers/index cache use < 3 KB of the 227 KB
 
@@ -1787,7 +1821,12 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         attr_set.set(dev);
     }
-    if (p.na > 0) {  // kernel A
+    int chain_rc = -1;
+    if (p.na > 0 && NSPLIT == 3) {
+        chain_rc = launch_point_mlp_chain(p, st);
+        if (chain_rc > 0) return chain_rc;
+    }
+    if (p.na > 0 && chain_rc != 0) {  // kernel A, fused variants
         int chunks = 0, kmax = 0, npmax = 0;
         for (int s = 0; s < p.na; s++) {
             chunks = max(chunks, p.a[s].Np / 128);
