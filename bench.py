@@ -345,11 +345,11 @@ def main():
         cfg = stack.cls1024_4layer(args.K, args.query)
         wl_name = "cls1024 4-layer GridConv encoder (O=512/128/32/8, K=%d, N=1024)" % args.K
     elif args.workload == "cls1024_shipped":
-        args.precision = "fp32"  # the tensor-core kernels implement the segmentation block only
         if args.query == "gridifyknn":
             args.query = "gridify"
         cfg = stack.cls1024_shipped(args.query)
-        wl_name = "cls1024 shipped 3-layer ladder, classification block (O=1024/128/1, P=64/64/128, kernel 7/3/1, N=1024)"
+        wl_name = "cls1024 shipped 3-layer ladder, classification block (O=1024/128/1, P=64/64/128, kernel 7/3/1, N=1024; " \
+                  "tf32x3 = chain of tensor-core row GEMMs, fp32 = CUDA-core kernel)"
     else:
         cfg = stack.seg81920_shipped(args.query)
         wl_name = "seg81920 shipped 3-layer GridConv encoder (O=1024/256/24, P=128/32/32, N=81920)"
@@ -610,6 +610,8 @@ def main():
             torch.cuda.empty_cache()
         side("config2_cls1024_B32_K32", lambda: measure_encoder(torch, flush, peaks, stack.cls1024_4layer(32), 32,
                                                                  args.precision, graph=True))
+        side("config2_cls1024_shipped_cls_block_B32", lambda: measure_encoder(torch, flush, peaks, stack.cls1024_shipped(), 32,
+                                                                               args.precision, steps=3))
         side("config3_seg8192_shipped_graph_B12", lambda: measure_seg_graph(torch, flush, 12, args.precision))
         side("config4_seg81920_B3", lambda: measure_encoder(torch, flush, peaks, stack.seg81920_shipped("gridify"), 3,
                                                              args.precision, graph=True))

@@ -55,6 +55,7 @@ SIGNATURES = {
     "gridgcn_gridconv_pack": (_i, [ctypes.POINTER(MlpDesc), _i, _vp, _sz, _vp]),
     "gridgcn_gridconv_workspace_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i, _i, _i]),
     "gridgcn_gridconv_fp32_scratch_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i, _i]),
+    "gridgcn_gridconv_edge_workspace_bytes": (_sz, [ctypes.POINTER(MlpDesc), _i, _i, _i, _i]),
     "gridgcn_gridconv_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(MlpDesc),
                                   _i, _vp, _vp, _sz, _vp, _vp]),
 }

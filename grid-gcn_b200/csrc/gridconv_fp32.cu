@@ -8,6 +8,8 @@
 // the K slots in shared memory and write one [cent | feats] row per centre.
 #include "gridconv_common.cuh"
 
+#include <algorithm>
+
 namespace gg {
 
 constexpr int kConvThreads = 256;
@@ -358,13 +360,22 @@ static bool tc_supported(const ConvParams &p) {
     return p.localfdim == 0 && p.att_full == GRIDGCN_ATT_FULL_OFF && (p.attfdim == 0 || p.n_att == 2);
 }
 
+// gridconv_cls_tc.cu: the classification-block variants as a chain of tensor-core row GEMMs over the edge rows
+bool cls_tc_ok(const ConvParams &p);
+long long cls_tc_packed_floats(const ConvParams &p);
+long long cls_tc_edge_bytes(const ConvParams &p);
+int cls_tc_pack(const ConvParams &p, float *packed, cudaStream_t st);
+int launch_gridconv_cls_tc(const ConvParams &p, const float *packed, float *ws, size_t ws_bytes, cudaStream_t st);
+constexpr size_t kClsWorkspaceCap = (size_t)6 << 30;  // clouds are processed in chunks that fit this much workspace
+
 }  // namespace gg
 
 using namespace gg;
 
 extern "C" size_t gridgcn_gridconv_packed_bytes(const gridgcn_mlp_t *m, int Cin) {
     ConvParams p{};
-    if (fill_mlp(m, Cin, p) || !tc_supported(p)) return 0;
+    if (fill_mlp(m, Cin, p)) return 0;
+    if (!tc_supported(p)) return cls_tc_ok(p) ? (size_t)cls_tc_packed_floats(p) * sizeof(float) : 0;
     int n = tc_packed_floats(p);
     return n < 0 ? 0 : (size_t)n * sizeof(float);
 }
@@ -374,7 +385,13 @@ extern "C" int gridgcn_gridconv_pack(const gridgcn_mlp_t *m, int Cin, void *pack
     ConvParams p{};
     int rc = fill_mlp(m, Cin, p);
     if (rc) return rc;
-    if (!tc_supported(p)) return GRIDGCN_ELIMIT;
+    if (!tc_supported(p)) {
+        if (!cls_tc_ok(p)) return GRIDGCN_ELIMIT;
+        if (!packed || packed_bytes < (size_t)cls_tc_packed_floats(p) * sizeof(float) ||
+            (reinterpret_cast<uintptr_t>(packed) & 15))
+            return GRIDGCN_EWORKSPACE;
+        return cls_tc_pack(p, static_cast<float *>(packed), static_cast<cudaStream_t>(stream));
+    }
     int n = tc_packed_floats(p);
     if (n < 0) return GRIDGCN_ELIMIT;
     if (!packed || packed_bytes < (size_t)n * sizeof(float) || (reinterpret_cast<uintptr_t>(packed) & 15))
@@ -391,6 +408,14 @@ extern "C" size_t gridgcn_gridconv_workspace_bytes(const gridgcn_mlp_t *m, int B
     int hmax = 0;
     for (int s = 0; s + 1 < p.n_feat; s++) hmax = p.cout[s] > hmax ? p.cout[s] : hmax;
     return (size_t)B * Nprev * ((size_t)p.Cout + 2 * (size_t)hmax) * sizeof(float);
+}
+
+extern "C" size_t gridgcn_gridconv_edge_workspace_bytes(const gridgcn_mlp_t *m, int B, int Cin, int O, int K) {
+    ConvParams p{};
+    if (fill_mlp(m, Cin, p) || B < 1 || O < 1 || K < 1 || tc_supported(p) || !cls_tc_ok(p)) return 0;
+    const size_t per_cloud = (size_t)O * K * (size_t)cls_tc_edge_bytes(p);
+    const size_t clouds = std::max<size_t>(1, std::min<size_t>((size_t)B, kClsWorkspaceCap / per_cloud));
+    return clouds * per_cloud;
 }
 
 extern "C" size_t gridgcn_gridconv_fp32_scratch_bytes(const gridgcn_mlp_t *m, int Cin, int K) {
@@ -430,8 +455,13 @@ extern "C" int gridgcn_gridconv_fwd(const float *table, const int *nebidx, const
         return launch_gridconv_fp32(p, st);
     }
     if (precision == GRIDGCN_PRECISION_TF32 || precision == GRIDGCN_PRECISION_TF32X3) {
-        if (!tc_supported(p)) return GRIDGCN_ELIMIT;  // classification-block variants: fp32 only
         if (!packed || (reinterpret_cast<uintptr_t>(packed) & 15)) return GRIDGCN_EWORKSPACE;
+        if (!tc_supported(p)) {  // classification-block variants: un-fused chain of tensor-core row GEMMs (3-pass only)
+            if (precision != GRIDGCN_PRECISION_TF32X3 || !cls_tc_ok(p)) return GRIDGCN_ELIMIT;
+            if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15)) return GRIDGCN_EWORKSPACE;
+            return launch_gridconv_cls_tc(p, static_cast<const float *>(packed), static_cast<float *>(workspace),
+                                          workspace_bytes, st);
+        }
         if (workspace_bytes < gridgcn_gridconv_workspace_bytes(m, B, Nprev, Cin) ||
             (Cin > 0 && (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15))))
             return GRIDGCN_EWORKSPACE;

@@ -71,66 +71,95 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_ws_kernel(const __grid_
 
     if (warp < 8) {
         // =========================== loaders ===========================
+        // Global loads are COALESCED (8 lanes read the 128 contiguous bytes of a row's chunk, 4 rows per instruction;
+        // r02l: one row per thread meant 32 sectors per request and an LSU-bound kernel at 1.7 TB/s) and transposed to
+        // the thread = row arrangement of the operand images through a warp-private staging tile.
         const int grp = warp >> 2;                     // chunks c with (c & 1) == grp
-        const int r = tid & 127;                       // tile row / weight row handled by this thread
-        const uint32_t row_off = ((uint32_t)r >> 3) * 128u + ((uint32_t)r & 7u) * 16u;
+        const int wq = warp & 3;                       // this warp's 32 tile rows / weight rows
+        float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes) + warp * (16 * 36);
+        const int lrow = lane >> 3, lg = lane & 7;     // load arrangement: row 4j + lrow, group lg
+        const int prow = lane & 15, pg0 = 4 * (lane >> 4);  // processing arrangement: row 16h + prow, groups pg0..pg0+3
         long long it = 0;                              // running chunk number of this CTA (ring position)
         for (int i = 0; i < n_my; i++) {
-            const long long row = (long long)(blockIdx.x + i * gridDim.x) * 128 + r;
-            const bool rv = row < p.rows;
-            const float *x1 = p.in1 + (rv ? row : 0) * p.ld1;
-            const float *x2 = p.in2 ? p.in2 + (rv ? row : 0) * p.ld2 : nullptr;
+            const long long row0 = (long long)(blockIdx.x + i * gridDim.x) * 128 + 32 * wq;
             for (int c = 0; c < nchunk; c++, it++) {
                 if ((c & 1) != grp) continue;
                 const int slot = (int)(it % S);
                 const uint32_t use = (uint32_t)(it / S);
-                const int k0 = c * kRgKC;
-                // issue every load of the chunk first: 8 x 16 B of this thread's input row, 8 (16) of its weight row(s)
-                float4 xv[8], wv[8], wv2[WIDE ? 8 : 1];
+                const int k = c * kRgKC + 4 * lg;
+                float4 xin[8], win[8], win2[WIDE ? 8 : 1];
 #pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    const int k = k0 + 4 * g;
+                for (int j = 0; j < 8; j++) {
+                    const long long row = row0 + 4 * j + lrow;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rv && k < p.K) v = k < p.c1 ? __ldg(reinterpret_cast<const float4 *>(x1 + k))
-                                                    : __ldg(reinterpret_cast<const float4 *>(x2 + (k - p.c1)));
-                    xv[g] = v;
+                    if (row < p.rows && k < p.K)
+                        v = k < p.c1 ? __ldg(reinterpret_cast<const float4 *>(p.in1 + row * p.ld1 + k))
+                                     : __ldg(reinterpret_cast<const float4 *>(p.in2 + row * p.ld2 + (k - p.c1)));
+                    xin[j] = v;
+                    const int n = 32 * wq + 4 * j + lrow;
                     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < p.N && k < p.K) w = __ldg(reinterpret_cast<const float4 *>(p.W + (size_t)r * p.K + k));
-                    wv[g] = w;
+                    if (n < p.N && k < p.K) w = __ldg(reinterpret_cast<const float4 *>(p.W + (size_t)n * p.K + k));
+                    win[j] = w;
                     if (WIDE) {
                         float4 w2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r + 128 < p.N && k < p.K) w2 = __ldg(reinterpret_cast<const float4 *>(p.W + (size_t)(r + 128) * p.K + k));
-                        wv2[g] = w2;
+                        if (n + 128 < p.N && k < p.K) w2 = __ldg(reinterpret_cast<const float4 *>(p.W + (size_t)(n + 128) * p.K + k));
+                        win2[j] = w2;
                     }
                 }
+                // in[j] = (row 4j + lrow, group lg)  ->  out[4h + gg] = (row 16h + prow, group pg0 + gg)
+                auto transpose = [&](const float4 *in, float4 *out) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            *reinterpret_cast<float4 *>(stage + (4 * j + lrow) * 36 + 4 * lg) = in[4 * h + j];
+                        __syncwarp();
+#pragma unroll
+                        for (int gg = 0; gg < 4; gg++)
+                            out[4 * h + gg] = *reinterpret_cast<const float4 *>(stage + prow * 36 + 4 * (pg0 + gg));
+                        __syncwarp();
+                    }
+                };
+                float4 xv[8], wv[8], wv2[WIDE ? 8 : 1];
+                transpose(xin, xv);
+                transpose(win, wv);
+                if (WIDE) transpose(win2, wv2);
                 if (use > 0) tc::mbar_wait(&empty[slot], (use - 1) & 1u);  // the MMAs that read this slot have retired
                 uint8_t *st = smem + (size_t)slot * stage_bytes;
-                uint8_t *xh = st + row_off, *xl = xh + 8u * kRgPanel;
-                uint8_t *wh = st + 16u * kRgPanel + row_off, *wl = wh + w_img;
 #pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    float4 v = xv[g];
-                    if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    float4 lo;  // activations: hardware truncation model (tc_common.cuh split_op<3>)
-                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    *reinterpret_cast<float4 *>(xh + (uint32_t)g * kRgPanel) = v;
-                    *reinterpret_cast<float4 *>(xl + (uint32_t)g * kRgPanel) = lo;
-                    if (r < Np) {
-                        float4 h, l;  // weights: round-to-nearest parts, as the packed images of gridconv_tc.cu
-                        tc::split_tf32(wv[g].x, h.x, l.x); tc::split_tf32(wv[g].y, h.y, l.y);
-                        tc::split_tf32(wv[g].z, h.z, l.z); tc::split_tf32(wv[g].w, h.w, l.w);
-                        *reinterpret_cast<float4 *>(wh + (uint32_t)g * lbo_w) = h;
-                        *reinterpret_cast<float4 *>(wl + (uint32_t)g * lbo_w) = l;
-                    }
-                    if (WIDE) {
-                        float4 h, l;
-                        tc::split_tf32(wv2[g].x, h.x, l.x); tc::split_tf32(wv2[g].y, h.y, l.y);
-                        tc::split_tf32(wv2[g].z, h.z, l.z); tc::split_tf32(wv2[g].w, h.w, l.w);
-                        *reinterpret_cast<float4 *>(wh + 2048u + (uint32_t)g * lbo_w) = h;  // rows 128.. : 16 row groups further
-                        *reinterpret_cast<float4 *>(wl + 2048u + (uint32_t)g * lbo_w) = l;
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t R = (uint32_t)(32 * wq + 16 * h + prow);  // tile row == weight row
+                    const uint32_t row_off = (R >> 3) * 128u + (R & 7u) * 16u;
+                    uint8_t *xh = st + row_off, *xl = xh + 8u * kRgPanel;
+                    uint8_t *wh = st + 16u * kRgPanel + row_off, *wl = wh + w_img;
+#pragma unroll
+                    for (int gg = 0; gg < 4; gg++) {
+                        const uint32_t g = (uint32_t)(pg0 + gg);
+                        float4 v = xv[4 * h + gg];
+                        if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        float4 lo;  // activations: hardware truncation model (tc_common.cuh split_op<3>)
+                        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                        *reinterpret_cast<float4 *>(xh + g * kRgPanel) = v;
+                        *reinterpret_cast<float4 *>(xl + g * kRgPanel) = lo;
+                        if ((int)R < Np) {
+                            float4 hh, l;  // weights: round-to-nearest parts, as the packed images of gridconv_tc.cu
+                            const float4 w = wv[4 * h + gg];
+                            tc::split_tf32(w.x, hh.x, l.x); tc::split_tf32(w.y, hh.y, l.y);
+                            tc::split_tf32(w.z, hh.z, l.z); tc::split_tf32(w.w, hh.w, l.w);
+                            *reinterpret_cast<float4 *>(wh + g * lbo_w) = hh;
+                            *reinterpret_cast<float4 *>(wl + g * lbo_w) = l;
+                        }
+                        if (WIDE) {
+                            float4 hh, l;
+                            const float4 w = wv2[4 * h + gg];
+                            tc::split_tf32(w.x, hh.x, l.x); tc::split_tf32(w.y, hh.y, l.y);
+                            tc::split_tf32(w.z, hh.z, l.z); tc::split_tf32(w.w, hh.w, l.w);
+                            *reinterpret_cast<float4 *>(wh + 2048u + g * lbo_w) = hh;  // rows 128.. : 16 row groups further
+                            *reinterpret_cast<float4 *>(wl + 2048u + g * lbo_w) = l;
+                        }
                     }
                 }
                 tc::fence_async_smem();
@@ -140,12 +169,17 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_ws_kernel(const __grid_
         }
     } else if (warp < 12) {
         // =========================== epilogue ===========================
+        // thread = row out of TMEM; the output rows leave through a warp-private staging tile so that 4 lanes write
+        // the 64 contiguous bytes of a row's 16 columns (8 rows per store instruction, full sectors)
         const uint32_t q = (uint32_t)(warp & 3);
         const int r = (int)q * 32 + lane;
         const int N = p.N;
+        float *stg = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes) + 8 * (16 * 36) + (warp - 8) * (32 * 20);
+        const int srow = lane >> 2, sg = lane & 3;  // store arrangement: row 8i + srow, columns 4 sg .. 4 sg + 3
         for (int i = 0; i < n_my; i++) {
             const int a = i & 1;
-            const long long row = (long long)(blockIdx.x + i * gridDim.x) * 128 + r;
+            const long long row_base = (long long)(blockIdx.x + i * gridDim.x) * 128 + 32 * (int)q;
+            const long long row = row_base + lane;
             const bool rv = row < p.rows;
             const float s = (rv && p.scale) ? __ldg(p.scale + row) : 1.f;
             float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -153,28 +187,39 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_ws_kernel(const __grid_
             tc::mbar_wait(&acc_full[a], (uint32_t)(i >> 1) & 1u);
             tc::fence_after_sync();
             const uint32_t taddr = tmem + ((q * 32u) << 16) + (uint32_t)a * acc_cols;
-            float *dst = p.out + (rv ? row : 0) * p.ldo;
             for (int c0 = 0; c0 < N; c0 += 16) {
                 uint32_t v[16];
                 tc::tmem_ld16(taddr + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
-                if (rv) {
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const int cc = c0 + 4 * g;
-                        float o[4];
+                for (int g = 0; g < 4; g++) {
+                    float o[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            float x = __uint_as_float(v[4 * g + j]) + bias_s[cc + j];
-                            if (p.relu_out) x = fmaxf(x, 0.f);
-                            o[j] = x * s;
+                    for (int j = 0; j < 4; j++) {
+                        float x = __uint_as_float(v[4 * g + j]) + bias_s[c0 + 4 * g + j];
+                        if (p.relu_out) x = fmaxf(x, 0.f);
+                        o[j] = x * s;
+                    }
+                    *reinterpret_cast<float4 *>(stg + lane * 20 + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                __syncwarp();
+                const int cc = c0 + 4 * sg;
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) {
+                    const int rl = 8 * ii + srow;
+                    const long long orow = row_base + rl;
+                    const float4 o = *reinterpret_cast<const float4 *>(stg + rl * 20 + 4 * sg);
+                    if (orow < p.rows) {
+                        float *dst = p.out + orow * p.ldo + cc;
+                        if (cc + 3 < N) *reinterpret_cast<float4 *>(dst) = o;
+                        else {
+                            if (cc < N) dst[0] = o.x;
+                            if (cc + 1 < N) dst[1] = o.y;
+                            if (cc + 2 < N) dst[2] = o.z;
                         }
-                        if (cc + 3 < N) *reinterpret_cast<float4 *>(dst + cc) = make_float4(o[0], o[1], o[2], o[3]);
-                        else
-                            for (int j = 0; j < 4; j++)
-                                if (cc + j < N) dst[cc + j] = o[j];
                     }
                 }
+                __syncwarp();
             }
             tc::fence_before_sync();
             __syncwarp();
@@ -240,17 +285,18 @@ int launch_rowgemm_tc(const float *in1, int ld1, int c1, const float *in2, int l
     if (tiles > 0x7fffffff) return -1;
     p.tiles = (int)tiles;
     const size_t stage = 2 * 8 * kRgPanel + 2 * (size_t)p.Np * 128;
-    p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage);
+    const size_t staging = 8 * (16 * 36) * 4 + 4 * (32 * 20) * 4;  // warp-private transposition tiles (loaders, epilogue)
+    p.stages = (int)std::min<size_t>(4, (225 * 1024 - staging) / stage);
     if (p.stages < 2) return -1;
-    const size_t smem = stage * p.stages + 1024;
+    const size_t smem = stage * p.stages + staging;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static PerDeviceOnce attr_set;
     if (!attr_set.done(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(rowgemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(rowgemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            e = cudaFuncSetAttribute(rowgemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set.set(dev);
     }

@@ -138,9 +138,8 @@ class GridConv:
             L = _lib.lib()
             nbytes = L.gridgcn_gridconv_packed_bytes(ctypes.byref(d), self.cin)
             if nbytes == 0:
-                raise _lib.GridGcnError("this MLP shape is not supported by the tensor-core GridConv (the "
-                                        "classification-block variants -- localfdim, att_full, explicit "
-                                        "attention widths -- run with precision='fp32')")
+                raise _lib.GridGcnError("this MLP shape is not supported by the tensor-core GridConv (widths that "
+                                        "are not multiples of 4 run with precision='fp32')")
             self._packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 rc = L.gridgcn_gridconv_pack(ctypes.byref(d), self.cin, self._packed.data_ptr(), nbytes,
@@ -164,7 +163,8 @@ class GridConv:
         ws, ws_bytes, packed = None, 0, None
         if self._packed is not None:
             packed = self._packed.data_ptr()
-            ws_bytes = L.gridgcn_gridconv_workspace_bytes(ctypes.byref(self._desc), B, Nprev, self.cin)
+            ws_bytes = max(L.gridgcn_gridconv_workspace_bytes(ctypes.byref(self._desc), B, Nprev, self.cin),
+                           L.gridgcn_gridconv_edge_workspace_bytes(ctypes.byref(self._desc), B, self.cin, O, K))
         else:  # fp32: activation scratch for layers too wide for shared memory
             ws_bytes = L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(self._desc), self.cin, K)
         if ws_bytes:

@@ -193,6 +193,10 @@ size_t gridgcn_gridconv_packed_bytes(const gridgcn_mlp_t *mlp_host, int Cin);
 int gridgcn_gridconv_pack(const gridgcn_mlp_t *mlp_host, int Cin, void *packed, size_t packed_bytes,
                           void *stream);
 size_t gridgcn_gridconv_workspace_bytes(const gridgcn_mlp_t *mlp_host, int B, int Nprev, int Cin);
+/* Classification-block variants (localfdim / att_full / explicit attention widths) in GRIDGCN_PRECISION_TF32X3 run
+ * as a chain of tensor-core row GEMMs over the edge rows (csrc/gridconv_cls_tc.cu) and need this much `workspace`
+ * (a multiple of one cloud's worth, capped: the clouds are processed in chunks); 0 for the segmentation block. */
+size_t gridgcn_gridconv_edge_workspace_bytes(const gridgcn_mlp_t *mlp_host, int B, int Cin, int O, int K);
 /* GRIDGCN_PRECISION_FP32 keeps a tile's activations in shared memory; layers too wide for that (the
  * classification block's 256/512-channel layers) need this much `workspace` instead (0 otherwise). */
 size_t gridgcn_gridconv_fp32_scratch_bytes(const gridgcn_mlp_t *mlp_host, int Cin, int K);

@@ -338,18 +338,20 @@ def test_gridconv_classification_block(gg, cuda_dev, oracle_mod, case):
     layer = gridconv.init_layer(np.random.default_rng(29), Cin, pt, attfdim, att_ele_lst=att,
                                 att_full=att_full, localfdim=localfdim)
     want = gridconv_oracle.gridconv_layer(table, nebidx, cent, centmsk, layer)
-    conv = gg.GridConv(layer, cuda_dev, precision="fp32")
-    got = conv(_t(table, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(centmsk, cuda_dev)).cpu().numpy()
-    assert np.array_equal(got[..., :4], want[..., :4])
-    err = _rel_err(got[..., 4:], want[..., 4:])
-    assert err <= 1e-3, "%s: rel err %.3g" % (name, err)
+    for precision in ("fp32", "tf32x3"):  # CUDA-core kernel / chain of tensor-core row GEMMs (gridconv_cls_tc.cu)
+        conv = gg.GridConv(layer, cuda_dev, precision=precision)
+        got = conv(_t(table, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(centmsk, cuda_dev)).cpu().numpy()
+        assert np.array_equal(got[..., :4], want[..., :4])
+        _assert_feats(got[..., 4:], want[..., 4:], "%s/%s" % (name, precision))
     assert np.abs(want[..., 4:]).max() > 0
-    if att_full or localfdim:  # the tensor-core kernels implement the segmentation block only: loud refusal
+    if att_full or localfdim:  # the single-pass tf32 option exists for the segmentation block only: loud refusal
+        conv = gg.GridConv(layer, cuda_dev, precision="tf32")
         with pytest.raises(gg._lib.GridGcnError):
-            gg.GridConv(layer, cuda_dev, precision="tf32x3")
+            conv(_t(table, cuda_dev), _t(nebidx, cuda_dev), _t(cent, cuda_dev), _t(centmsk, cuda_dev))
 
 
-def test_classification_stack_matches_oracle(gg, cuda_dev, oracle_mod):
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_classification_stack_matches_oracle(gg, cuda_dev, oracle_mod, precision):
     """The shipped ModelNet40 ladder (classification/configs/configs.yaml:44-68: kernel 7/3/1, O 1024/128/1,
     P 64/64/128, attfdim 4, localfdim 3, att_full next) end to end: Gridify indices bit-exact per layer,
     features within 1e-3."""
@@ -358,7 +360,7 @@ def test_classification_stack_matches_oracle(gg, cuda_dev, oracle_mod):
     cfg = stack.cls1024_shipped()
     params = stack.init_params(cfg, seed=4)
     data, npts = synth.make_batch(2, cfg.num_points, seed0=210, voxels=cfg.voxels)
-    enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision="fp32")
+    enc = stack.GridGcnEncoder(cfg, params, cuda_dev, precision=precision)
     out = enc(_t(data, cuda_dev), _t(npts, cuda_dev), keep_trace=True)
     table, loc, num = data, data, npts
     for i, (l, p) in enumerate(zip(cfg.layers, params)):
@@ -368,8 +370,7 @@ def test_classification_stack_matches_oracle(gg, cuda_dev, oracle_mod):
         tr = enc.trace[i]
         _check5([tr[n] for n in NAMES], want, "cls1024_shipped layer %d" % i)
         table = gridconv_oracle.gridconv_layer(table, want[0], want[2], want[3], p, pre_relu=cfg.pre_relu)
-        err = _rel_err(tr["table"].cpu().numpy()[..., 4:], table[..., 4:])
-        assert err <= 1e-3, "cls1024_shipped layer %d: rel err %.3g" % (i, err)
+        _assert_feats(tr["table"].cpu().numpy()[..., 4:], table[..., 4:], "cls1024_shipped/%s layer %d" % (precision, i))
         loc, num = want[2], want[4]
     assert out.shape == (2, 1, 4 + 512)
 
@@ -662,8 +663,9 @@ def test_seg_graph_encoder_decoder_head(gg, cuda_dev, oracle_mod, B, fetch):
     assert _rel_err(logits, gridconv_oracle.seg_head(f_last[..., 4:], params["head"])) <= 1e-3
 
 
-@pytest.mark.parametrize("B", [2, 32], ids=["B2", "B32_baseline_batch"])
-def test_classification_graph_with_head(gg, cuda_dev, oracle_mod, B):
+@pytest.mark.parametrize("B,precision", [(2, "fp32"), (32, "fp32"), (32, "tf32x3")],
+                         ids=["B2_fp32", "B32_baseline_batch_fp32", "B32_baseline_batch_tf32x3"])
+def test_classification_graph_with_head(gg, cuda_dev, oracle_mod, B, precision):
     """BASELINE config 2's model family: the shipped ModelNet40 ladder + FC 512-256-40 head
     (classification/models/ggcn_models_g.py:25-35, :37-111) from the reference's YAML keys, at the batch
     BASELINE names (32) -- class scores within 1e-3 of the oracle chain."""
@@ -672,7 +674,7 @@ def test_classification_graph_with_head(gg, cuda_dev, oracle_mod, B):
     cfg = stack.cls1024_shipped()
     params = stack.init_cls_params(cfg, seed=6)
     data, npts = synth.make_batch(B, cfg.num_points, seed0=500, voxels=cfg.voxels)
-    net = stack.GridGcnCls(cfg, params, cuda_dev, precision="fp32")
+    net = stack.GridGcnCls(cfg, params, cuda_dev, precision=precision)
     scores = net(_t(data, cuda_dev), _t(npts, cuda_dev)).cpu().numpy()
     probs = net(_t(data, cuda_dev), _t(npts, cuda_dev), probs=True).cpu().numpy()
     table, loc, num = data, data, npts
