@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_ws_kernel(const __grid_
         // Global loads are COALESCED (8 lanes read the 128 contiguous bytes of a row's chunk, 4 rows per instruction;
         // r02l: one row per thread meant 32 sectors per request and an LSU-bound kernel at 1.7 TB/s) and transposed to
         // the thread = row arrangement of the operand images through a warp-private staging tile.
-        const int grp = warp >> 2;                     // chunks c with (c & 1) == grp
+        const int grp = warp >> 2;                     // running chunks `it` with (it & 1) == grp
         const int wq = warp & 3;                       // this warp's 32 tile rows / weight rows
         float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes) + warp * (16 * 36);
         const int lrow = lane >> 3, lg = lane & 7;     // load arrangement: row 4j + lrow, group lg
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_ws_kernel(const __grid_
         for (int i = 0; i < n_my; i++) {
             const long long row0 = (long long)(blockIdx.x + i * gridDim.x) * 128 + 32 * wq;
             for (int c = 0; c < nchunk; c++, it++) {
-                if ((c & 1) != grp) continue;
+                if ((int)(it & 1) != grp) continue;  // alternate on the RUNNING chunk number: both groups work when nchunk is odd
                 const int slot = (int)(it % S);
                 const uint32_t use = (uint32_t)(it / S);
                 const int k = c * kRgKC + 4 * lg;
