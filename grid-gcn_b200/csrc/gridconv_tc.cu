@@ -1749,6 +1749,7 @@ static void kernel_b_sequence(const TcParams &p, int &n_slices, size_t &seq_byte
 }
 
 int launch_first_ws(const TcParams &p, cudaStream_t st);  // gridconv_first_ws.cu; -1: layer does not fit
+int launch_edge_ws(const TcParams &p, cudaStream_t st);   // gridconv_edge_ws.cu;  -1: layer does not fit
 int launch_rowgemm_tc(const float *in1, int ld1, int c1, const float *in2, int ld2, int c2, const float *W,
                       const float *bias, int N, int relu_in, int relu_out, const float *scale, float *out, int ldo,
                       const float *cent, float *out_table, long long rows, cudaStream_t st);  // rowgemm_tc.cu
@@ -1884,6 +1885,10 @@ static int launch_tc_t(TcParams &p, cudaStream_t st) {
         if ((long long)c.B * c.Nprev * c.Cout >= (1LL << 32)) return GRIDGCN_ELIMIT;  // 32-bit row offsets
         if (NSPLIT == 3 && p.has_ff) {  // persistent warp-specialised first-layer pipeline (gridconv_first_ws.cu)
             const int rc = launch_first_ws(p, st);
+            if (rc >= 0) return rc;
+        }
+        if (NSPLIT == 3 && !p.has_ff) {  // weight-stationary pipeline for the layers with input features (gridconv_edge_ws.cu)
+            const int rc = launch_edge_ws(p, st);
             if (rc >= 0) return rc;
         }
         if (NSPLIT == 3 && p.has_ff && p.has_att && p.f0_cuda && p.dbg == nullptr && c.Cout <= 64 &&
