@@ -17,11 +17,12 @@
 //       - hidden feature stage: its A operand (the stage-0 activations, hi | lo) is written by the stage-0
 //         epilogue straight into TMEM (tcgen05.st, thread = edge = lane), over the dead stage-0 accumulator;
 //       - last feature stage (transposed, M = 64): its A operand, the weights, sits in TMEM for the whole kernel.
-//   * Roles (21 warps, one CTA per SM, units of 128 edges round-robin over the CTAs):
-//       G    warps  0-3   gather: neighbour index -> table row (128-bit) + centre -> input image X0 (smem)
+//   * Roles (25 warps, one CTA per SM, units of 128 edges round-robin over the CTAs):
 //       E0   warps  4-7   stage-0 epilogue (thread = edge): D0 -> relu -> hi/lo: xf -> TMEM, xa -> smem
 //       EH   warps  8-11  hidden-stage epilogue (thread = edge): relu(D + b) -> hi/lo image xf2 (smem)
-//       EF   warps 12-15  final epilogue (thread = channel x half): relu(F + b) * relu(G + b), max over K, store
+//       G    warps 21-24  gather: neighbour index -> table row (128-bit) + centre -> input image X0 (smem)
+//       EF   warps 12-15 and 0-3: final epilogue (thread = channel x 64-edge half, each group 32 of the 64 columns):
+//                         relu(F + b) * relu(G + b), max over K, store -- the role that bounds the kernel
 //       MS / MH / MA / MF0 / MF1   warps 16-20: one thread each issues the MMAs of stage 0 / the hidden stage /
 //            attention stage 1 / the last feature stage (one warp per 64-edge half) and commits their mbarriers
 //     Every hand-over is an mbarrier (ONE arrival per epilogue warp -- every arrival wakes the warps sleeping on
@@ -40,9 +41,22 @@
 
 #include <cstdlib>
 
+// -DGG_WS_TIMING (tools/build_variant.py): CTA 0 accumulates, per role, the cycles spent in every barrier wait and the
+// role's total loop time into the debug buffer (gridgcn_debug_phase_buffer, 32 x u64; tools/ws_timing.py).
+#ifdef GG_WS_TIMING
+#define WS_WAIT(idx, bar, par)                                        \
+    {                                                                 \
+        const long long t_ = clock64();                               \
+        tc::mbar_wait(bar, par);                                      \
+        if (ws_timing) ws_tw[idx] += (unsigned long long)(clock64() - t_); \
+    }
+#else
+#define WS_WAIT(idx, bar, par) tc::mbar_wait(bar, par)
+#endif
+
 namespace gg {
 
-constexpr int kWsThreads = 672;
+constexpr int kWsThreads = 800;
 constexpr int kDX = 2;  // X0 input images                      (smem, 8 KB each)
 constexpr int kDA = 2;  // front slots: S0 acc / xf / hidden acc (TMEM, 96 columns each: [0, 192))
 constexpr int kDI = 3;  // activation images xf2 | xa            (smem)
@@ -155,6 +169,7 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[kDX + 4 * kDA + 2 * kDI + 3 * kDF];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float ef_pair[4][32];  // K >= 64: partial maxima handed from the second final-epilogue group to the first
     uint64_t *x0_full = bars;                                                    // G -> MS (4: one arrival per warp)
     uint64_t *s0_done = x0_full + kDX, *e0_done = s0_done + kDA;                 // MS -> E0, G (1); E0 -> MH (4: one arrival per warp)
     uint64_t *h_done = e0_done + kDA, *acc_free = h_done + kDA;                  // MH -> EH (1); EH -> MS (4: one arrival per warp)
@@ -182,7 +197,7 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
         for (int i = 0; i < kDF; i++) {
             tc::mbar_init(&f_full[i], 2);
             tc::mbar_init(&g_full[i], 1);
-            tc::mbar_init(&fg_free[i], 4);
+            tc::mbar_init(&fg_free[i], 8);
         }
         tc::mbar_init_fence();
     }
@@ -260,12 +275,21 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
     const int n_my = (int)blockIdx.x < num_units ? (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const unsigned centers_total = (unsigned)c.B * (unsigned)c.O;
     const int out_w = 4 + C;
-    const uint32_t row = q * 32u + (uint32_t)lane;                          // edge row of the unit (G, E0, EH)
+#ifdef GG_WS_TIMING
+    const bool ws_timing = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && ((warp < 16 && (warp & 3) == 0) || (warp >= 16 && warp <= 21));
+    unsigned long long ws_tw[16];
+    for (int i = 0; i < 16; i++) ws_tw[i] = 0;
+    const long long ws_t0 = clock64();
+#endif
+    const uint32_t row = q * 32u + (uint32_t)lane;                          // edge row of the unit (E0, EH)
     const uint32_t row_off = (row >> 3) * 128u + (row & 7u) * 16u;           // its offset inside a panel
 
-    if (warp < 4) {
+    if (warp >= 21) {
         // =========================== G: gather + input image ===========================
-        const int r = tid;
+        // (its own four warps: the fence.proxy.async behind every image store waits for the prefetch loads of the
+        //  following units, ~1500 cycles -- harmless here, fatal on the critical path of an epilogue role, r02)
+        const int r = tid - 672;
+        const uint32_t row_off = ((uint32_t)r >> 3) * 128u + ((uint32_t)r & 7u) * 16u;
         const int my_cl = r >> log2k, my_slot = r & ((1 << log2k) - 1);
         const int Nprev = c.Nprev, O = c.O;
         const int rows_total = c.B * c.Nprev;
@@ -318,7 +342,7 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
 #pragma unroll
             for (int k = 0; k < 8; k++) lo[k] = in[k] - __uint_as_float(__float_as_uint(in[k]) & 0xFFFFE000u);
             if (i >= kDX) {
-                tc::mbar_wait(&s0_done[sa.slot], sa.ph);
+                WS_WAIT(0, &s0_done[sa.slot], sa.ph);
                 sa.next();
             }
             uint8_t *x0 = smem + L.x0 + (uint32_t)x * 4u * kPanel + row_off;
@@ -338,15 +362,44 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             head = head_n; cent = cent_n; v_cur = v_nxt;
             idx_nxt = idx_n2; v_nxt = v_n2;
         }
-    } else if (warp < 8) {
+    } else if (warp >= 8 && warp < 12) {
+        // =========================== EH: hidden-stage epilogue ===========================
+        const float *bias_h = reinterpret_cast<const float *>(smem + L.bias_h);
+        RingPos<kDA> a;
+        RingPos<kDI> d;
+        for (int i = 0; i < n_my; i++) {
+            WS_WAIT(3, &h_done[a.slot], a.ph);
+            tc::fence_after_sync();
+            const uint32_t taddr = tmem + lane_base + (uint32_t)a.slot * kFrontCols + kHidCol;
+            uint8_t *img = smem + L.img + (uint32_t)d.slot * L.img_stride + row_off;
+            constexpr int H1L = (H1P + 15) / 16 * 16;
+            uint32_t v[H1L];
+#pragma unroll
+            for (int c0 = 0; c0 < H1L; c0 += 16) tc::tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(v + c0));
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_free[a.slot]);  // the whole front slot (xf and both accumulators) is dead now
+#pragma unroll
+            for (int cc = 0; cc < H1P; cc += 4) {
+                uint8_t *dst = img + (uint32_t)(cc >> 2) * kPanel;
+                relu_split_store4(v + cc, *reinterpret_cast<const float4 *>(bias_h + cc), dst, dst + L.xf_lo);
+            }
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&eh_done[d.slot]);
+            a.next();
+            d.next();
+        }
+    } else if (warp >= 4 && warp < 8) {
         // =========================== E0: stage-0 epilogue ===========================
         // D0 -> relu -> hi/lo.  The feature half goes back into TMEM over the accumulator (A operand of the hidden
         // stage: row = this thread's lane), the attention half into the shared-memory image (B operand of stage a1).
         RingPos<kDA> a;
         RingPos<kDI> d;
         for (int i = 0; i < n_my; i++) {
-            if (i >= kDI) tc::mbar_wait(&img_free[d.slot], d.ph ^ 1u);  // last-stage MMAs of unit i-3 have read the images
-            tc::mbar_wait(&s0_done[a.slot], a.ph);
+            if (i >= kDI) WS_WAIT(1, &img_free[d.slot], d.ph ^ 1u);  // last-stage MMAs of unit i-3 have read the images
+            WS_WAIT(2, &s0_done[a.slot], a.ph);
             tc::fence_after_sync();
             const uint32_t taddr = tmem + lane_base + (uint32_t)a.slot * kFrontCols;
             uint8_t *img = smem + L.img + (uint32_t)d.slot * L.img_stride + row_off;
@@ -383,40 +436,13 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             a.next();
             d.next();
         }
-    } else if (warp < 12) {
-        // =========================== EH: hidden-stage epilogue ===========================
-        const float *bias_h = reinterpret_cast<const float *>(smem + L.bias_h);
-        RingPos<kDA> a;
-        RingPos<kDI> d;
-        for (int i = 0; i < n_my; i++) {
-            tc::mbar_wait(&h_done[a.slot], a.ph);
-            tc::fence_after_sync();
-            const uint32_t taddr = tmem + lane_base + (uint32_t)a.slot * kFrontCols + kHidCol;
-            uint8_t *img = smem + L.img + (uint32_t)d.slot * L.img_stride + row_off;
-            constexpr int H1L = (H1P + 15) / 16 * 16;
-            uint32_t v[H1L];
-#pragma unroll
-            for (int c0 = 0; c0 < H1L; c0 += 16) tc::tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(v + c0));
-            tc::tmem_ld_wait();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_free[a.slot]);  // the whole front slot (xf and both accumulators) is dead now
-#pragma unroll
-            for (int cc = 0; cc < H1P; cc += 4) {
-                uint8_t *dst = img + (uint32_t)(cc >> 2) * kPanel;
-                relu_split_store4(v + cc, *reinterpret_cast<const float4 *>(bias_h + cc), dst, dst + L.xf_lo);
-            }
-            tc::fence_async_smem();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&eh_done[d.slot]);
-            a.next();
-            d.next();
-        }
-    } else if (warp < 16) {
-        // =========================== EF: final epilogue ===========================
-        // lane l of warp q: channel 16q + (l & 15), edges [64h, 64h + 64) of the unit with h = l >> 4.
+    } else if (warp < 4 || (warp >= 12 && warp < 16)) {
+        // =========================== EF: final epilogue (two groups of four warps) ===========================
+        // lane l of a warp with quadrant q: channel 16q + (l & 15), edges [64h, 64h + 64) of the unit with h = l >> 4;
+        // group g (warps 12-15: 0, warps 0-3: 1) reduces the 32 columns [32g, 32g + 32) of those.
         // (Tried, r02: starting the accumulators at the bias through tcgen05.st.x16 -- the 16 source registers of
         // every store have to be filled with MOVs, which costs what the bias adds cost.)
+        const int grp = warp < 4 ? 1 : 0;
         const int h = lane >> 4;
         const int ch = 16 * (int)q + (lane & 15);
         const bool chv = ch < C;
@@ -428,12 +454,12 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
         RingPos<kDF> f;
         for (int i = 0; i < n_my; i++) {
             const unsigned c_base = (unsigned)(blockIdx.x + i * gridDim.x) * (unsigned)cpt;
-            tc::mbar_wait(&f_full[f.slot], f.ph);
-            tc::mbar_wait(&g_full[f.slot], f.ph);
+            WS_WAIT(4, &f_full[f.slot], f.ph);
+            WS_WAIT(5, &g_full[f.slot], f.ph);
             tc::fence_after_sync();
-            const uint32_t taddr = tmem + lane_base + kFgCol0 + (uint32_t)f.slot * 128u;
+            const uint32_t taddr = tmem + lane_base + kFgCol0 + (uint32_t)f.slot * 128u + (uint32_t)(32 * grp);
             float m = -3.402823466e+38f;
-            uint32_t fa[16], ga[16], fb[16], gb[16];
+            uint32_t fa[16], ga[16];
             auto reduce16 = [&](const uint32_t (&fv)[16], const uint32_t (&gv)[16], int c0) {
                 float pr[16];
 #pragma unroll
@@ -443,8 +469,8 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
 #pragma unroll
                 for (int j = 1; j < 16; j++) mm = fmaxf(mm, pr[j]);
                 m = fmaxf(m, mm);
-                const int e_end = 64 * h + c0 + 16;  // edges of this lane reduced so far end here
-                if (log2k <= 6 && (e_end & kmask) == 0) {
+                const int e_end = 64 * h + 32 * grp + c0 + 16;  // edges of this lane reduced so far end here
+                if (log2k <= 5 && (e_end & kmask) == 0) {       // K <= 32: the centre lies inside this group's columns
                     const unsigned center = c_base + (unsigned)((e_end >> log2k) - 1);
                     if (chv && center < centers_total)
                         out_ch[(size_t)center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
@@ -454,27 +480,25 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             tc::tmem_ld16(taddr, fa);
             tc::tmem_ld16(taddr + 64u, ga);
             tc::tmem_ld_wait();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                tc::tmem_ld16(taddr + (uint32_t)(c0 + 16), fb);
-                tc::tmem_ld16(taddr + (uint32_t)(c0 + 80), gb);
-                reduce16(fa, ga, c0);
-                tc::tmem_ld_wait();
-                if (c0 == 0) {
-                    tc::tmem_ld16(taddr + 32u, fa);
-                    tc::tmem_ld16(taddr + 96u, ga);
-                } else {  // every TMEM read of this unit is done: the slot may be overwritten
-                    tc::fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&fg_free[f.slot]);
+            reduce16(fa, ga, 0);
+            tc::tmem_ld16(taddr + 16u, fa);
+            tc::tmem_ld16(taddr + 80u, ga);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&fg_free[f.slot]);  // every TMEM read of this warp is done (8 arrivals free the slot)
+            reduce16(fa, ga, 16);
+            if (log2k >= 6) {  // K = 64 / 128: the centre spans both groups' columns -- group 1 hands its partial maximum over
+                if (grp == 1) ef_pair[q][lane] = m;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)q) : "memory");
+                if (grp == 0) {
+                    m = fmaxf(m, ef_pair[q][lane]);
+                    if (log2k == 7) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));  // one centre per unit: both lane halves
+                    const unsigned center = c_base + (log2k == 7 ? 0u : (unsigned)h);
+                    if (chv && center < centers_total && (log2k == 6 || h == 0))
+                        out_ch[(size_t)center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
                 }
-                reduce16(fb, gb, c0 + 16);
-                tc::tmem_ld_wait();
-            }
-            if (log2k == 7) {  // one centre per unit: its two 64-edge halves meet across the lane pair
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                if (h == 0 && chv && c_base < centers_total)
-                    out_ch[(size_t)c_base * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + c_base);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)q) : "memory");
             }
             f.next();
         }
@@ -494,8 +518,8 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             RingPos<kDX> x;
             RingPos<kDA> a;
             for (int i = 0; i < n_my; i++) {
-                tc::mbar_wait(&x0_full[x.slot], x.ph);
-                if (i >= kDA) tc::mbar_wait(&acc_free[a.slot], a.ph ^ 1u);
+                WS_WAIT(6, &x0_full[x.slot], x.ph);
+                if (i >= kDA) WS_WAIT(7, &acc_free[a.slot], a.ph ^ 1u);
                 tc::fence_after_sync();
                 const uint64_t ah = adv(xh0, (uint32_t)x.slot * 4u * kPanel), al = adv(xl0, (uint32_t)x.slot * 4u * kPanel);
                 const uint32_t dacc = tmem + (uint32_t)a.slot * kFrontCols;
@@ -515,7 +539,7 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             constexpr int ks_h = H0P / 8;
             RingPos<kDA> a;
             for (int i = 0; i < n_my; i++) {
-                tc::mbar_wait(&e0_done[a.slot], a.ph);
+                WS_WAIT(8, &e0_done[a.slot], a.ph);
                 tc::fence_after_sync();
                 const uint32_t a_hi = tmem + (uint32_t)a.slot * kFrontCols, a_lo = a_hi + kXfLoCol, dacc = a_hi + kHidCol;
                 uint64_t bh = wh0, bl = wl0;
@@ -540,8 +564,8 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             RingPos<kDI> d;
             RingPos<kDF> f;
             for (int i = 0; i < n_my; i++) {
-                tc::mbar_wait(&eh_done[d.slot], d.ph);
-                if (i >= kDF) tc::mbar_wait(&fg_free[f.slot], f.ph ^ 1u);
+                WS_WAIT(9, &eh_done[d.slot], d.ph);
+                if (i >= kDF) WS_WAIT(10, &fg_free[f.slot], f.ph ^ 1u);
                 tc::fence_after_sync();
                 uint64_t ah = wh0, al = wl0;
                 uint64_t bh = adv(xh0, (uint32_t)d.slot * L.img_stride), bl = adv(xl0, (uint32_t)d.slot * L.img_stride);
@@ -574,8 +598,8 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             RingPos<kDI> d;
             RingPos<kDF> f;
             for (int i = 0; i < n_my; i++) {
-                tc::mbar_wait(&eh_done[d.slot], d.ph);
-                if (i >= kDF) tc::mbar_wait(&fg_free[f.slot], f.ph ^ 1u);
+                WS_WAIT(11, &eh_done[d.slot], d.ph);
+                if (i >= kDF) WS_WAIT(12, &fg_free[f.slot], f.ph ^ 1u);
                 tc::fence_after_sync();
                 uint64_t bh = adv(xh0, (uint32_t)d.slot * L.img_stride), bl = adv(xl0, (uint32_t)d.slot * L.img_stride);
                 const uint32_t dc = tmem + ((hh * 16u) << 16) + kFgCol0 + (uint32_t)f.slot * 128u;
@@ -593,6 +617,15 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             }
         }
     }
+#ifdef GG_WS_TIMING
+    if (ws_timing) {
+        const int role = warp < 16 ? warp >> 2 : (warp < 21 ? 4 + (warp - 16) : 9);  // EF1 E0 EH EF0 MS MH MA MF0 MF1 G
+        for (int i = 0; i < 16; i++)
+            if (ws_tw[i]) p.dbg[i] = ws_tw[i];
+        p.dbg[16 + role] = (unsigned long long)(clock64() - ws_t0);
+        if (role == 0) p.dbg[31] = (unsigned long long)n_my;
+    }
+#endif
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -614,7 +647,10 @@ static bool first_ws_enabled() {
 int launch_first_ws(const TcParams &p, cudaStream_t st) {
     const ConvParams &c = p.c;
     if (!first_ws_enabled()) return -1;
-    if (p.nsplit != 3 || !p.has_ff || !p.has_att || !p.f0_cuda || p.nfh != 1 || p.dbg != nullptr) return -1;
+    #ifndef GG_WS_TIMING
+    if (p.dbg != nullptr) return -1;
+#endif
+    if (p.nsplit != 3 || !p.has_ff || !p.has_att || !p.f0_cuda || p.nfh != 1) return -1;
     if (!(c.K == 16 || c.K == 32 || c.K == 64 || c.K == 128)) return -1;
     if (c.Cout > 64 || p.ff.Np != 128 || p.a1.Np != 128) return -1;
     const FirstWsLayout L = first_ws_layout(p);
