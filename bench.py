@@ -259,14 +259,14 @@ def measure_seg_graph(torch, flush, B, precision, steps=5):
             "cuda_graph": {"ms_per_step": gms, "points_per_s": B * cfg.num_points / (gms * 1e-3)}}
 
 
-def measure_train_step(torch, dist, dev, world, B=3, steps=4):
+def measure_train_step(torch, dist, dev, world, B=3, steps=4, block="cuda"):
     """BASELINE config 4: one data-parallel TRAINING step of the seg81920 ladder, B clouds per GPU: forward
     (index operators = this library's kernels; training-mode block on torch ops, train.py), backward, ONE flat
     NCCL all-reduce of the gradient bucket, update.  Every rank takes part; times are MAX over ranks."""
     from gridgcn_b200 import stack, synth, train, shard
     cfg = stack.seg81920_shipped("gridify")
     params = stack.init_params(cfg, seed=0)
-    model = train.GridGcnClassifier(cfg, params, num_classes=21).to(dev)
+    model = train.GridGcnClassifier(cfg, params, num_classes=21, block=block).to(dev)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3)
     base, _ = synth.make_batch(1, cfg.num_points, seed0=3000 + (dist.get_rank() if world > 1 else 0), voxels=cfg.voxels)
     data = torch.from_numpy(np.tile(base, (B, 1, 1)).copy()).to(dev)
@@ -296,8 +296,8 @@ def measure_train_step(torch, dist, dev, world, B=3, steps=4):
             t_step.append(e0.elapsed_time(e3))
             t_ar.append(e1.elapsed_time(e2))
     step_ms, ar_ms = shard.max_over_ranks([sum(t_step) / len(t_step), sum(t_ar) / len(t_ar)], device=dev)
-    return {"workload": "seg81920 ladder, %d clouds per GPU, training step (torch autograd block behind the CUDA index "
-                        "operators)" % B, "n_gpus": world, "step_ms": step_ms, "allreduce_ms": ar_ms,
+    return {"workload": "seg81920 ladder, %d clouds per GPU, training step; block = %s" % (B, "hand-written training kernels "
+                        "(csrc/train_ops.cu + tcgen05 row GEMM)" if block == "cuda" else "torch ops + autograd"), "n_gpus": world, "step_ms": step_ms, "allreduce_ms": ar_ms,
             "allreduce_share": ar_ms / step_ms, "gradient_bytes": grad_bytes,
             "points_per_s": world * B * cfg.num_points / (step_ms * 1e-3),
             "collective": "one flat NCCL all-reduce (SUM, then / world)" if world > 1 else "none (single rank)"}
@@ -507,7 +507,8 @@ def main():
     train_cfg = None
     if not args.no_configs and args.workload == "seg8192":
         try:
-            train_cfg = measure_train_step(torch, dist, dev, world)
+            train_cfg = measure_train_step(torch, dist, dev, world, block="cuda")
+            train_cfg["torch_autograd_block_step_ms"] = measure_train_step(torch, dist, dev, world, block="torch")["step_ms"]
         except Exception as e:  # never lose the headline line to a side measurement
             train_cfg = {"error": "%s: %s" % (type(e).__name__, e)}
         barrier()

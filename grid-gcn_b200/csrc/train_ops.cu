@@ -1,0 +1,280 @@
+// Training-mode GridConv block: the hand-written kernels of the forward (BatchNorm with BATCH statistics between the
+// 1x1 convolutions) and of the backward pass.
+//
+// Reference: utils/ops.py:149-158 (conv2d: Convolution -> BatchNorm(fix_gamma=False, use_global_stats=False,
+// momentum=bn_decay) -> relu; `use_global_stats: False` in segmentation/configs/configs.yaml:27),
+// segmentation/models/gcn_module_g_att.py:120-170 (feature MLP, attention MLP, product), :45-79 (max pool over the K
+// slots), :24-43 (pre-ReLU), :284-285 (centre mask), utils/ops.py:78-93 (batch_take_g), base_solver.py:153-156 (fit).
+// The index operators in front (Gridify / GridifyKNN / BallKNN) have no gradient in the reference either
+// (gridify-inl.h:227-231), so coordinates are constants and the gradient flows through the feature columns only.
+//
+// Layout: the block runs on EDGE ROWS (one row per (centre, slot) edge, channels contiguous) -- the layout of the
+// tensor-core row GEMM (rowgemm_tc.cu), which computes every 1x1 convolution of the forward (Z = X W^T + b) and every
+// input gradient of the backward (dX = dZ W); the kernels here are everything around those GEMMs:
+//     edge rows + gather indices, per-channel batch statistics, normalise + ReLU, max pool with arg-max, its routing
+//     backward, BatchNorm + ReLU backward (two passes: sums, then elementwise), weight gradient (dW = dZ^T X), and the
+//     scatter-add of the gather.
+// They are orchestrated from the host (grid-gcn_b200/train_cuda.py); this is an un-fused training path -- one HBM
+// round trip per operator, like the reference's MXNet graph -- whose GEMMs run on tcgen05.
+#include "gridconv_common.cuh"
+
+namespace gg {
+
+constexpr int kTrThreads = 256;
+
+// per edge: neighbour row index (take with clip after the batch offset), X_f = [geo, 0] (Cin == 0) or the gathered
+// feature columns, X_a = att_vec (padded to a multiple of 4)
+__global__ void __launch_bounds__(kTrThreads)
+train_edge_rows_kernel(const float *__restrict__ table, const int *__restrict__ nebidx, const float4 *__restrict__ cent,
+                       int B, int Nprev, int Cin, int O, int K, int attfdim, int ain_p, float *__restrict__ xf,
+                       float *__restrict__ xa, int *__restrict__ rowidx) {
+    const int fin_p = Cin > 0 ? Cin : 4, groups = fin_p / 4, row_w = 4 + Cin;
+    const long long edges = (long long)B * O * K, rows_total = (long long)B * Nprev;
+    for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < edges * groups; i += (long long)gridDim.x * kTrThreads) {
+        const long long e = i / groups;
+        const int g = (int)(i % groups);
+        const long long centre = e / K;
+        const int b = (int)(centre / O);
+        const long long row = take_row(__ldg(nebidx + e), b, Nprev, rows_total);
+        const float *src = table + row * row_w;
+        if (g == 0) {
+            const float4 c = __ldg(cent + centre);
+            float att[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) att[k] = 0.f;
+            float dx, dy, dz;
+            att_vector(attfdim > 0 ? attfdim : 3, c, __ldg(src), __ldg(src + 1), __ldg(src + 2), att, dx, dy, dz);
+            for (int k = 0; k < ain_p; k += 4)
+                *reinterpret_cast<float4 *>(xa + e * ain_p + k) = make_float4(att[k], att[k + 1], att[k + 2], att[k + 3]);
+            rowidx[e] = (int)row;
+            if (Cin == 0) {
+                *reinterpret_cast<float4 *>(xf + e * 4) = make_float4(dx, dy, dz, 0.f);
+                continue;
+            }
+        }
+        *reinterpret_cast<float4 *>(xf + e * fin_p + 4 * g) = __ldg(reinterpret_cast<const float4 *>(src + 4 + 4 * g));
+    }
+}
+
+// per-channel sums over the rows: s0[c] += sum a[r,c] * (b ? b[r,c] : 1), s1[c] += sum a[r,c]^2 (s1 may be null).
+// One CTA per slab of rows, thread = channel (coalesced), one atomicAdd per channel and CTA.
+__global__ void __launch_bounds__(kTrThreads)
+train_col_sums_kernel(const float *__restrict__ a, const float *__restrict__ b, long long rows, int C, int rows_per_cta,
+                      float *__restrict__ s0, float *__restrict__ s1) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    for (int c = threadIdx.x; c < C; c += kTrThreads) {
+        float t0 = 0.f, t1 = 0.f;
+        for (long long r = r0; r < r1; r++) {
+            const float v = a[r * C + c];
+            t0 += b ? v * b[r * C + c] : v;
+            t1 += v * v;
+        }
+        atomicAdd(s0 + c, t0);
+        if (s1) atomicAdd(s1 + c, t1);
+    }
+}
+
+// y = relu(gamma * (z - mean) * invstd + beta)
+__global__ void __launch_bounds__(kTrThreads)
+train_bn_relu_fwd_kernel(const float *__restrict__ z, long long n, int C, const float *__restrict__ mean,
+                         const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta,
+                         float *__restrict__ y) {
+    for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTrThreads) {
+        const int c = (int)(i % C);
+        y[i] = fmaxf(gamma[c] * (z[i] - mean[c]) * invstd[c] + beta[c], 0.f);
+    }
+}
+
+// dz = dy * (y > 0);  xhat = (z - mean) * invstd;  writes dz in place of dy and xhat in place of z (scratch reuse)
+__global__ void __launch_bounds__(kTrThreads)
+train_relu_bwd_xhat_kernel(float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ z, long long n, int C,
+                           const float *__restrict__ mean, const float *__restrict__ invstd) {
+    for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTrThreads) {
+        const int c = (int)(i % C);
+        dy[i] = y[i] > 0.f ? dy[i] : 0.f;
+        z[i] = (z[i] - mean[c]) * invstd[c];
+    }
+}
+
+// BatchNorm backward (batch statistics): dzpre = gamma * invstd / N * (N * dz - sum_dz - xhat * sum_dz_xhat)
+__global__ void __launch_bounds__(kTrThreads)
+train_bn_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ xhat, long long n, int C, float inv_rows,
+                    const float *__restrict__ gamma, const float *__restrict__ invstd, const float *__restrict__ sum_dz,
+                    const float *__restrict__ sum_dzx, float *__restrict__ dzpre) {
+    for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTrThreads) {
+        const int c = (int)(i % C);
+        dzpre[i] = gamma[c] * invstd[c] * (dz[i] - inv_rows * (sum_dz[c] + xhat[i] * sum_dzx[c]));
+    }
+}
+
+// max pool over the K slots of F * A (A may be null), arg-max slot, pre-ReLU, centre mask
+__global__ void __launch_bounds__(kTrThreads)
+train_pool_fwd_kernel(const float *__restrict__ F, const float *__restrict__ A, long long centres, int K, int C, int pre_relu,
+                      const float *__restrict__ mask, float *__restrict__ out, int ldo, int *__restrict__ argmax) {
+    for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < centres * C; i += (long long)gridDim.x * kTrThreads) {
+        const long long o = i / C;
+        const int c = (int)(i % C);
+        float m = -3.402823466e+38f;
+        int am = 0;
+        for (int k = 0; k < K; k++) {
+            const long long e = (o * K + k) * C + c;
+            const float v = A ? F[e] * A[e] : F[e];
+            if (v > m) { m = v; am = k; }
+        }
+        if (pre_relu && m <= 0.f) { m = 0.f; am = -1; }  // relu gate closed: no gradient
+        out[o * ldo + c] = m * mask[o];
+        argmax[i] = am;
+    }
+}
+
+// routing backward of the pool: dP goes to the arg-max edge only; dF = dP * A, dA = dP * F (zero elsewhere)
+__global__ void __launch_bounds__(kTrThreads)
+train_pool_bwd_kernel(const float *__restrict__ dout, int ldo, const float *__restrict__ F, const float *__restrict__ A,
+                      const int *__restrict__ argmax, const float *__restrict__ mask, long long centres, int K, int C,
+                      float *__restrict__ dF, float *__restrict__ dA) {
+    for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < centres * K * C; i += (long long)gridDim.x * kTrThreads) {
+        const int c = (int)(i % C);
+        const long long ek = i / C, o = ek / K;
+        const int k = (int)(ek % K);
+        float g = 0.f;
+        if (argmax[o * C + c] == k) g = dout[o * ldo + c] * mask[o];
+        dF[i] = A ? g * A[i] : g;
+        if (dA) dA[i] = g * F[i];
+    }
+}
+
+// weight gradient dW[o, i] += sum_r dz[r, o] * x[r, i] over a slab of rows per CTA (x = [in1 | in2] row views).
+// Tile: 32 x 32 outputs per CTA column/row block, rows streamed through shared memory.
+__global__ void __launch_bounds__(kTrThreads)
+train_wgrad_kernel(const float *__restrict__ dz, int Cout, const float *__restrict__ in1, int ld1, int c1,
+                   const float *__restrict__ in2, int ld2, int c2, long long rows, int rows_per_cta, float *__restrict__ dW) {
+    __shared__ float sd[32][33], sx[32][33];
+    const int Kin = c1 + c2;
+    const int o0 = blockIdx.y * 32, i0 = blockIdx.z * 32;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long rb = r0; rb < r1; rb += 32) {
+        for (int j = ty; j < 32; j += 8) {
+            const long long r = rb + j;
+            const int o = o0 + tx, ii = i0 + tx;
+            sd[j][tx] = (r < r1 && o < Cout) ? dz[r * Cout + o] : 0.f;
+            float xv = 0.f;
+            if (r < r1 && ii < Kin) xv = ii < c1 ? in1[r * ld1 + ii] : in2[r * ld2 + (ii - c1)];
+            sx[j][tx] = xv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) {
+            const float xv = sx[j][tx];
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[q] = fmaf(sd[j][ty + 8 * q], xv, acc[q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int o = o0 + ty + 8 * q, ii = i0 + tx;
+        if (o < Cout && ii < Kin) atomicAdd(dW + (size_t)o * Kin + ii, acc[q]);
+    }
+}
+
+// gather backward: dtable[rowidx[e], 4 + c] += dxf[e, c]
+__global__ void __launch_bounds__(kTrThreads)
+train_scatter_add_kernel(const float *__restrict__ dxf, const int *__restrict__ rowidx, long long edges, int Cin, int row_w,
+                         float *__restrict__ dtable) {
+    for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < edges * Cin; i += (long long)gridDim.x * kTrThreads) {
+        const long long e = i / Cin;
+        const int c = (int)(i % Cin);
+        atomicAdd(dtable + (long long)rowidx[e] * row_w + 4 + c, dxf[i]);
+    }
+}
+
+static int tr_blocks(long long n) { return (int)max(1LL, min((n + kTrThreads - 1) / kTrThreads, 148LL * 16)); }
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gridgcn_train_edge_rows(const float *table, const int *nebidx, const float *cent, int B, int Nprev, int Cin, int O,
+                            int K, int attfdim, float *xf, float *xa, int *rowidx, void *stream) {
+    if (!table || !nebidx || !cent || !xf || !rowidx || B < 0 || Nprev < 1 || Cin < 0 || (Cin & 3) || O < 1 || K < 1)
+        return GRIDGCN_EINVAL;
+    if (attfdim > 0 && !xa) return GRIDGCN_EINVAL;
+    if (B == 0) return 0;
+    const int ain_p = attfdim > 0 ? (att_in_width(attfdim) + 3) / 4 * 4 : 0;
+    const long long work = (long long)B * O * K * ((Cin > 0 ? Cin : 4) / 4);
+    train_edge_rows_kernel<<<tr_blocks(work), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        table, nebidx, reinterpret_cast<const float4 *>(cent), B, Nprev, Cin, O, K, attfdim, ain_p, xf, xa, rowidx);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_col_sums(const float *a, const float *b, long long rows, int C, float *s0, float *s1, void *stream) {
+    if (!a || !s0 || rows < 0 || C < 1) return GRIDGCN_EINVAL;
+    if (rows == 0) return 0;
+    const int per = (int)max(64LL, (rows + 148 * 8 - 1) / (148 * 8));
+    train_col_sums_kernel<<<(int)((rows + per - 1) / per), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, b, rows, C, per, s0, s1);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_bn_relu_fwd(const float *z, long long rows, int C, const float *mean, const float *invstd,
+                              const float *gamma, const float *beta, float *y, void *stream) {
+    if (!z || !mean || !invstd || !gamma || !beta || !y || rows < 0 || C < 1) return GRIDGCN_EINVAL;
+    if (rows == 0) return 0;
+    train_bn_relu_fwd_kernel<<<tr_blocks(rows * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(z, rows * C, C, mean, invstd, gamma, beta, y);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_relu_bwd_xhat(float *dy, const float *y, float *z, long long rows, int C, const float *mean,
+                                const float *invstd, void *stream) {
+    if (!dy || !y || !z || !mean || !invstd || rows < 0 || C < 1) return GRIDGCN_EINVAL;
+    if (rows == 0) return 0;
+    train_relu_bwd_xhat_kernel<<<tr_blocks(rows * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, z, rows * C, C, mean, invstd);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_bn_bwd(const float *dz, const float *xhat, long long rows, int C, const float *gamma, const float *invstd,
+                         const float *sum_dz, const float *sum_dzx, float *dzpre, void *stream) {
+    if (!dz || !xhat || !gamma || !invstd || !sum_dz || !sum_dzx || !dzpre || rows < 1 || C < 1) return GRIDGCN_EINVAL;
+    train_bn_bwd_kernel<<<tr_blocks(rows * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        dz, xhat, rows * C, C, 1.0f / (float)rows, gamma, invstd, sum_dz, sum_dzx, dzpre);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_pool_fwd(const float *F, const float *A, long long centres, int K, int C, int pre_relu, const float *mask,
+                           float *out, int ld_out, int *argmax, void *stream) {
+    if (!F || !mask || !out || !argmax || centres < 0 || K < 1 || C < 1 || ld_out < C) return GRIDGCN_EINVAL;
+    if (centres == 0) return 0;
+    train_pool_fwd_kernel<<<tr_blocks(centres * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(F, A, centres, K, C, pre_relu, mask, out, ld_out, argmax);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_pool_bwd(const float *dout, int ld_out, const float *F, const float *A, const int *argmax, const float *mask,
+                           long long centres, int K, int C, float *dF, float *dA, void *stream) {
+    if (!dout || !F || !argmax || !mask || !dF || centres < 0 || K < 1 || C < 1) return GRIDGCN_EINVAL;
+    if ((A == nullptr) != (dA == nullptr)) return GRIDGCN_EINVAL;
+    if (centres == 0) return 0;
+    train_pool_bwd_kernel<<<tr_blocks(centres * K * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dout, ld_out, F, A, argmax, mask, centres, K, C, dF, dA);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_wgrad(const float *dz, int Cout, const float *in1, int ld1, int c1, const float *in2, int ld2, int c2,
+                        long long rows, float *dW, void *stream) {
+    if (!dz || !in1 || !dW || Cout < 1 || c1 < 1 || c2 < 0 || (c2 > 0 && !in2) || rows < 0) return GRIDGCN_EINVAL;
+    if (rows == 0) return 0;
+    const int per = (int)max(256LL, (rows + 148 * 2 - 1) / (148 * 2));
+    dim3 grid((unsigned)((rows + per - 1) / per), (unsigned)((Cout + 31) / 32), (unsigned)((c1 + c2 + 31) / 32));
+    train_wgrad_kernel<<<grid, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dz, Cout, in1, ld1, c1, in2, ld2, c2, rows, per, dW);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_scatter_add(const float *dxf, const int *rowidx, long long edges, int Cin, int row_w, float *dtable, void *stream) {
+    if (!dxf || !rowidx || !dtable || edges < 0 || Cin < 1 || row_w < 4 + Cin) return GRIDGCN_EINVAL;
+    if (edges == 0) return 0;
+    train_scatter_add_kernel<<<tr_blocks(edges * Cin), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dxf, rowidx, edges, Cin, row_w, dtable);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

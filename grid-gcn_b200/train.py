@@ -119,10 +119,16 @@ class GridGcnClassifier(nn.Module):
     needs.  ``query(data_loc, num, layer_cfg) -> (nebidx, nebidxmsk, cent, centmsk, num)`` supplies the
     indices: the CUDA operators on a GPU (default), anything with the same outputs in CPU tests."""
 
-    def __init__(self, cfg, params, num_classes=40, query=None, bn_decay=0.9):
+    def __init__(self, cfg, params, num_classes=40, query=None, bn_decay=0.9, block="torch"):
         super().__init__()
         self.cfg = cfg
-        self.layers = nn.ModuleList([GridConvTrain(p, cfg.pre_relu, bn_decay) for p in params])
+        if block == "cuda":  # forward + backward on the library's own kernels (train_cuda.py, csrc/train_ops.cu)
+            from .train_cuda import GridConvTrainCuda as Block
+        elif block == "torch":
+            Block = GridConvTrain
+        else:
+            raise ValueError("block must be 'torch' or 'cuda'")
+        self.layers = nn.ModuleList([Block(p, cfg.pre_relu, bn_decay) for p in params])
         self.head = nn.Linear(cfg.layers[-1].pt_mlp_lst[-1], num_classes)
         self._query = query
 

@@ -1,0 +1,213 @@
+"""Training-mode GridConv block on this library's own kernels.
+
+Same math and parameters as ``train.GridConvTrain`` (the block of segmentation/models/gcn_module_g_att.py:172-287 with
+BatchNorm in TRAINING mode, utils/ops.py:149-158, ``use_global_stats: False`` configs.yaml:27) -- but the forward and
+the backward run on hand-written CUDA kernels instead of PyTorch ops + autograd:
+
+  * every 1x1 convolution of the forward (Z = X W^T + b) and every input gradient of the backward (dX = dZ W) is one
+    launch of the persistent tcgen05 row GEMM (csrc/rowgemm_tc.cu, 3-pass tf32 = fp32-class accuracy);
+  * csrc/train_ops.cu holds the rest: edge rows + gather indices, per-channel batch statistics, normalise + ReLU,
+    max pool with arg-max, its routing backward, ReLU / BatchNorm backward, weight gradients, gather scatter-add.
+
+``torch.autograd.Function`` is only the seam that hands ``grad_output`` in and the parameter gradients out; PyTorch
+supplies device memory and the optimiser.  Supported: the segmentation flavour (localfdim 0, att_full off, two
+attention stages) -- what the shipped ScanNet configs train.  The un-fused layout (one HBM round trip per operator,
+like the reference's MXNet graph) is deliberate for this first version; tests/test_gpu_train.py holds it to the
+autograd module within 1e-3.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, gridconv
+from .train import GridConvTrain
+
+BN_EPS = gridconv.BN_EPS
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _gemm(x, w, b, relu):
+    """rows x Cin @ (Cout x Cin)^T + b on the tensor-core row GEMM."""
+    return gridconv.rowmlp(x, None, w, b, relu_out=relu, tc=True)
+
+
+def _col_sums(a, b=None, want_sq=False):
+    L = _lib.lib()
+    rows, C = a.shape
+    s0 = torch.zeros(C, dtype=torch.float32, device=a.device)
+    s1 = torch.zeros(C, dtype=torch.float32, device=a.device) if want_sq else None
+    _lib.check(L.gridgcn_train_col_sums(a.data_ptr(), b.data_ptr() if b is not None else None, rows, C, s0.data_ptr(),
+                                        s1.data_ptr() if s1 is not None else None, _stream(a)), "gridgcn_train_col_sums")
+    return (s0, s1) if want_sq else s0
+
+
+class _Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, table, nebidx, cent, centmsk, *params):
+        L = _lib.lib()
+        dev = table.device
+        B, Nprev, roww = table.shape
+        _, O, K = nebidx.shape
+        cin, C = mod.cin, mod.cout
+        edges = B * O * K
+        table, nebidx, cent, centmsk = table.contiguous(), nebidx.contiguous(), cent.contiguous(), centmsk.contiguous()
+        fin_p = cin if cin > 0 else 4
+        ain_p = mod.ain_p
+        xf = torch.empty((edges, fin_p), dtype=torch.float32, device=dev)
+        xa = torch.empty((edges, max(ain_p, 4)), dtype=torch.float32, device=dev)
+        rowidx = torch.empty(edges, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.gridgcn_train_edge_rows(table.data_ptr(), nebidx.data_ptr(), cent.data_ptr(), B, Nprev, cin, O, K,
+                                                 mod.attfdim, xf.data_ptr(), xa.data_ptr(), rowidx.data_ptr(), _stream(table)),
+                       "gridgcn_train_edge_rows")
+            saved = []
+
+            def stage(x, idx):
+                w, b, gamma, beta = params[4 * idx:4 * idx + 4]
+                wp = mod._pad_w(idx, w)                       # zero columns for the padded input layouts
+                z = _gemm(x, wp, b, False)
+                rows = z.shape[0]
+                s0, s1 = _col_sums(z, want_sq=True)
+                mean = s0 / rows
+                var = torch.clamp(s1 / rows - mean * mean, min=0.0)   # biased, as BatchNorm normalises with
+                invstd = torch.rsqrt(var + BN_EPS)
+                y = torch.empty_like(z)
+                _lib.check(L.gridgcn_train_bn_relu_fwd(z.data_ptr(), rows, z.shape[1], mean.data_ptr(), invstd.data_ptr(),
+                                                       gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _stream(z)),
+                           "gridgcn_train_bn_relu_fwd")
+                mod._update_running(idx, mean, var, rows)
+                saved.append((x, z, y, mean, invstd))
+                return y
+
+            x = xf
+            for s in range(mod.n_feat):
+                x = stage(x, s)
+            F = x
+            A = None
+            if mod.n_att:
+                a = xa
+                for s in range(mod.n_att):
+                    a = stage(a, mod.n_feat + s)
+                A = a
+            out = torch.empty((B, O, 4 + C), dtype=torch.float32, device=dev)
+            out[:, :, :4] = cent
+            argmax = torch.empty((B * O, C), dtype=torch.int32, device=dev)
+            feats = out[:, :, 4:]
+            _lib.check(L.gridgcn_train_pool_fwd(F.data_ptr(), A.data_ptr() if A is not None else None, B * O, K, C,
+                                                1 if mod.pre_relu else 0, centmsk.data_ptr(), feats.data_ptr(), 4 + C,
+                                                argmax.data_ptr(), _stream(F)), "gridgcn_train_pool_fwd")
+        ctx.mod, ctx.saved, ctx.misc = mod, saved, (F, A, argmax, centmsk, rowidx, (B, Nprev, roww, O, K), params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        mod, saved = ctx.mod, ctx.saved
+        F, A, argmax, centmsk, rowidx, (B, Nprev, roww, O, K), params = ctx.misc
+        dev = dout.device
+        cin, C = mod.cin, mod.cout
+        edges = B * O * K
+        dout = dout.contiguous()
+        grads = [None] * len(params)
+        with torch.cuda.device(dev):
+            dF = torch.empty_like(F)
+            dA = torch.empty_like(A) if A is not None else None
+            _lib.check(L.gridgcn_train_pool_bwd(dout.data_ptr() + 16, 4 + C, F.data_ptr(), A.data_ptr() if A is not None else None,
+                                                argmax.data_ptr(), centmsk.data_ptr(), B * O, K, C, dF.data_ptr(),
+                                                dA.data_ptr() if dA is not None else None, _stream(dout)),
+                       "gridgcn_train_pool_bwd")
+
+            def stage_bwd(dy, idx, need_dx):
+                x, z, y, mean, invstd = saved[idx]
+                w, b, gamma, beta = params[4 * idx:4 * idx + 4]
+                rows, Cout = z.shape
+                # dy <- dz = dy * (y > 0);  z <- xhat
+                _lib.check(L.gridgcn_train_relu_bwd_xhat(dy.data_ptr(), y.data_ptr(), z.data_ptr(), rows, Cout, mean.data_ptr(),
+                                                         invstd.data_ptr(), _stream(dy)), "gridgcn_train_relu_bwd_xhat")
+                sum_dz = _col_sums(dy)
+                sum_dzx = _col_sums(dy, z)
+                dzpre = torch.empty_like(dy)
+                _lib.check(L.gridgcn_train_bn_bwd(dy.data_ptr(), z.data_ptr(), rows, Cout, gamma.data_ptr(), invstd.data_ptr(),
+                                                  sum_dz.data_ptr(), sum_dzx.data_ptr(), dzpre.data_ptr(), _stream(dy)),
+                           "gridgcn_train_bn_bwd")
+                wp = mod._pad_w(idx, w)
+                dwp = torch.zeros_like(wp)
+                _lib.check(L.gridgcn_train_wgrad(dzpre.data_ptr(), Cout, x.data_ptr(), x.stride(0), x.shape[1], None, 0, 0, rows,
+                                                 dwp.data_ptr(), _stream(dy)), "gridgcn_train_wgrad")
+                grads[4 * idx] = mod._unpad_w(idx, dwp).reshape(w.shape)
+                grads[4 * idx + 1] = _col_sums(dzpre)
+                grads[4 * idx + 2] = sum_dzx   # d gamma
+                grads[4 * idx + 3] = sum_dz    # d beta
+                if not need_dx:
+                    return None
+                zero_b = torch.zeros(wp.shape[1], dtype=torch.float32, device=dev)
+                return _gemm(dzpre, wp.t().contiguous(), zero_b, False)   # dX = dZ W
+
+            if A is not None:
+                d = dA
+                for s in range(mod.n_att - 1, -1, -1):
+                    d = stage_bwd(d, mod.n_feat + s, need_dx=s > 0)
+            d = dF
+            for s in range(mod.n_feat - 1, -1, -1):
+                d = stage_bwd(d, s, need_dx=(s > 0 or cin > 0))
+            dtable = None
+            if cin > 0 and ctx.needs_input_grad[1]:
+                dtable = torch.zeros((B, Nprev, roww), dtype=torch.float32, device=dev)
+                _lib.check(L.gridgcn_train_scatter_add(d.data_ptr(), rowidx.data_ptr(), edges, cin, roww, dtable.data_ptr(),
+                                                       _stream(d)), "gridgcn_train_scatter_add")
+        return (None, dtable, None, None, None) + tuple(grads)
+
+
+class GridConvTrainCuda(GridConvTrain):
+    """Drop-in for ``train.GridConvTrain`` (same constructor, parameters, state dict and ``export_layer``): forward and
+    backward on the library's CUDA kernels.  In eval mode (``module.eval()``) it defers to the parent's op-by-op
+    forward with the moving statistics."""
+
+    def __init__(self, layer, pre_relu=True, bn_decay=0.9):
+        super().__init__(layer, pre_relu, bn_decay)
+        if self.localfdim or self.att_full or len(self.att) not in (0, 2):
+            raise NotImplementedError("GridConvTrainCuda implements the segmentation flavour of the block")
+        self.n_feat, self.n_att = len(self.feat), len(self.att)
+        self.cout = int(self.feat[-1].weight.shape[0])
+        aw = 0 if self.attfdim <= 0 else (3 if self.attfdim <= 3 else (4 if self.attfdim < 10 else 10))
+        self.ain, self.ain_p = aw, (aw + 3) // 4 * 4
+        self.bn_decay = bn_decay
+
+    def _stages(self):
+        return list(self.feat) + list(self.att)
+
+    def _pad_w(self, idx, w):
+        """(Cout, Cin) -> (Cout, Cin padded): [geo, 0] for the first feature stage without input features, trailing
+        zeros of att_vec for the first attention stage."""
+        w = w.reshape(w.shape[0], -1)
+        want = None
+        if idx == 0 and self.cin == 0:
+            want = 4
+        elif idx == self.n_feat and self.n_att:
+            want = self.ain_p
+        if want is None or w.shape[1] == want:
+            return w.contiguous()
+        return torch.cat([w, w.new_zeros(w.shape[0], want - w.shape[1])], 1).contiguous()
+
+    def _unpad_w(self, idx, dwp):
+        st = self._stages()[idx]
+        return dwp[:, :st.weight.reshape(st.weight.shape[0], -1).shape[1]].contiguous()
+
+    def _update_running(self, idx, mean, var, rows):
+        bn = self._stages()[idx].bn
+        with torch.no_grad():  # torch.nn.BatchNorm2d convention (momentum weighs the NEW value; unbiased running variance)
+            m = bn.momentum
+            bn.running_mean.mul_(1 - m).add_(m * mean)
+            bn.running_var.mul_(1 - m).add_(m * var * (rows / max(rows - 1, 1)))
+            bn.num_batches_tracked += 1
+
+    def forward(self, table, nebidx, cent, centmsk):
+        if not self.training or not table.is_cuda:
+            return super().forward(table, nebidx, cent, centmsk)
+        params = []
+        for st in self._stages():
+            params += [st.weight, st.bias, st.bn.weight, st.bn.bias]
+        return _Fn.apply(self, table, nebidx.int(), cent, centmsk, *params)

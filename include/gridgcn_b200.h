@@ -229,6 +229,34 @@ int gridgcn_rowmlp_tc_fwd(const float *in1, int ld1, int c1, const float *in2, i
                           const float *row_scale, float *out, int ld_out, const float *cent,
                           float *out_table, long long rows, void *stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Training-mode GridConv block (BatchNorm with batch statistics, utils/ops.py:149-158 with       */
+/* use_global_stats False; backward of gather / MLP / attention product / max pool): the kernels  */
+/* around the tensor-core row GEMMs (gridgcn_rowmlp_tc_fwd computes Z = X W^T + b and dX = dZ W). */
+/* All tensors are EDGE ROWS (edges = B*O*K rows, channels contiguous).  csrc/train_ops.cu;       */
+/* orchestration: grid-gcn_b200/train_cuda.py.                                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* xf (edges, Cin or 4 = [geo, 0]), xa (edges, pad4(att width)), rowidx (edges) = gathered table row */
+int gridgcn_train_edge_rows(const float *table, const int *nebidx, const float *cent, int B, int Nprev, int Cin, int O,
+                            int K, int attfdim, float *xf, float *xa, int *rowidx, void *stream);
+/* s0[c] += sum_r a[r,c] * (b ? b[r,c] : 1);  s1[c] += sum_r a[r,c]^2 (s1 may be NULL); zero them first */
+int gridgcn_train_col_sums(const float *a, const float *b, long long rows, int C, float *s0, float *s1, void *stream);
+int gridgcn_train_bn_relu_fwd(const float *z, long long rows, int C, const float *mean, const float *invstd,
+                              const float *gamma, const float *beta, float *y, void *stream);
+/* in place: dy <- dy * (y > 0), z <- (z - mean) * invstd */
+int gridgcn_train_relu_bwd_xhat(float *dy, const float *y, float *z, long long rows, int C, const float *mean,
+                                const float *invstd, void *stream);
+int gridgcn_train_bn_bwd(const float *dz, const float *xhat, long long rows, int C, const float *gamma, const float *invstd,
+                         const float *sum_dz, const float *sum_dzx, float *dzpre, void *stream);
+int gridgcn_train_pool_fwd(const float *F, const float *A, long long centres, int K, int C, int pre_relu, const float *mask,
+                           float *out, int ld_out, int *argmax, void *stream);
+int gridgcn_train_pool_bwd(const float *dout, int ld_out, const float *F, const float *A, const int *argmax, const float *mask,
+                           long long centres, int K, int C, float *dF, float *dA, void *stream);
+/* dW[o, i] += sum_r dz[r, o] * [in1 | in2][r, i]; zero dW first */
+int gridgcn_train_wgrad(const float *dz, int Cout, const float *in1, int ld1, int c1, const float *in2, int ld2, int c2,
+                        long long rows, float *dW, void *stream);
+int gridgcn_train_scatter_add(const float *dxf, const int *rowidx, long long edges, int Cin, int row_w, float *dtable, void *stream);
+
 /* Self-test of the tcgen05 primitives (not an operator): D[128,N] = A[128,K] * B[N,K]^T on one CTA,
  * kind::tf32, nsplit 1 (plain) or 3 (error-compensated).  N % 16 == 0, N <= 256, K % 8 == 0. */
 int gridgcn_debug_tc_gemm(const float *A, const float *B, float *D, int N, int K, int nsplit,

