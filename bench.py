@@ -572,13 +572,13 @@ def main():
     q_bytes = B * gridify_bytes(cfg.num_points, l0.max_o_grid, l0.max_p_grid)
     q_gbs = q_bytes / (q_ms * 1e-3) / 1e9
 
-    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01s_traffic.json),
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r02_traffic.json),
     # scaled to this run's batch; null when no capture exists for the kernel
     traffic = {}
     try:
         if not (args.workload == "seg8192" and args.K == 64 and args.query == "gridifyknn"):
             raise KeyError("the committed capture is of the default workload only")
-        with open(os.path.join(ROOT, "profiles", "r01s_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f)["per_launch"]
         for k, v in tj.items():
             traffic[k] = (v["dram_read_bytes"] + v["dram_write_bytes"]) * B / v["clouds"]
