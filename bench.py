@@ -295,9 +295,32 @@ def measure_train_step(torch, dist, dev, world, B=3, steps=4, block="cuda"):
         if it >= 2:
             t_step.append(e0.elapsed_time(e3))
             t_ar.append(e1.elapsed_time(e2))
+    eager_ms = shard.max_over_ranks([sum(t_step) / len(t_step)], device=dev)[0]
+    # the same step replayed as CUDA graphs (train.GraphedTrainStep): the eager step is launch bound
+    del loss  # its autograd graph pins AccumulateGrad nodes to the eager stream
+    gstep = train.GraphedTrainStep(model, opt, data, npts, labels)
+    t_step, t_ar = [], []
+    for it in range(4 * steps + 2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        gstep.g1.replay()
+        e1.record()
+        gstep._reduce()
+        e2.record()
+        gstep.g2.replay()
+        e3.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            t_step.append(e0.elapsed_time(e3))
+            t_ar.append(e1.elapsed_time(e2))
     step_ms, ar_ms = shard.max_over_ranks([sum(t_step) / len(t_step), sum(t_ar) / len(t_ar)], device=dev)
-    return {"workload": "seg81920 ladder, %d clouds per GPU, training step; block = %s" % (B, "hand-written training kernels "
-                        "(csrc/train_ops.cu + tcgen05 row GEMM)" if block == "cuda" else "torch ops + autograd"), "n_gpus": world, "step_ms": step_ms, "allreduce_ms": ar_ms,
+    return {"workload": "seg81920 ladder, %d clouds per GPU, training step (forward+backward and the update replayed as CUDA graphs, "
+                        "all-reduce between them; eager_step_ms = the same step launched op by op); block = %s" % (B, "hand-written training kernels "
+                        "(csrc/train_ops.cu + tcgen05 row GEMM)" if block == "cuda" else "torch ops + autograd"), "n_gpus": world, "step_ms": step_ms, "cuda_graph": True,
+            "eager_step_ms": eager_ms, "allreduce_ms": ar_ms,
             "allreduce_share": ar_ms / step_ms, "gradient_bytes": grad_bytes,
             "points_per_s": world * B * cfg.num_points / (step_ms * 1e-3),
             "collective": "one flat NCCL all-reduce (SUM, then / world)" if world > 1 else "none (single rank)"}
@@ -508,7 +531,9 @@ def main():
     if not args.no_configs and args.workload == "seg8192":
         try:
             train_cfg = measure_train_step(torch, dist, dev, world, block="cuda")
-            train_cfg["torch_autograd_block_step_ms"] = measure_train_step(torch, dist, dev, world, block="torch")["step_ms"]
+            tt = measure_train_step(torch, dist, dev, world, block="torch")
+            train_cfg["torch_autograd_block_step_ms"] = tt["step_ms"]
+            train_cfg["torch_autograd_block_eager_step_ms"] = tt["eager_step_ms"]
         except Exception as e:  # never lose the headline line to a side measurement
             train_cfg = {"error": "%s: %s" % (type(e).__name__, e)}
         barrier()

@@ -51,12 +51,13 @@ SIGNATURES = {
     # training-mode block kernels (csrc/train_ops.cu)
     "gridgcn_train_edge_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gridgcn_train_col_sums": (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp]),
+    "gridgcn_train_bn_finalize": (_i, [_vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),
     "gridgcn_train_bn_relu_fwd": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gridgcn_train_relu_bwd_xhat": (_i, [_vp, _vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp]),
+    "gridgcn_train_relu_bwd_xhat": (_i, [_vp, _vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp, _vp, _vp]),
     "gridgcn_train_bn_bwd": (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gridgcn_train_pool_fwd": (_i, [_vp, _vp, ctypes.c_longlong, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "gridgcn_train_pool_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp]),
-    "gridgcn_train_wgrad": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, ctypes.c_longlong, _vp, _vp]),
+    "gridgcn_train_wgrad": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, ctypes.c_longlong, _vp, _vp, _vp]),
     "gridgcn_train_scatter_add": (_i, [_vp, _vp, ctypes.c_longlong, _i, _i, _vp, _vp]),
     "gridgcn_debug_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "gridgcn_debug_curand_first_uniform": (_i, [_vp, _i, _vp, _vp, _vp]),

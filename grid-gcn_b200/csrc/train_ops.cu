@@ -74,6 +74,22 @@ train_col_sums_kernel(const float *__restrict__ a, const float *__restrict__ b, 
     }
 }
 
+// batch statistics from the column sums: mean, biased variance -> invstd; moving statistics (torch convention:
+// momentum weighs the NEW value, unbiased variance)
+__global__ void __launch_bounds__(kTrThreads)
+train_bn_finalize_kernel(const float *__restrict__ s0, const float *__restrict__ s1, float rows, int C, float eps, float momentum,
+                         float *__restrict__ mean, float *__restrict__ invstd, float *__restrict__ running_mean,
+                         float *__restrict__ running_var) {
+    const int c = blockIdx.x * kTrThreads + threadIdx.x;
+    if (c >= C) return;
+    const float mu = s0[c] / rows;
+    const float var = fmaxf(s1[c] / rows - mu * mu, 0.f);
+    mean[c] = mu;
+    invstd[c] = rsqrtf(var + eps);
+    if (running_mean) running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * mu;
+    if (running_var) running_var[c] = running_var[c] * (1.f - momentum) + momentum * (var * (rows / fmaxf(rows - 1.f, 1.f)));
+}
+
 // y = relu(gamma * (z - mean) * invstd + beta)
 __global__ void __launch_bounds__(kTrThreads)
 train_bn_relu_fwd_kernel(const float *__restrict__ z, long long n, int C, const float *__restrict__ mean,
@@ -179,6 +195,195 @@ train_wgrad_kernel(const float *__restrict__ dz, int Cout, const float *__restri
     }
 }
 
+
+// ---- float4 forms (C % 4 == 0, C <= 1024): thread = one group of 4 consecutive channels, walking the rows of its CTA's
+// slab with stride R = 256 / (C/4) -- 128-bit coalesced accesses, per-channel constants in registers, no div / mod per
+// element.  The reductions end in one shared-memory pass and one atomicAdd per channel and CTA.
+struct ColMap {
+    int G, R, cg, rr;
+    bool active;
+    __device__ __forceinline__ ColMap(int C) {
+        G = C >> 2;
+        R = kTrThreads / G;
+        cg = threadIdx.x % G;
+        rr = threadIdx.x / G;
+        active = rr < R;
+    }
+};
+
+__device__ __forceinline__ void col_reduce_store(const ColMap &m, int C, float4 t, float (*red)[4], float *__restrict__ dst) {
+    __syncthreads();
+    red[threadIdx.x][0] = t.x; red[threadIdx.x][1] = t.y; red[threadIdx.x][2] = t.z; red[threadIdx.x][3] = t.w;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kTrThreads) {
+        float acc = 0.f;
+        for (int r = 0; r < m.R; r++) acc += red[r * m.G + (c >> 2)][c & 3];
+        atomicAdd(dst + c, acc);
+    }
+}
+
+template <bool HAS_B, bool SQ>
+__global__ void __launch_bounds__(kTrThreads)
+train_col_sums4_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, long long rows, int C, int rows_per_cta,
+                       float *__restrict__ s0, float *__restrict__ s1) {
+    __shared__ float red[kTrThreads][4];
+    const ColMap m(C);
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    if (m.active)
+        for (long long r = r0 + m.rr; r < r1; r += m.R) {
+            const float4 v = __ldg(a + r * m.G + m.cg);
+            if (HAS_B) {
+                const float4 w = __ldg(b + r * m.G + m.cg);
+                t0.x = fmaf(v.x, w.x, t0.x); t0.y = fmaf(v.y, w.y, t0.y); t0.z = fmaf(v.z, w.z, t0.z); t0.w = fmaf(v.w, w.w, t0.w);
+            } else {
+                t0.x += v.x; t0.y += v.y; t0.z += v.z; t0.w += v.w;
+            }
+            if (SQ) { t1.x = fmaf(v.x, v.x, t1.x); t1.y = fmaf(v.y, v.y, t1.y); t1.z = fmaf(v.z, v.z, t1.z); t1.w = fmaf(v.w, v.w, t1.w); }
+        }
+    col_reduce_store(m, C, t0, red, s0);
+    if (SQ) col_reduce_store(m, C, t1, red, s1);
+}
+
+__global__ void __launch_bounds__(kTrThreads)
+train_bn_relu_fwd4_kernel(const float4 *__restrict__ z, long long rows, int C, int rows_per_cta, const float4 *__restrict__ mean,
+                          const float4 *__restrict__ invstd, const float4 *__restrict__ gamma, const float4 *__restrict__ beta,
+                          float4 *__restrict__ y) {
+    const ColMap m(C);
+    if (!m.active) return;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    const float4 mu = __ldg(mean + m.cg), is = __ldg(invstd + m.cg), ga = __ldg(gamma + m.cg), be = __ldg(beta + m.cg);
+    for (long long r = r0 + m.rr; r < r1; r += m.R) {
+        const float4 v = __ldg(z + r * m.G + m.cg);
+        float4 o;  // same association as the scalar kernel: gamma * (z - mean) * invstd + beta
+        o.x = fmaxf(ga.x * (v.x - mu.x) * is.x + be.x, 0.f);
+        o.y = fmaxf(ga.y * (v.y - mu.y) * is.y + be.y, 0.f);
+        o.z = fmaxf(ga.z * (v.z - mu.z) * is.z + be.z, 0.f);
+        o.w = fmaxf(ga.w * (v.w - mu.w) * is.w + be.w, 0.f);
+        y[r * m.G + m.cg] = o;
+    }
+}
+
+// ReLU backward + xhat (in place) AND the two BatchNorm-backward sums in the same pass:
+//     dy <- dz = dy * (y > 0),  z <- xhat = (z - mean) * invstd,  sum_dz[c] += dz,  sum_dzx[c] += dz * xhat
+__global__ void __launch_bounds__(kTrThreads)
+train_relu_bwd_xhat4_kernel(float4 *__restrict__ dy, const float4 *__restrict__ y, float4 *__restrict__ z, long long rows, int C,
+                            int rows_per_cta, const float4 *__restrict__ mean, const float4 *__restrict__ invstd,
+                            float *__restrict__ sum_dz, float *__restrict__ sum_dzx) {
+    __shared__ float red[kTrThreads][4];
+    const ColMap m(C);
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    if (m.active) {
+        const float4 mu = __ldg(mean + m.cg), is = __ldg(invstd + m.cg);
+        for (long long r = r0 + m.rr; r < r1; r += m.R) {
+            const long long i = r * m.G + m.cg;
+            float4 d = dy[i], x = z[i];
+            const float4 yy = __ldg(y + i);
+            d.x = yy.x > 0.f ? d.x : 0.f; d.y = yy.y > 0.f ? d.y : 0.f; d.z = yy.z > 0.f ? d.z : 0.f; d.w = yy.w > 0.f ? d.w : 0.f;
+            x.x = (x.x - mu.x) * is.x; x.y = (x.y - mu.y) * is.y; x.z = (x.z - mu.z) * is.z; x.w = (x.w - mu.w) * is.w;
+            dy[i] = d;
+            z[i] = x;
+            t0.x += d.x; t0.y += d.y; t0.z += d.z; t0.w += d.w;
+            t1.x = fmaf(d.x, x.x, t1.x); t1.y = fmaf(d.y, x.y, t1.y); t1.z = fmaf(d.z, x.z, t1.z); t1.w = fmaf(d.w, x.w, t1.w);
+        }
+    }
+    if (sum_dz) {
+        col_reduce_store(m, C, t0, red, sum_dz);
+        col_reduce_store(m, C, t1, red, sum_dzx);
+    }
+}
+
+__global__ void __launch_bounds__(kTrThreads)
+train_bn_bwd4_kernel(const float4 *__restrict__ dz, const float4 *__restrict__ xhat, long long rows, int C, int rows_per_cta,
+                     float inv_rows, const float4 *__restrict__ gamma, const float4 *__restrict__ invstd,
+                     const float4 *__restrict__ sum_dz, const float4 *__restrict__ sum_dzx, float4 *__restrict__ dzpre) {
+    const ColMap m(C);
+    if (!m.active) return;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    const float4 ga = __ldg(gamma + m.cg), is = __ldg(invstd + m.cg), sd = __ldg(sum_dz + m.cg), sx = __ldg(sum_dzx + m.cg);
+    for (long long r = r0 + m.rr; r < r1; r += m.R) {
+        const long long i = r * m.G + m.cg;
+        const float4 d = __ldg(dz + i), x = __ldg(xhat + i);
+        float4 o;
+        o.x = ga.x * is.x * (d.x - inv_rows * (sd.x + x.x * sx.x));
+        o.y = ga.y * is.y * (d.y - inv_rows * (sd.y + x.y * sx.y));
+        o.z = ga.z * is.z * (d.z - inv_rows * (sd.z + x.z * sx.z));
+        o.w = ga.w * is.w * (d.w - inv_rows * (sd.w + x.w * sx.w));
+        dzpre[i] = o;
+    }
+}
+
+// weight gradient, register-tiled: one CTA = a slab of rows x a 64 (outputs) x 32 (inputs) tile of dW; 64 rows at a
+// time are staged in shared memory with 128-bit loads; thread = 4 x 4 outputs over half of the staged rows (two
+// 128-bit shared loads per 16 FMAs); db[o] += sum_r dz[r, o] rides along (the i-tile 0 CTAs).  Needs Cout % 4 == 0,
+// c1 % 4 == 0, c2 % 4 == 0, ld1 % 4 == 0, ld2 % 4 == 0.
+constexpr int kWgRows = 64, kWgTO = 64, kWgTI = 32;
+__global__ void __launch_bounds__(kTrThreads)
+train_wgrad4_kernel(const float *__restrict__ dz, int Cout, const float *__restrict__ in1, int ld1, int c1,
+                    const float *__restrict__ in2, int ld2, int c2, long long rows, int rows_per_cta, float *__restrict__ dW,
+                    float *__restrict__ db) {
+    __shared__ __align__(16) float sd[kWgRows][kWgTO + 4];
+    __shared__ __align__(16) float sx[kWgRows][kWgTI + 4];
+    const int Kin = c1 + c2;
+    const int o0 = blockIdx.y * kWgTO, i0 = blockIdx.z * kWgTI;
+    const int to_n = min(kWgTO, Cout - o0) >> 2, ti_n = min(kWgTI, Kin - i0) >> 2;  // float4 groups in this tile
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    const int t = threadIdx.x, half = t >> 7, ti = t & 7, to = (t & 127) >> 3;
+    const bool worker = to < to_n && ti < ti_n;
+    const bool want_db = db != nullptr && blockIdx.z == 0;
+    float acc[4][4];
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+    for (long long rb = r0; rb < r1; rb += kWgRows) {
+        const int nrow = (int)min((long long)kWgRows, r1 - rb);
+        for (int q = t; q < kWgRows * to_n; q += kTrThreads) {
+            const int j = q / to_n, g = q % to_n;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < nrow) v = __ldg(reinterpret_cast<const float4 *>(dz + (rb + j) * Cout + o0) + g);
+            *reinterpret_cast<float4 *>(&sd[j][4 * g]) = v;
+        }
+        for (int q = t; q < kWgRows * ti_n; q += kTrThreads) {
+            const int j = q / ti_n, g = q % ti_n;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < nrow) {
+                const int ii = i0 + 4 * g;
+                v = ii < c1 ? __ldg(reinterpret_cast<const float4 *>(in1 + (rb + j) * ld1 + ii))
+                            : __ldg(reinterpret_cast<const float4 *>(in2 + (rb + j) * ld2 + (ii - c1)));
+            }
+            *reinterpret_cast<float4 *>(&sx[j][4 * g]) = v;
+        }
+        __syncthreads();
+        if (worker) {
+            const int j0 = half * (kWgRows / 2);
+#pragma unroll 8
+            for (int j = j0; j < j0 + kWgRows / 2; j++) {
+                const float4 d = *reinterpret_cast<const float4 *>(&sd[j][4 * to]);
+                const float4 x = *reinterpret_cast<const float4 *>(&sx[j][4 * ti]);
+                const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+                    if (ti == 0) bsum[a] += dv[a];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (worker) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) atomicAdd(dW + (size_t)(o0 + 4 * to + a) * Kin + i0 + 4 * ti + b, acc[a][b]);
+            if (want_db && ti == 0) atomicAdd(db + o0 + 4 * to + a, bsum[a]);
+        }
+    }
+}
+
 // gather backward: dtable[rowidx[e], 4 + c] += dxf[e, c]
 __global__ void __launch_bounds__(kTrThreads)
 train_scatter_add_kernel(const float *__restrict__ dxf, const int *__restrict__ rowidx, long long edges, int Cin, int row_w,
@@ -190,6 +395,16 @@ train_scatter_add_kernel(const float *__restrict__ dxf, const int *__restrict__ 
     }
 }
 
+static bool col4_ok(int C, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr) {
+    auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return C % 4 == 0 && C <= 1024 && al(a) && al(b) && al(c) && al(d);
+}
+// slabs of rows for the float4 kernels: about 4 CTAs per SM, at least one sweep of R rows each
+static int col4_rows_per_cta(long long rows, int C) {
+    const int R = kTrThreads / (C / 4);
+    const long long per = (rows + 148 * 4 - 1) / (148 * 4);
+    return (int)max((long long)max(R, 1) * 4, per);
+}
 static int tr_blocks(long long n) { return (int)max(1LL, min((n + kTrThreads - 1) / kTrThreads, 148LL * 16)); }
 
 }  // namespace gg
@@ -214,8 +429,27 @@ int gridgcn_train_edge_rows(const float *table, const int *nebidx, const float *
 int gridgcn_train_col_sums(const float *a, const float *b, long long rows, int C, float *s0, float *s1, void *stream) {
     if (!a || !s0 || rows < 0 || C < 1) return GRIDGCN_EINVAL;
     if (rows == 0) return 0;
+    if (col4_ok(C, a, b)) {
+        const int per4 = col4_rows_per_cta(rows, C);
+        const int nb = (int)((rows + per4 - 1) / per4);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b);
+        if (b && s1) train_col_sums4_kernel<true, true><<<nb, kTrThreads, 0, st>>>(a4, b4, rows, C, per4, s0, s1);
+        else if (b) train_col_sums4_kernel<true, false><<<nb, kTrThreads, 0, st>>>(a4, b4, rows, C, per4, s0, s1);
+        else if (s1) train_col_sums4_kernel<false, true><<<nb, kTrThreads, 0, st>>>(a4, b4, rows, C, per4, s0, s1);
+        else train_col_sums4_kernel<false, false><<<nb, kTrThreads, 0, st>>>(a4, b4, rows, C, per4, s0, s1);
+        return (int)cudaGetLastError();
+    }
     const int per = (int)max(64LL, (rows + 148 * 8 - 1) / (148 * 8));
     train_col_sums_kernel<<<(int)((rows + per - 1) / per), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, b, rows, C, per, s0, s1);
+    return (int)cudaGetLastError();
+}
+
+int gridgcn_train_bn_finalize(const float *s0, const float *s1, long long rows, int C, float eps, float momentum, float *mean,
+                              float *invstd, float *running_mean, float *running_var, void *stream) {
+    if (!s0 || !s1 || !mean || !invstd || rows < 1 || C < 1) return GRIDGCN_EINVAL;
+    train_bn_finalize_kernel<<<(C + kTrThreads - 1) / kTrThreads, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        s0, s1, (float)rows, C, eps, momentum, mean, invstd, running_mean, running_var);
     return (int)cudaGetLastError();
 }
 
@@ -223,21 +457,49 @@ int gridgcn_train_bn_relu_fwd(const float *z, long long rows, int C, const float
                               const float *gamma, const float *beta, float *y, void *stream) {
     if (!z || !mean || !invstd || !gamma || !beta || !y || rows < 0 || C < 1) return GRIDGCN_EINVAL;
     if (rows == 0) return 0;
+    if (col4_ok(C, z, y) && col4_ok(C, mean, invstd, gamma, beta)) {
+        const int per4 = col4_rows_per_cta(rows, C);
+        train_bn_relu_fwd4_kernel<<<(int)((rows + per4 - 1) / per4), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4 *>(z), rows, C, per4, reinterpret_cast<const float4 *>(mean),
+            reinterpret_cast<const float4 *>(invstd), reinterpret_cast<const float4 *>(gamma),
+            reinterpret_cast<const float4 *>(beta), reinterpret_cast<float4 *>(y));
+        return (int)cudaGetLastError();
+    }
     train_bn_relu_fwd_kernel<<<tr_blocks(rows * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(z, rows * C, C, mean, invstd, gamma, beta, y);
     return (int)cudaGetLastError();
 }
 
 int gridgcn_train_relu_bwd_xhat(float *dy, const float *y, float *z, long long rows, int C, const float *mean,
-                                const float *invstd, void *stream) {
+                                const float *invstd, float *sum_dz, float *sum_dzx, void *stream) {
     if (!dy || !y || !z || !mean || !invstd || rows < 0 || C < 1) return GRIDGCN_EINVAL;
+    if ((sum_dz == nullptr) != (sum_dzx == nullptr)) return GRIDGCN_EINVAL;
     if (rows == 0) return 0;
-    train_relu_bwd_xhat_kernel<<<tr_blocks(rows * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, z, rows * C, C, mean, invstd);
-    return (int)cudaGetLastError();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (col4_ok(C, dy, y, z) && col4_ok(C, mean, invstd)) {
+        const int per4 = col4_rows_per_cta(rows, C);
+        train_relu_bwd_xhat4_kernel<<<(int)((rows + per4 - 1) / per4), kTrThreads, 0, st>>>(
+            reinterpret_cast<float4 *>(dy), reinterpret_cast<const float4 *>(y), reinterpret_cast<float4 *>(z), rows, C, per4,
+            reinterpret_cast<const float4 *>(mean), reinterpret_cast<const float4 *>(invstd), sum_dz, sum_dzx);
+        return (int)cudaGetLastError();
+    }
+    train_relu_bwd_xhat_kernel<<<tr_blocks(rows * C), kTrThreads, 0, st>>>(dy, y, z, rows * C, C, mean, invstd);
+    int rc = (int)cudaGetLastError();
+    if (rc || !sum_dz) return rc;
+    rc = gridgcn_train_col_sums(dy, nullptr, rows, C, sum_dz, nullptr, stream);
+    return rc ? rc : gridgcn_train_col_sums(dy, z, rows, C, sum_dzx, nullptr, stream);
 }
 
 int gridgcn_train_bn_bwd(const float *dz, const float *xhat, long long rows, int C, const float *gamma, const float *invstd,
                          const float *sum_dz, const float *sum_dzx, float *dzpre, void *stream) {
     if (!dz || !xhat || !gamma || !invstd || !sum_dz || !sum_dzx || !dzpre || rows < 1 || C < 1) return GRIDGCN_EINVAL;
+    if (col4_ok(C, dz, xhat, dzpre) && col4_ok(C, gamma, invstd, sum_dz, sum_dzx)) {
+        const int per4 = col4_rows_per_cta(rows, C);
+        train_bn_bwd4_kernel<<<(int)((rows + per4 - 1) / per4), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4 *>(dz), reinterpret_cast<const float4 *>(xhat), rows, C, per4, 1.0f / (float)rows,
+            reinterpret_cast<const float4 *>(gamma), reinterpret_cast<const float4 *>(invstd),
+            reinterpret_cast<const float4 *>(sum_dz), reinterpret_cast<const float4 *>(sum_dzx), reinterpret_cast<float4 *>(dzpre));
+        return (int)cudaGetLastError();
+    }
     train_bn_bwd_kernel<<<tr_blocks(rows * C), kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         dz, xhat, rows * C, C, 1.0f / (float)rows, gamma, invstd, sum_dz, sum_dzx, dzpre);
     return (int)cudaGetLastError();
@@ -261,9 +523,22 @@ int gridgcn_train_pool_bwd(const float *dout, int ld_out, const float *F, const 
 }
 
 int gridgcn_train_wgrad(const float *dz, int Cout, const float *in1, int ld1, int c1, const float *in2, int ld2, int c2,
-                        long long rows, float *dW, void *stream) {
+                        long long rows, float *dW, float *db, void *stream) {
     if (!dz || !in1 || !dW || Cout < 1 || c1 < 1 || c2 < 0 || (c2 > 0 && !in2) || rows < 0) return GRIDGCN_EINVAL;
     if (rows == 0) return 0;
+    auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (Cout % 4 == 0 && c1 % 4 == 0 && c2 % 4 == 0 && ld1 % 4 == 0 && (c2 == 0 || ld2 % 4 == 0) && al(dz) && al(in1) && al(in2)) {
+        const int tiles = ((Cout + kWgTO - 1) / kWgTO) * ((c1 + c2 + kWgTI - 1) / kWgTI);
+        const long long want = max(1LL, (148LL * 4) / tiles);  // about 4 CTAs per SM over all tiles
+        const int per4 = (int)max((long long)kWgRows, ((rows + want - 1) / want + kWgRows - 1) / kWgRows * kWgRows);
+        dim3 grid4((unsigned)((rows + per4 - 1) / per4), (unsigned)((Cout + kWgTO - 1) / kWgTO), (unsigned)((c1 + c2 + kWgTI - 1) / kWgTI));
+        train_wgrad4_kernel<<<grid4, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dz, Cout, in1, ld1, c1, in2, ld2, c2, rows, per4, dW, db);
+        return (int)cudaGetLastError();
+    }
+    if (db) {
+        const int rc = gridgcn_train_col_sums(dz, nullptr, rows, Cout, db, nullptr, stream);
+        if (rc) return rc;
+    }
     const int per = (int)max(256LL, (rows + 148 * 2 - 1) / (148 * 2));
     dim3 grid((unsigned)((rows + per - 1) / per), (unsigned)((Cout + 31) / 32), (unsigned)((c1 + c2 + 31) / 32));
     train_wgrad_kernel<<<grid, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dz, Cout, in1, ld1, c1, in2, ld2, c2, rows, per, dW);

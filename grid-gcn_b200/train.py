@@ -18,6 +18,7 @@ two together.
 """
 import numpy as np
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -164,3 +165,92 @@ def train_step(model, optimizer, data, actual_numpoints, labels):
     shard.allreduce_gradients([p for p in model.parameters()])
     optimizer.step()
     return float(loss.detach())
+
+
+class GraphedTrainStep:
+    """The data-parallel training step replayed as CUDA graphs (the step is launch bound at the reference's batch
+    sizes: ~300 small kernels for 3 clouds of 81920 points).
+
+        graph 1:  zero the flat gradient bucket, forward, cross entropy, backward   (every p.grad is a VIEW of the bucket)
+        eager  :  ONE all-reduce of the bucket over torch.distributed (NCCL), world > 1 only
+        graph 2:  bucket /= world, optimizer.step()
+
+    Same arithmetic as ``train_step``.  Inputs are copied into static buffers before each replay; shapes are fixed at
+    construction.  Autograd graphs of earlier eager steps of the same model must be gone (``del loss``): their
+    AccumulateGrad nodes are tied to the stream they ran on and would invalidate the capture.  The caller must not call ``optimizer.zero_grad(set_to_none=True)`` afterwards (it would detach the
+    gradients from the bucket).  Warm-up iterations run on copies of the parameters / buffers / optimiser state, which
+    are restored before capture, so constructing this object does not train the model."""
+
+    def __init__(self, model, optimizer, data, actual_numpoints, labels, warmup=3):
+        if not data.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors")
+        self.model, self.optimizer = model, optimizer
+        self.data, self.num, self.labels = data.clone(), actual_numpoints.clone(), labels.clone()
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        self.bucket = torch.zeros(total, dtype=torch.float32, device=data.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.bucket[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.loss = None
+        model.train()
+        saved_model = {k: v.clone() for k, v in model.state_dict().items()}
+        saved_opt = _clone_state(optimizer.state_dict())
+        side = torch.cuda.Stream(device=data.device)
+        side.wait_stream(torch.cuda.current_stream(data.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._fwd_bwd()
+                self._reduce()
+                self._update()
+        torch.cuda.current_stream(data.device).wait_stream(side)
+        torch.cuda.synchronize(data.device)
+        self.loss = None  # drops the warm-up autograd graph (its AccumulateGrad nodes are tied to the warm-up stream)
+        with torch.no_grad():
+            model.load_state_dict(saved_model)
+        optimizer.load_state_dict(saved_opt)
+        self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g1):
+            self._fwd_bwd()
+        with torch.cuda.graph(self.g2, pool=self.g1.pool()):
+            self._update()
+        # capture executed nothing, but BatchNorm's python-side counters / moving statistics must match "no step yet"
+        with torch.no_grad():
+            model.load_state_dict(saved_model)
+
+    def _fwd_bwd(self):
+        self.bucket.zero_()
+        self.loss = F.cross_entropy(self.model(self.data, self.num), self.labels)
+        self.loss.backward()
+
+    def _reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM)
+
+    def _update(self):
+        if self.world > 1:
+            self.bucket.mul_(1.0 / self.world)
+        self.optimizer.step()
+
+    def __call__(self, data=None, actual_numpoints=None, labels=None):
+        """One step; returns the (static) loss tensor of this rank -- no host synchronisation."""
+        if data is not None:
+            self.data.copy_(data, non_blocking=True)
+        if actual_numpoints is not None:
+            self.num.copy_(actual_numpoints, non_blocking=True)
+        if labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+        self.g1.replay()
+        self._reduce()
+        self.g2.replay()
+        return self.loss.detach()
+
+
+def _clone_state(sd):
+    import copy
+    out = copy.deepcopy({k: v for k, v in sd.items() if k != "state"})
+    out["state"] = {k: {kk: (vv.clone() if torch.is_tensor(vv) else copy.deepcopy(vv)) for kk, vv in st.items()}
+                    for k, st in sd["state"].items()}
+    return out

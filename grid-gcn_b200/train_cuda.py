@@ -6,8 +6,9 @@ the backward run on hand-written CUDA kernels instead of PyTorch ops + autograd:
 
   * every 1x1 convolution of the forward (Z = X W^T + b) and every input gradient of the backward (dX = dZ W) is one
     launch of the persistent tcgen05 row GEMM (csrc/rowgemm_tc.cu, 3-pass tf32 = fp32-class accuracy);
-  * csrc/train_ops.cu holds the rest: edge rows + gather indices, per-channel batch statistics, normalise + ReLU,
-    max pool with arg-max, its routing backward, ReLU / BatchNorm backward, weight gradients, gather scatter-add.
+  * csrc/train_ops.cu holds the rest: edge rows + gather indices, per-channel batch statistics (+ moving statistics),
+    normalise + ReLU, max pool with arg-max, its routing backward, ReLU backward fused with the BatchNorm-backward
+    sums, BatchNorm backward, weight + bias gradients, gather scatter-add.
 
 ``torch.autograd.Function`` is only the seam that hands ``grad_output`` in and the parameter gradients out; PyTorch
 supplies device memory and the optimiser.  Supported: the segmentation flavour (localfdim 0, att_full off, two
@@ -34,14 +35,15 @@ def _gemm(x, w, b, relu):
     return gridconv.rowmlp(x, None, w, b, relu_out=relu, tc=True)
 
 
-def _col_sums(a, b=None, want_sq=False):
-    L = _lib.lib()
-    rows, C = a.shape
-    s0 = torch.zeros(C, dtype=torch.float32, device=a.device)
-    s1 = torch.zeros(C, dtype=torch.float32, device=a.device) if want_sq else None
-    _lib.check(L.gridgcn_train_col_sums(a.data_ptr(), b.data_ptr() if b is not None else None, rows, C, s0.data_ptr(),
-                                        s1.data_ptr() if s1 is not None else None, _stream(a)), "gridgcn_train_col_sums")
-    return (s0, s1) if want_sq else s0
+_ZEROS = {}
+
+
+def _zeros(n, dev):
+    """cached read-only zero vector (the bias of the backward GEMMs)"""
+    key = (n, str(dev))
+    if key not in _ZEROS:
+        _ZEROS[key] = torch.zeros(n, dtype=torch.float32, device=dev)
+    return _ZEROS[key]
 
 
 class _Fn(torch.autograd.Function):
@@ -69,16 +71,20 @@ class _Fn(torch.autograd.Function):
                 w, b, gamma, beta = params[4 * idx:4 * idx + 4]
                 wp = mod._pad_w(idx, w)                       # zero columns for the padded input layouts
                 z = _gemm(x, wp, b, False)
-                rows = z.shape[0]
-                s0, s1 = _col_sums(z, want_sq=True)
-                mean = s0 / rows
-                var = torch.clamp(s1 / rows - mean * mean, min=0.0)   # biased, as BatchNorm normalises with
-                invstd = torch.rsqrt(var + BN_EPS)
+                rows, Cout = z.shape
+                st = torch.zeros((4, Cout), dtype=torch.float32, device=dev)   # sum, sum of squares -> mean, invstd
+                mean, invstd = st[2], st[3]
+                _lib.check(L.gridgcn_train_col_sums(z.data_ptr(), None, rows, Cout, st[0].data_ptr(), st[1].data_ptr(),
+                                                    _stream(z)), "gridgcn_train_col_sums")
+                bn = mod._stages()[idx].bn   # biased variance normalises; the moving one is unbiased (torch convention)
+                _lib.check(L.gridgcn_train_bn_finalize(st[0].data_ptr(), st[1].data_ptr(), rows, Cout, BN_EPS, float(bn.momentum),
+                                                       mean.data_ptr(), invstd.data_ptr(), bn.running_mean.data_ptr(),
+                                                       bn.running_var.data_ptr(), _stream(z)), "gridgcn_train_bn_finalize")
+                bn.num_batches_tracked += 1
                 y = torch.empty_like(z)
-                _lib.check(L.gridgcn_train_bn_relu_fwd(z.data_ptr(), rows, z.shape[1], mean.data_ptr(), invstd.data_ptr(),
+                _lib.check(L.gridgcn_train_bn_relu_fwd(z.data_ptr(), rows, Cout, mean.data_ptr(), invstd.data_ptr(),
                                                        gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _stream(z)),
                            "gridgcn_train_bn_relu_fwd")
-                mod._update_running(idx, mean, var, rows)
                 saved.append((x, z, y, mean, invstd))
                 return y
 
@@ -124,27 +130,28 @@ class _Fn(torch.autograd.Function):
                 x, z, y, mean, invstd = saved[idx]
                 w, b, gamma, beta = params[4 * idx:4 * idx + 4]
                 rows, Cout = z.shape
-                # dy <- dz = dy * (y > 0);  z <- xhat
+                # dy <- dz = dy * (y > 0);  z <- xhat;  per-channel sum dz, sum dz * xhat in the same pass
+                sums = torch.zeros((2, Cout), dtype=torch.float32, device=dev)
+                sum_dz, sum_dzx = sums[0], sums[1]
                 _lib.check(L.gridgcn_train_relu_bwd_xhat(dy.data_ptr(), y.data_ptr(), z.data_ptr(), rows, Cout, mean.data_ptr(),
-                                                         invstd.data_ptr(), _stream(dy)), "gridgcn_train_relu_bwd_xhat")
-                sum_dz = _col_sums(dy)
-                sum_dzx = _col_sums(dy, z)
+                                                         invstd.data_ptr(), sum_dz.data_ptr(), sum_dzx.data_ptr(), _stream(dy)),
+                           "gridgcn_train_relu_bwd_xhat")
                 dzpre = torch.empty_like(dy)
                 _lib.check(L.gridgcn_train_bn_bwd(dy.data_ptr(), z.data_ptr(), rows, Cout, gamma.data_ptr(), invstd.data_ptr(),
                                                   sum_dz.data_ptr(), sum_dzx.data_ptr(), dzpre.data_ptr(), _stream(dy)),
                            "gridgcn_train_bn_bwd")
                 wp = mod._pad_w(idx, w)
-                dwp = torch.zeros_like(wp)
+                dwb = torch.zeros(wp.numel() + Cout, dtype=torch.float32, device=dev)   # dW | db
+                dwp, dbias = dwb[:wp.numel()].view_as(wp), dwb[wp.numel():]
                 _lib.check(L.gridgcn_train_wgrad(dzpre.data_ptr(), Cout, x.data_ptr(), x.stride(0), x.shape[1], None, 0, 0, rows,
-                                                 dwp.data_ptr(), _stream(dy)), "gridgcn_train_wgrad")
+                                                 dwp.data_ptr(), dbias.data_ptr(), _stream(dy)), "gridgcn_train_wgrad")
                 grads[4 * idx] = mod._unpad_w(idx, dwp).reshape(w.shape)
-                grads[4 * idx + 1] = _col_sums(dzpre)
+                grads[4 * idx + 1] = dbias
                 grads[4 * idx + 2] = sum_dzx   # d gamma
                 grads[4 * idx + 3] = sum_dz    # d beta
                 if not need_dx:
                     return None
-                zero_b = torch.zeros(wp.shape[1], dtype=torch.float32, device=dev)
-                return _gemm(dzpre, wp.t().contiguous(), zero_b, False)   # dX = dZ W
+                return _gemm(dzpre, wp.t().contiguous(), _zeros(wp.shape[1], dev), False)   # dX = dZ W
 
             if A is not None:
                 d = dA
@@ -195,14 +202,6 @@ class GridConvTrainCuda(GridConvTrain):
     def _unpad_w(self, idx, dwp):
         st = self._stages()[idx]
         return dwp[:, :st.weight.reshape(st.weight.shape[0], -1).shape[1]].contiguous()
-
-    def _update_running(self, idx, mean, var, rows):
-        bn = self._stages()[idx].bn
-        with torch.no_grad():  # torch.nn.BatchNorm2d convention (momentum weighs the NEW value; unbiased running variance)
-            m = bn.momentum
-            bn.running_mean.mul_(1 - m).add_(m * mean)
-            bn.running_var.mul_(1 - m).add_(m * var * (rows / max(rows - 1, 1)))
-            bn.num_batches_tracked += 1
 
     def forward(self, table, nebidx, cent, centmsk):
         if not self.training or not table.is_cuda:

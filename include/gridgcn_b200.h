@@ -160,8 +160,10 @@ int gridgcn_ball_knn_fwd(const float *unknown, const float *known, const int *do
 /*  `localfdim` = 3 puts the geo vector in front of the gathered features (:186-191), the        */
 /*  attention MLP has explicit widths (`n_att_stages` >= 2, the last one = C) and, with          */
 /*  `att_full`, its stages after the first also see the feature MLP's output ("next", :91-93) or */
-/*  its input ("last", :88-90).  These variants run in GRIDGCN_PRECISION_FP32 only (the tensor-  */
-/*  core kernels implement the segmentation block); the other precisions return GRIDGCN_ELIMIT. */
+/*  its input ("last", :88-90).  These variants run in GRIDGCN_PRECISION_FP32 (one fused CUDA-   */
+/*  core kernel) and GRIDGCN_PRECISION_TF32X3 (un-fused chain of tcgen05 row GEMMs over the edge  */
+/*  rows: size the workspace with gridgcn_gridconv_edge_workspace_bytes); GRIDGCN_PRECISION_TF32  */
+/*  returns GRIDGCN_ELIMIT for them.                                                             */
 /* ------------------------------------------------------------------------------------------ */
 #define GRIDGCN_MAX_STAGES 8
 
@@ -241,20 +243,25 @@ int gridgcn_train_edge_rows(const float *table, const int *nebidx, const float *
                             int K, int attfdim, float *xf, float *xa, int *rowidx, void *stream);
 /* s0[c] += sum_r a[r,c] * (b ? b[r,c] : 1);  s1[c] += sum_r a[r,c]^2 (s1 may be NULL); zero them first */
 int gridgcn_train_col_sums(const float *a, const float *b, long long rows, int C, float *s0, float *s1, void *stream);
+/* mean = s0 / rows, invstd = rsqrt(max(s1 / rows - mean^2, 0) + eps); moving statistics (may be NULL) updated as   */
+/* running = (1 - momentum) * running + momentum * new, variance unbiased (torch.nn.BatchNorm convention)            */
+int gridgcn_train_bn_finalize(const float *s0, const float *s1, long long rows, int C, float eps, float momentum, float *mean,
+                              float *invstd, float *running_mean, float *running_var, void *stream);
 int gridgcn_train_bn_relu_fwd(const float *z, long long rows, int C, const float *mean, const float *invstd,
                               const float *gamma, const float *beta, float *y, void *stream);
-/* in place: dy <- dy * (y > 0), z <- (z - mean) * invstd */
+/* in place: dy <- dz = dy * (y > 0), z <- xhat = (z - mean) * invstd; when sum_dz / sum_dzx are given (both or    */
+/* neither; zero them first) the same pass adds sum_r dz and sum_r dz * xhat per channel (BatchNorm backward)       */
 int gridgcn_train_relu_bwd_xhat(float *dy, const float *y, float *z, long long rows, int C, const float *mean,
-                                const float *invstd, void *stream);
+                                const float *invstd, float *sum_dz, float *sum_dzx, void *stream);
 int gridgcn_train_bn_bwd(const float *dz, const float *xhat, long long rows, int C, const float *gamma, const float *invstd,
                          const float *sum_dz, const float *sum_dzx, float *dzpre, void *stream);
 int gridgcn_train_pool_fwd(const float *F, const float *A, long long centres, int K, int C, int pre_relu, const float *mask,
                            float *out, int ld_out, int *argmax, void *stream);
 int gridgcn_train_pool_bwd(const float *dout, int ld_out, const float *F, const float *A, const int *argmax, const float *mask,
                            long long centres, int K, int C, float *dF, float *dA, void *stream);
-/* dW[o, i] += sum_r dz[r, o] * [in1 | in2][r, i]; zero dW first */
+/* dW[o, i] += sum_r dz[r, o] * [in1 | in2][r, i];  db[o] += sum_r dz[r, o] (db may be NULL); zero them first */
 int gridgcn_train_wgrad(const float *dz, int Cout, const float *in1, int ld1, int c1, const float *in2, int ld2, int c2,
-                        long long rows, float *dW, void *stream);
+                        long long rows, float *dW, float *db, void *stream);
 int gridgcn_train_scatter_add(const float *dxf, const int *rowidx, long long edges, int Cin, int row_w, float *dtable, void *stream);
 
 /* Self-test of the tcgen05 primitives (not an operator): D[128,N] = A[128,K] * B[N,K]^T on one CTA,

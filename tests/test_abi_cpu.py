@@ -103,8 +103,9 @@ def test_missing_library_fails_loudly(gg, monkeypatch):
 
 
 def test_mlp_description_validation_without_gpu(gg):
-    """gridgcn_mlp_t: the classification-block fields are validated on the host; the tensor-core packing
-    refuses them, the fp32 path reports the activation scratch the wide layers need."""
+    """gridgcn_mlp_t: the classification-block fields are validated on the host; the tensor-core path takes them as an
+    un-fused chain of row GEMMs (its own packed image + per-edge workspace), the fp32 path reports the activation
+    scratch the wide layers need."""
     import ctypes
     L = gg._lib.lib()
 
@@ -123,9 +124,12 @@ def test_mlp_description_validation_without_gpu(gg):
     assert L.gridgcn_gridconv_packed_bytes(ctypes.byref(seg), 64) > 0
     assert L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(seg), 64, 64) == 0
     cls = desc([128, 128, 256], [128, 256, 256], 128, localfdim=3, att_full=1)
-    assert L.gridgcn_gridconv_packed_bytes(ctypes.byref(cls), 128) == 0          # tensor cores: seg block only
+    L.gridgcn_gridconv_edge_workspace_bytes.restype = ctypes.c_size_t
+    assert L.gridgcn_gridconv_packed_bytes(ctypes.byref(cls), 128) > 0           # tensor cores: chain of row GEMMs
+    assert L.gridgcn_gridconv_edge_workspace_bytes(ctypes.byref(cls), 4, 128, 128, 64) > 0
+    assert L.gridgcn_gridconv_edge_workspace_bytes(ctypes.byref(seg), 4, 64, 128, 64) == 0  # fused kernels: none
     assert L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(cls), 128, 64) > 0  # too wide for shared memory
-    assert L.gridgcn_gridconv_pack(ctypes.byref(cls), 128, 16, 1 << 30, None) == -2
+    assert L.gridgcn_gridconv_pack(ctypes.byref(cls), 128, None, 0, None) == -3  # GRIDGCN_EWORKSPACE: no buffer
     bad = desc([64, 128], [32, 64], 16, att_full=1)  # last attention width must equal the feature width
     assert L.gridgcn_gridconv_fp32_scratch_bytes(ctypes.byref(bad), 16, 8) == 0
     assert L.gridgcn_gridconv_fwd(16, 16, 16, 16, 1, 8, 16, 4, 8, ctypes.byref(bad), 0, None, None, 0, 16, None) == -1

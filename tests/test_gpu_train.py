@@ -116,3 +116,34 @@ def test_training_step_on_cuda_kernels(gg, cuda_dev):
     labels = torch.arange(8, device=cuda_dev) % 4
     losses = [train.train_step(model, opt, d, n, labels) for _ in range(30)]
     assert losses[-1] < 0.5 * losses[0], losses[::5]
+
+
+@pytest.mark.parametrize("block", ["cuda", "torch"])
+def test_graphed_train_step_matches_eager(gg, cuda_dev, block):
+    """train.GraphedTrainStep (forward + backward and the update replayed as CUDA graphs, gradients in one flat bucket)
+    is the same arithmetic as train.train_step: after 5 SGD steps from the same start the parameters, the BatchNorm
+    moving statistics and the losses agree (1e-4: the weight-gradient kernels sum with atomics), and constructing the
+    graphed step does not move the parameters."""
+    cfg = stack.tiny(8)
+    data, npts = synth.make_batch(8, cfg.num_points, seed0=40, voxels=cfg.voxels)
+    d, n = torch.from_numpy(data).to(cuda_dev), torch.from_numpy(npts).to(cuda_dev)
+    labels = torch.arange(8, device=cuda_dev) % 4
+
+    def make():
+        torch.manual_seed(0)
+        m = train.GridGcnClassifier(cfg, stack.init_params(cfg, seed=2), num_classes=4, block=block).to(cuda_dev)
+        return m, torch.optim.SGD(m.parameters(), lr=1e-2)
+
+    m0, o0 = make()
+    eager = [train.train_step(m0, o0, d, n, labels) for _ in range(5)]
+    m1, o1 = make()
+    before = {k: v.clone() for k, v in m1.state_dict().items()}
+    step = train.GraphedTrainStep(m1, o1, d, n, labels)
+    for k, v in m1.state_dict().items():
+        assert torch.equal(v, before[k]), "construction changed " + k
+    graphed = [float(step(d, n, labels)) for _ in range(5)]
+    assert np.allclose(graphed, eager, rtol=1e-4, atol=1e-6), (graphed, eager)
+    s0, s1 = m0.state_dict(), m1.state_dict()
+    for k in s0:
+        a, b = s0[k].float().cpu().numpy(), s1[k].float().cpu().numpy()
+        assert _rel_err(b, a) <= 1e-4, k
