@@ -315,52 +315,74 @@ train_bn_bwd4_kernel(const float4 *__restrict__ dz, const float4 *__restrict__ x
 }
 
 // weight gradient, register-tiled: one CTA = a slab of rows x a 64 (outputs) x 32 (inputs) tile of dW; 64 rows at a
-// time are staged in shared memory with 128-bit loads; thread = 4 x 4 outputs over half of the staged rows (two
-// 128-bit shared loads per 16 FMAs); db[o] += sum_r dz[r, o] rides along (the i-tile 0 CTAs).  Needs Cout % 4 == 0,
-// c1 % 4 == 0, c2 % 4 == 0, ld1 % 4 == 0, ld2 % 4 == 0.
+// time go through shared memory (128-bit loads, the NEXT block's loads are in flight in registers while the current one
+// is multiplied); thread = 4 x 4 outputs over every S-th staged row, S = 256 / (4x4 tiles in this dW tile) row groups;
+// the row groups are summed in shared memory, then one atomicAdd per output and CTA.  db[o] += sum_r dz[r, o] rides
+// along (the i-tile 0 CTAs).  Needs Cout, c1, c2, ld1, ld2 multiples of 4 and 16-byte aligned pointers.
 constexpr int kWgRows = 64, kWgTO = 64, kWgTI = 32;
 __global__ void __launch_bounds__(kTrThreads)
 train_wgrad4_kernel(const float *__restrict__ dz, int Cout, const float *__restrict__ in1, int ld1, int c1,
                     const float *__restrict__ in2, int ld2, int c2, long long rows, int rows_per_cta, float *__restrict__ dW,
                     float *__restrict__ db) {
-    __shared__ __align__(16) float sd[kWgRows][kWgTO + 4];
-    __shared__ __align__(16) float sx[kWgRows][kWgTI + 4];
+    __shared__ __align__(16) float wg_smem[kWgRows * (kWgTO + 4) + kWgRows * (kWgTI + 4)];  // 6656 floats
+    float (*sd)[kWgTO + 4] = reinterpret_cast<float (*)[kWgTO + 4]>(wg_smem);
+    float (*sx)[kWgTI + 4] = reinterpret_cast<float (*)[kWgTI + 4]>(wg_smem + kWgRows * (kWgTO + 4));
     const int Kin = c1 + c2;
     const int o0 = blockIdx.y * kWgTO, i0 = blockIdx.z * kWgTI;
     const int to_n = min(kWgTO, Cout - o0) >> 2, ti_n = min(kWgTI, Kin - i0) >> 2;  // float4 groups in this tile
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-    const int t = threadIdx.x, half = t >> 7, ti = t & 7, to = (t & 127) >> 3;
-    const bool worker = to < to_n && ti < ti_n;
+    const int t = threadIdx.x;
+    const int W = to_n * ti_n;                 // 4 x 4 register tiles in this dW tile (<= 128)
+    int S = 1;                                 // row groups: the largest power of two with W * S <= 256, at most 64
+    while (S < kWgRows && W * S * 2 <= kTrThreads) S *= 2;
+    const int w = t % W, sgrp = t / W;
+    const int ti = w % ti_n, to = w / ti_n;
+    const bool worker = sgrp < S;
     const bool want_db = db != nullptr && blockIdx.z == 0;
+    // staging map: thread t moves float4 #(t + 256 u) of the block; (row, group) fixed per u
+    float4 pd[4], px[2];
+    auto prefetch = [&](long long rb) {
+        const int nrow = (int)min((long long)kWgRows, r1 - rb);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int q = t + kTrThreads * u, j = q / to_n, g = q - j * to_n;
+            pd[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < kWgRows * to_n && j < nrow) pd[u] = __ldg(reinterpret_cast<const float4 *>(dz + (rb + j) * Cout + o0) + g);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int q = t + kTrThreads * u, j = q / ti_n, g = q - j * ti_n;
+            px[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < kWgRows * ti_n && j < nrow) {
+                const int ii = i0 + 4 * g;
+                px[u] = ii < c1 ? __ldg(reinterpret_cast<const float4 *>(in1 + (rb + j) * ld1 + ii))
+                                : __ldg(reinterpret_cast<const float4 *>(in2 + (rb + j) * ld2 + (ii - c1)));
+            }
+        }
+    };
     float acc[4][4];
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+    if (r0 < r1) prefetch(r0);
     for (long long rb = r0; rb < r1; rb += kWgRows) {
-        const int nrow = (int)min((long long)kWgRows, r1 - rb);
-        for (int q = t; q < kWgRows * to_n; q += kTrThreads) {
-            const int j = q / to_n, g = q % to_n;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < nrow) v = __ldg(reinterpret_cast<const float4 *>(dz + (rb + j) * Cout + o0) + g);
-            *reinterpret_cast<float4 *>(&sd[j][4 * g]) = v;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int q = t + kTrThreads * u, j = q / to_n, g = q - j * to_n;
+            if (q < kWgRows * to_n) *reinterpret_cast<float4 *>(&sd[j][4 * g]) = pd[u];
         }
-        for (int q = t; q < kWgRows * ti_n; q += kTrThreads) {
-            const int j = q / ti_n, g = q % ti_n;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < nrow) {
-                const int ii = i0 + 4 * g;
-                v = ii < c1 ? __ldg(reinterpret_cast<const float4 *>(in1 + (rb + j) * ld1 + ii))
-                            : __ldg(reinterpret_cast<const float4 *>(in2 + (rb + j) * ld2 + (ii - c1)));
-            }
-            *reinterpret_cast<float4 *>(&sx[j][4 * g]) = v;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int q = t + kTrThreads * u, j = q / ti_n, g = q - j * ti_n;
+            if (q < kWgRows * ti_n) *reinterpret_cast<float4 *>(&sx[j][4 * g]) = px[u];
         }
         __syncthreads();
+        if (rb + kWgRows < r1) prefetch(rb + kWgRows);
         if (worker) {
-            const int j0 = half * (kWgRows / 2);
-#pragma unroll 8
-            for (int j = j0; j < j0 + kWgRows / 2; j++) {
+#pragma unroll 4
+            for (int j = sgrp; j < kWgRows; j += S) {
                 const float4 d = *reinterpret_cast<const float4 *>(&sd[j][4 * to]);
                 const float4 x = *reinterpret_cast<const float4 *>(&sx[j][4 * ti]);
                 const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
@@ -368,19 +390,32 @@ train_wgrad4_kernel(const float *__restrict__ dz, int Cout, const float *__restr
                 for (int a = 0; a < 4; a++) {
 #pragma unroll
                     for (int b = 0; b < 4; b++) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
-                    if (ti == 0) bsum[a] += dv[a];
+                    bsum[a] += dv[a];
                 }
             }
         }
         __syncthreads();
     }
+    // sum the S row groups through shared memory (the staging buffers are free now: S * W * 20 <= 5120 floats)
+    float *red = wg_smem;
     if (worker) {
 #pragma unroll
         for (int a = 0; a < 4; a++) {
 #pragma unroll
-            for (int b = 0; b < 4; b++) atomicAdd(dW + (size_t)(o0 + 4 * to + a) * Kin + i0 + 4 * ti + b, acc[a][b]);
-            if (want_db && ti == 0) atomicAdd(db + o0 + 4 * to + a, bsum[a]);
+            for (int b = 0; b < 4; b++) red[(sgrp * W + w) * 20 + 4 * a + b] = acc[a][b];
+            red[(sgrp * W + w) * 20 + 16 + a] = bsum[a];
         }
+    }
+    __syncthreads();
+    for (int q = t; q < W * 20; q += kTrThreads) {
+        const int ww = q / 20, e = q - ww * 20;
+        float v = 0.f;
+        for (int g = 0; g < S; g++) v += red[(g * W + ww) * 20 + e];
+        const int wti = ww % ti_n, wto = ww / ti_n;
+        if (e < 16)
+            atomicAdd(dW + (size_t)(o0 + 4 * wto + (e >> 2)) * Kin + i0 + 4 * wti + (e & 3), v);
+        else if (want_db && wti == 0)
+            atomicAdd(db + o0 + 4 * wto + (e - 16), v);
     }
 }
 
@@ -529,7 +564,7 @@ int gridgcn_train_wgrad(const float *dz, int Cout, const float *in1, int ld1, in
     auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (Cout % 4 == 0 && c1 % 4 == 0 && c2 % 4 == 0 && ld1 % 4 == 0 && (c2 == 0 || ld2 % 4 == 0) && al(dz) && al(in1) && al(in2)) {
         const int tiles = ((Cout + kWgTO - 1) / kWgTO) * ((c1 + c2 + kWgTI - 1) / kWgTI);
-        const long long want = max(1LL, (148LL * 4) / tiles);  // about 4 CTAs per SM over all tiles
+        const long long want = max(1LL, (148LL * 3) / tiles);  // about 3 CTAs per SM over all tiles
         const int per4 = (int)max((long long)kWgRows, ((rows + want - 1) / want + kWgRows - 1) / kWgRows * kWgRows);
         dim3 grid4((unsigned)((rows + per4 - 1) / per4), (unsigned)((Cout + kWgTO - 1) / kWgTO), (unsigned)((c1 + c2 + kWgTI - 1) / kWgTI));
         train_wgrad4_kernel<<<grid4, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(dz, Cout, in1, ld1, c1, in2, ld2, c2, rows, per4, dW, db);
