@@ -50,13 +50,7 @@ __device__ __forceinline__ void voxel_segment(const CloudTable &t, const GridPar
 // weight is read into an `int`).  The terms are integers, so while sum|term| < 2^24 every partial
 // fp32 sum is exact and the order is immaterial: reduce exactly in int64.  Otherwise lane 0 redoes
 // the reference's sequential fp32 accumulation.
-__device__ __forceinline__ float weight_sum(const float4 *pts, const int *row, int n, int lane) {
-    long long s = 0, a = 0;
-    for (int i = lane; i < n; i += 32) {
-        int iw = (int)__ldg(&pts[row[i]].w);
-        s += iw;
-        a += iw < 0 ? -(long long)iw : iw;
-    }
+__device__ __forceinline__ float weight_finish(long long s, long long a, const float4 *pts, const int *row, int n, int lane) {
     // warp totals with two REDUX instructions: clamp the per-lane |.| sums to 2^24 (32 lanes: < 2^30); if
     // the clamped total is below 2^24 no lane was clamped, the total is exact and the signed sum fits
     const unsigned at = __reduce_add_sync(kFull, (unsigned)min(a, 1LL << 24));
@@ -67,6 +61,15 @@ __device__ __forceinline__ float weight_sum(const float4 *pts, const int *row, i
         for (int i = 0; i < n; i++) f = __fadd_rn(f, (float)(int)__ldg(&pts[row[i]].w));
     return __shfl_sync(kFull, f, 0);
 }
+__device__ __forceinline__ float weight_sum(const float4 *pts, const int *row, int n, int lane) {
+    long long s = 0, a = 0;
+    for (int i = lane; i < n; i += 32) {
+        int iw = (int)__ldg(&pts[row[i]].w);
+        s += iw;
+        a += iw < 0 ? -(long long)iw : iw;
+    }
+    return weight_finish(s, a, pts, row, n, lane);
+}
 
 __device__ __forceinline__ float4 center_row(const CloudTable &t, int o, int loc, float wsum) {
     float4 c = make_float4(1.f, 1.f, 1.f, wsum);  // loc==0: xyz keep the init value 1.0
@@ -75,6 +78,20 @@ __device__ __forceinline__ float4 center_row(const CloudTable &t, int o, int loc
         c.x = __fdiv_rn(a.x, a.w);
         c.y = __fdiv_rn(a.y, a.w);
         c.z = __fdiv_rn(a.z, a.w);
+    }
+    return c;
+}
+// the same row computed by lanes 0..2 in parallel (one IEEE division sequence per warp instead of three); every lane
+// must call, lane 0 ends up with the row
+__device__ __forceinline__ float4 center_row_warp(const CloudTable &t, int o, int loc, float wsum, int lane) {
+    float4 c = make_float4(1.f, 1.f, 1.f, wsum);
+    if (loc == 1) {
+        const float *a = reinterpret_cast<const float *>(t.cent_acc + o);
+        float q = 1.f;
+        if (lane < 3) q = __fdiv_rn(a[lane], a[3]);
+        c.x = q;
+        c.y = __shfl_sync(kFull, q, 1);
+        c.z = __shfl_sync(kFull, q, 2);
     }
     return c;
 }
@@ -410,7 +427,8 @@ __device__ __forceinline__ void bitonic_regs(unsigned (&v)[R], int lane) {
 template <int CAP>
 __device__ __forceinline__ bool knn_shell01_fast(const CloudTable &t, const GridParams &g, const float4 *pts, int c2,
                                                  int c1, int c0, float ux, float uy, float uz, int fma, int P, int ks,
-                                                 int lane, int *buf, int &found) {
+                                                 int lane, int *buf, int &found, long long &wsum_s, long long &wsum_a,
+                                                 bool &all_kept) {
     constexpr int R = CAP / 32;
     constexpr unsigned SEQM = (unsigned)CAP - 1u;
     // lane l looks up voxel tt: the centre voxel (shell 0, tt = 13) first, then the 26 of shell 1 in loop order
@@ -443,6 +461,9 @@ __device__ __forceinline__ bool knn_shell01_fast(const CloudTable &t, const Grid
                 const float dst = dist2(ux, uy, uz, q.x, q.y, q.z, fma);
                 key[r] = (__float_as_uint(dst) & ~SEQM) | (unsigned)f;
                 buf[CAP + f] = id;
+                const int iw = (int)q.w;  // weight of the candidate: the whole row's sum when every candidate is kept
+                wsum_s += iw;
+                wsum_a += iw < 0 ? -(long long)iw : iw;
             }
         }
     }
@@ -466,6 +487,7 @@ __device__ __forceinline__ bool knn_shell01_fast(const CloudTable &t, const Grid
         if (r * 32 + lane < total) buf[r * 32 + lane] = buf[CAP + (key[r] & SEQM)];
     __syncwarp();
     found = min(total, P);
+    all_kept = total <= P;
     return true;
 }
 
@@ -518,8 +540,12 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
         const float uy = (float)(((double)c1 + 0.5) * (double)g.voxel[1]);
         const float uz = (float)(((double)c2 + 0.5) * (double)g.voxel[2]);
         int found = 0;
+        long long wsum_s = 0, wsum_a = 0;  // per-lane weight sums over ALL candidates of the fast path
+        bool all_kept = false;             // ... which are the row's weights when no candidate was dropped
         int *ids = reinterpret_cast<int *>(s_keys[warp]);  // CAP 64-bit keys == 2 * CAP ints
-        if (!(ks >= 3 && knn_shell01_fast<CAP>(t, g, pts, c2, c1, c0, ux, uy, uz, fma, P, ks, lane, ids, found))) {
+        if (!(ks >= 3 && knn_shell01_fast<CAP>(t, g, pts, c2, c1, c0, ux, uy, uz, fma, P, ks, lane, ids, found, wsum_s,
+                                               wsum_a, all_kept))) {
+        all_kept = false;
         __syncwarp();
         TopP<CAP> tp{s_keys[warp], 0, (1u << idbits) - 1u, 0, false};
         int seq = 0, vbase = 0;
@@ -579,8 +605,9 @@ gridify_knn_query_kernel(const float4 *__restrict__ data, GridParams g,
             out_idx[s] = s < found ? ids[s] : pad;  // :308-310, :317-321
             out_msk[s] = 1.f;                       // :312 mask 1 on every slot
         }
-        float wsum = weight_sum(pts, ids, found, lane);
-        if (lane == 0) cent[ci] = center_row(t, o, g.loc, wsum);
+        const float wsum = all_kept ? weight_finish(wsum_s, wsum_a, pts, ids, found, lane) : weight_sum(pts, ids, found, lane);
+        const float4 crow = center_row_warp(t, o, g.loc, wsum, lane);
+        if (lane == 0) cent[ci] = crow;
         __syncwarp();
     }
 }
