@@ -74,11 +74,11 @@ struct EwCfg {
 
 template <int A0P>
 __global__ void __launch_bounds__(kEwThreads, 1)
-edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int log2k, int nchunk) {
+edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int log2k, int nchunk, int blocked) {
     using Cf = EwCfg<A0P>;
     constexpr int DA = Cf::DA, DI = Cf::DI, DD = Cf::DD;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bars[4 + 2 * DA + 2 * DI + 2 * DD + kEwRo];
+    __shared__ uint64_t bars[4 + 2 * DA + 2 * DI + 2 * DD + 2 * kEwRo];
     __shared__ uint32_t tmem_base_s;
     __shared__ float pair_max[4][32];  // K = 128: the second half's partial maxima
     uint64_t *x0_full = bars, *x0_free = bars + 2;             // G  -> MS (4); MS -> G (commit: the stage-0 MMAs have read X0)
@@ -86,6 +86,7 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
     uint64_t *e0_done = acc_free + DA, *img_free = e0_done + DI;  // E0 -> MA (4); MA -> E0 (commit)
     uint64_t *d_full = img_free + DI, *d_free = d_full + DD;    // MA -> EF (commit); EF -> MA (8)
     uint64_t *ro_free = d_free + DD;                            // EF -> G (8)
+    uint64_t *ro_full = ro_free + kEwRo;                        // G -> EF (4): row offsets of a unit are written
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const ConvParams &c = p.c;
     const int C = c.Cout;
@@ -98,7 +99,7 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
         for (int i = 0; i < DA; i++) { tc::mbar_init(&s0_done[i], 1); tc::mbar_init(&acc_free[i], 4); }
         for (int i = 0; i < DI; i++) { tc::mbar_init(&e0_done[i], 4); tc::mbar_init(&img_free[i], 1); }
         for (int i = 0; i < DD; i++) { tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_free[i], 8); }
-        for (int i = 0; i < kEwRo; i++) tc::mbar_init(&ro_free[i], 8);
+        for (int i = 0; i < kEwRo; i++) { tc::mbar_init(&ro_free[i], 8); tc::mbar_init(&ro_full[i], 4); }
         tc::mbar_init_fence();
     }
     {   // folded attention stage 0 as the K = 8 image W0[A0P x 8] (att0_folded_weight), bias of this chunk
@@ -143,10 +144,15 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
     __syncthreads();
     tc::fence_after_sync();
 
-    const int n_my = me < num_units ? (num_units - me + owners - 1) / owners : 0;
+    // units per owner: CONSECUTIVE units (blocked != 0: a CTA stays inside one cloud for many units, so the feature rows
+    // its EF warps gather are re-used out of L1 -- the gathers were L2-bandwidth bound, r02) or round-robin
+    const int u_base = num_units / owners, u_rem = num_units % owners;
+    const int u_first = blocked ? me * u_base + min(me, u_rem) : me;
+    const int u_step = blocked ? 1 : owners;
+    const int n_my = blocked ? u_base + (me < u_rem ? 1 : 0) : (me < num_units ? (num_units - me + owners - 1) / owners : 0);
     const unsigned centers_total = (unsigned)c.B * (unsigned)c.O;
     const int out_w = 4 + C;
-    auto unit_of = [&](int i) { return (unsigned)(me + i * owners); };
+    auto unit_of = [&](int i) { return (unsigned)(u_first + i * u_step); };
 
     if (warp < 4) {
         // =========================== G: gather ===========================
@@ -214,7 +220,10 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
             *reinterpret_cast<float4 *>(x0 + 3 * kEwPanel) = make_float4(lo[4], lo[5], lo[6], lo[7]);
             tc::fence_async_smem();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&x0_full[x]);  // (the row offsets reach EF through the later barriers of the chain)
+            if (lane == 0) {
+                tc::mbar_arrive(&x0_full[x]);
+                tc::mbar_arrive(&ro_full[ro.slot]);  // EF prefetches the feature rows of a unit ahead of its MMAs
+            }
             if (chunk == 0 && r < cpt * 4) {  // centre columns of the output rows: written by the chunk-0 owner
                 const unsigned center = unit_of(i) * (unsigned)cpt + (unsigned)(r >> 2);
                 if (center < centers_total)
@@ -276,29 +285,50 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
         float *out_ch = c.out + 4 + ch;
         const int kmask = (1 << log2k) - 1;
         EwRing<DD> dd;
-        EwRing<kEwRo> ro;
+        EwRing<kEwRo> rc;  // ring position of the current unit's row offsets
+        // The gathered features (this channel x the 64 edges of this half = four groups of 16 per unit) are prefetched TWO
+        // GROUPS AHEAD through a 32-register window: when group k has been consumed its registers are re-loaded with group
+        // k + 2 (of this unit, or groups 0 / 1 of the next one), so the L2 latency of the gather overlaps the compute of
+        // the group in between and the wait for the next unit's MMAs (before: four exposed round trips per unit, the
+        // kernel's bound -- r02 profile).
+        float f[32];
+        auto load_group = [&](const uint32_t *roff, int c0, int slot) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {  // coalesced over the warp (32 consecutive channels of one row)
+                const uint4 o4 = *reinterpret_cast<const uint4 *>(roff + c0 + j);
+                f[slot * 16 + j] = __ldg(fbase + o4.x); f[slot * 16 + j + 1] = __ldg(fbase + o4.y);
+                f[slot * 16 + j + 2] = __ldg(fbase + o4.z); f[slot * 16 + j + 3] = __ldg(fbase + o4.w);
+            }
+        };
+        if (n_my > 0) {
+            tc::mbar_wait(&ro_full[0], 0u);
+            const uint32_t *roff = reinterpret_cast<const uint32_t *>(smem + Cf::ro) + 64 * hh;
+            load_group(roff, 0, 0);
+            load_group(roff, 16, 1);
+        }
         for (int i = 0; i < n_my; i++) {
             const unsigned c_base = unit_of(i) * (unsigned)cpt;
+            const bool has_next = i + 1 < n_my;
+            EwRing<kEwRo> rn = rc;
+            rn.next();
             tc::mbar_wait(&d_full[dd.slot], dd.ph);
             tc::fence_after_sync();
+            if (has_next) tc::mbar_wait(&ro_full[rn.slot], rn.ph);
             const uint32_t taddr = tmem + lane_base + Cf::kDCol + (uint32_t)dd.slot * 128u + (uint32_t)(64 * hh);
-            const uint32_t *roff = reinterpret_cast<const uint32_t *>(smem + Cf::ro) + ro.slot * 128 + 64 * hh;
+            const uint32_t *roff_c = reinterpret_cast<const uint32_t *>(smem + Cf::ro) + rc.slot * 128 + 64 * hh;
+            const uint32_t *roff_n = reinterpret_cast<const uint32_t *>(smem + Cf::ro) + rn.slot * 128 + 64 * hh;
             float m = -3.402823466e+38f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                float f[16];
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {  // gathered features of 16 edges for this channel (coalesced over the warp)
-                    const uint4 o4 = *reinterpret_cast<const uint4 *>(roff + c0 + j);
-                    f[j] = __ldg(fbase + o4.x); f[j + 1] = __ldg(fbase + o4.y);
-                    f[j + 2] = __ldg(fbase + o4.z); f[j + 3] = __ldg(fbase + o4.w);
-                }
+            for (int k = 0; k < 4; k++) {
+                const int c0 = 16 * k, slot = k & 1;
                 uint32_t g[16];
                 tc::tmem_ld16(taddr + (uint32_t)c0, g);
                 tc::tmem_ld_wait();
                 float mm = -3.402823466e+38f;
 #pragma unroll
-                for (int j = 0; j < 16; j++) mm = fmaxf(mm, f[j] * fmaxf(__uint_as_float(g[j]) + ba, 0.f));  // :167 att * feats
+                for (int j = 0; j < 16; j++) mm = fmaxf(mm, f[slot * 16 + j] * fmaxf(__uint_as_float(g[j]) + ba, 0.f));  // :167 att * feats
+                if (k < 2) load_group(roff_c, c0 + 32, slot);
+                else if (has_next) load_group(roff_n, c0 - 32, slot);
                 m = fmaxf(m, mm);
                 const int e_end = 64 * hh + c0 + 16;
                 if (log2k <= 6 && (e_end & kmask) == 0) {
@@ -312,8 +342,9 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
             __syncwarp();
             if (lane == 0) {
                 tc::mbar_arrive(&d_free[dd.slot]);
-                tc::mbar_arrive(&ro_free[ro.slot]);
+                tc::mbar_arrive(&ro_free[rc.slot]);
             }
+            rc = rn;
             if (log2k == 7) {  // one centre per unit: the two 64-edge halves meet through shared memory
                 if (hh == 1) pair_max[q][lane] = m;
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)q) : "memory");
@@ -325,7 +356,6 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)q) : "memory");
             }
             dd.next();
-            ro.next();
         }
     } else if (lane == 0) {
         const uint32_t sb = tc::smem_u32(smem);
@@ -415,7 +445,8 @@ static int launch_edge_ws_t(const TcParams &p, cudaStream_t st, int sms) {
         attr_set.set(dev);
     }
     const long long owners = std::max<long long>(1, std::min<long long>(units, sms / nchunk));
-    edge_ws_kernel<A0P><<<(int)(owners * nchunk), kEwThreads, smem, st>>>(p, (int)units, cpt, log2k, nchunk);
+    static const int blocked = [] { const char *e = getenv("GRIDGCN_EDGE_WS_BLOCKED"); return e ? atoi(e) : 1; }();
+    edge_ws_kernel<A0P><<<(int)(owners * nchunk), kEwThreads, smem, st>>>(p, (int)units, cpt, log2k, nchunk, blocked);
     return (int)cudaGetLastError();
 }
 
