@@ -280,7 +280,6 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
         const int ch = chunk * 128 + chl;
         const bool chv = ch < C;
         const float ba = reinterpret_cast<const float *>(smem + Cf::bias)[chl];
-        const float pre_floor = c.pre_relu ? 0.f : -3.402823466e+38f;
         const float *fbase = p.ftab + (chv ? ch : 0);
         float *out_ch = c.out + 4 + ch;
         const int kmask = (1 << log2k) - 1;
@@ -326,7 +325,8 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
                 tc::tmem_ld_wait();
                 float mm = -3.402823466e+38f;
 #pragma unroll
-                for (int j = 0; j < 16; j++) mm = fmaxf(mm, f[slot * 16 + j] * fmaxf(__uint_as_float(g[j]) + ba, 0.f));  // :167 att * feats
+                for (int j = 0; j < 16; j++) mm = fmaxf(mm, f[slot * 16 + j] * (__uint_as_float(g[j]) + ba));  // :167 att * feats; the features
+                // are ReLU outputs (>= 0), so f * relu(a) == max(f * a, 0): the attention ReLU is applied once per centre below
                 if (k < 2) load_group(roff_c, c0 + 32, slot);
                 else if (has_next) load_group(roff_n, c0 - 32, slot);
                 m = fmaxf(m, mm);
@@ -334,7 +334,7 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
                 if (log2k <= 6 && (e_end & kmask) == 0) {
                     const unsigned center = c_base + (unsigned)((e_end >> log2k) - 1);
                     if (chv && center < centers_total)
-                        out_ch[(size_t)center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
+                        out_ch[(size_t)center * out_w] = fmaxf(m, 0.f) * __ldg(c.centmsk + center);
                     m = -3.402823466e+38f;
                 }
             }
@@ -351,7 +351,7 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
                 if (hh == 0) {
                     m = fmaxf(m, pair_max[q][lane]);
                     if (chv && c_base < centers_total)
-                        out_ch[(size_t)c_base * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + c_base);
+                        out_ch[(size_t)c_base * out_w] = fmaxf(m, 0.f) * __ldg(c.centmsk + c_base);
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)q) : "memory");
             }

@@ -448,7 +448,6 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
         const bool chv = ch < C;
         const float bf = chv ? __ldg(p.ff.bias + ch) : 0.f;
         const float bg = chv ? __ldg(p.a1.bias + ch) : 0.f;
-        const float pre_floor = c.pre_relu ? 0.f : -3.402823466e+38f;
         float *out_ch = c.out + 4 + ch;
         const int kmask = (1 << log2k) - 1;
         RingPos<kDF> f;
@@ -464,7 +463,9 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
                 float pr[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++)
-                    pr[j] = fmaxf(__uint_as_float(fv[j]) + bf, 0.f) * fmaxf(__uint_as_float(gv[j]) + bg, 0.f);  // :167 att * feats
+                    // :167 att * feats.  relu(F) >= 0, so relu(F) * relu(G) == max(relu(F) * G, 0): the attention ReLU is
+                    // hoisted out of the max over K (applied once per centre below)
+                    pr[j] = fmaxf(__uint_as_float(fv[j]) + bf, 0.f) * (__uint_as_float(gv[j]) + bg);
                 float mm = pr[0];
 #pragma unroll
                 for (int j = 1; j < 16; j++) mm = fmaxf(mm, pr[j]);
@@ -473,7 +474,7 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
                 if (log2k <= 5 && (e_end & kmask) == 0) {       // K <= 32: the centre lies inside this group's columns
                     const unsigned center = c_base + (unsigned)((e_end >> log2k) - 1);
                     if (chv && center < centers_total)
-                        out_ch[(size_t)center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
+                        out_ch[(size_t)center * out_w] = fmaxf(m, 0.f) * __ldg(c.centmsk + center);
                     m = -3.402823466e+38f;
                 }
             };
@@ -496,7 +497,7 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
                     if (log2k == 7) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));  // one centre per unit: both lane halves
                     const unsigned center = c_base + (log2k == 7 ? 0u : (unsigned)h);
                     if (chv && center < centers_total && (log2k == 6 || h == 0))
-                        out_ch[(size_t)center * out_w] = fmaxf(m, pre_floor) * __ldg(c.centmsk + center);
+                        out_ch[(size_t)center * out_w] = fmaxf(m, 0.f) * __ldg(c.centmsk + center);
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)q) : "memory");
             }
