@@ -23,7 +23,7 @@
 // 2 * A0p * C * 4 bytes of weights per unit.
 //
 // TMEM (512 columns): weights hi | lo (2 * A0p), stage-0 accumulator ring, D^T ring:
-//     A0p = 32:  64 + 2 x 32 + 3 x 128      A0p = 64:  128 + 2 x 64 + 2 x 128      A0p = 128:  256 + 1 x 128 + 1 x 128
+//     A0p = 32:  64 + 2 x 32 + 3 x 128      A0p = 64:  128 + 2 x 64 + 2 x 128      A0p = 128:  256 + 2 x 128 (S0 and D^T of a unit share a slot)
 #include "gridconv_tc.cuh"
 
 #include <algorithm>
@@ -61,11 +61,20 @@ __device__ __forceinline__ void ew_tmem_st8(uint32_t taddr, const float *v) {
 
 template <int A0P>
 struct EwCfg {
-    static constexpr int DA = A0P <= 64 ? 2 : 1;                   // stage-0 accumulator ring
+    // A0P = 128: the weights take 256 of the 512 columns; the stage-0 accumulator of a unit and its D^T tile then SHARE a
+    // 128-column slot (S0(u) is dead once E0 has turned ALL of it into the xa image -- MA(u) waits for both K halves
+    // before its first MMA overwrites the slot), which gives both rings depth 2: EF drains D^T(u) while the tensor core
+    // works on unit u + 1.
+    static constexpr bool kWide = A0P > 64;
+    static constexpr int DA = 2;                                   // stage-0 accumulator ring
     static constexpr int DI = A0P <= 32 ? 3 : (A0P <= 64 ? 2 : 1); // xa image ring
-    static constexpr int DD = A0P <= 32 ? 3 : (A0P <= 64 ? 2 : 1); // D^T ring
-    static constexpr uint32_t kWCol = 0, kAccCol = 2 * A0P, kDCol = 2 * A0P + DA * A0P;
+    static constexpr int DD = A0P <= 32 ? 3 : 2;                   // D^T ring
+    static constexpr uint32_t kWCol = 0, kAccCol = 2 * A0P, kAccStride = kWide ? 128 : A0P;
+    static constexpr uint32_t kDCol = kWide ? kAccCol : 2 * A0P + DA * A0P;
     static_assert(kDCol + DD * 128 <= 512, "TMEM map");
+    static constexpr int KH = kWide ? 2 : 1;   // the (single) xa image of A0P = 128 is handed over in two K halves: MA multiplies
+                                               // half 0 while E0 still writes half 1, and E0 starts the next unit's half 0
+                                               // as soon as MA has read this unit's (E0 and MA took ~3000 cycles EACH, in turn)
     static constexpr uint32_t kImgBytes = 2u * (A0P / 4) * kEwPanel;  // hi | lo
     // shared memory: W0 hi | lo, bias chunk, X0 ring, row-offset ring, xa ring
     static constexpr uint32_t w0_hi = 0, w0_lo = A0P * 32, bias = 2 * A0P * 32, x0 = (bias + 512 + 127) & ~127u;
@@ -78,13 +87,14 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
     using Cf = EwCfg<A0P>;
     constexpr int DA = Cf::DA, DI = Cf::DI, DD = Cf::DD;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bars[4 + 2 * DA + 2 * DI + 2 * DD + 2 * kEwRo];
+    __shared__ uint64_t bars[4 + 2 * DA + 2 * DI * Cf::KH + 2 * DD + 2 * kEwRo];
     __shared__ uint32_t tmem_base_s;
     __shared__ float pair_max[4][32];  // K = 128: the second half's partial maxima
     uint64_t *x0_full = bars, *x0_free = bars + 2;             // G  -> MS (4); MS -> G (commit: the stage-0 MMAs have read X0)
     uint64_t *s0_done = x0_free + 2, *acc_free = s0_done + DA;  // MS -> E0 (commit); E0 -> MS (4)
-    uint64_t *e0_done = acc_free + DA, *img_free = e0_done + DI;  // E0 -> MA (4); MA -> E0 (commit)
-    uint64_t *d_full = img_free + DI, *d_free = d_full + DD;    // MA -> EF (commit); EF -> MA (8)
+    constexpr int KH = Cf::KH;
+    uint64_t *e0_done = acc_free + DA, *img_free = e0_done + DI * KH;  // E0 -> MA (4); MA -> E0 (commit); per K half
+    uint64_t *d_full = img_free + DI * KH, *d_free = d_full + DD;    // MA -> EF (commit); EF -> MA (8)
     uint64_t *ro_free = d_free + DD;                            // EF -> G (8)
     uint64_t *ro_full = ro_free + kEwRo;                        // G -> EF (4): row offsets of a unit are written
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,7 +107,7 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
     if (tid == 32) {
         for (int i = 0; i < 2; i++) { tc::mbar_init(&x0_full[i], 4); tc::mbar_init(&x0_free[i], 1); }
         for (int i = 0; i < DA; i++) { tc::mbar_init(&s0_done[i], 1); tc::mbar_init(&acc_free[i], 4); }
-        for (int i = 0; i < DI; i++) { tc::mbar_init(&e0_done[i], 4); tc::mbar_init(&img_free[i], 1); }
+        for (int i = 0; i < DI * KH; i++) { tc::mbar_init(&e0_done[i], 4); tc::mbar_init(&img_free[i], 1); }
         for (int i = 0; i < DD; i++) { tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_free[i], 8); }
         for (int i = 0; i < kEwRo; i++) { tc::mbar_init(&ro_free[i], 8); tc::mbar_init(&ro_full[i], 4); }
         tc::mbar_init_fence();
@@ -240,35 +250,38 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
         EwRing<DA> a;
         EwRing<DI> d;
         for (int i = 0; i < n_my; i++) {
-            if (i >= DI) tc::mbar_wait(&img_free[d.slot], d.ph ^ 1u);
             tc::mbar_wait(&s0_done[a.slot], a.ph);
             tc::fence_after_sync();
-            const uint32_t taddr = tmem + lane_base + Cf::kAccCol + (uint32_t)a.slot * A0P;
+            const uint32_t taddr = tmem + lane_base + Cf::kAccCol + (uint32_t)a.slot * Cf::kAccStride;
             uint8_t *img = smem + Cf::img + (uint32_t)d.slot * Cf::kImgBytes + row_off;
 #pragma unroll 1
-            for (int c0 = 0; c0 < A0P; c0 += 16) {
-                uint32_t v[16];
-                tc::tmem_ld16(taddr + (uint32_t)c0, v);
-                tc::tmem_ld_wait();
+            for (int h = 0; h < KH; h++) {
+                if (i >= DI) tc::mbar_wait(&img_free[d.slot * KH + h], d.ph ^ 1u);
+#pragma unroll 1
+                for (int c0 = h * (A0P / KH); c0 < (h + 1) * (A0P / KH); c0 += 16) {
+                    uint32_t v[16];
+                    tc::tmem_ld16(taddr + (uint32_t)c0, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    float x[4], lo[4];
+                    for (int g = 0; g < 4; g++) {
+                        float x[4], lo[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        x[j] = fmaxf(__uint_as_float(v[4 * g + j]), 0.f);
-                        lo[j] = x[j] - __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
+                        for (int j = 0; j < 4; j++) {
+                            x[j] = fmaxf(__uint_as_float(v[4 * g + j]), 0.f);
+                            lo[j] = x[j] - __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
+                        }
+                        uint8_t *dst = img + (uint32_t)((c0 >> 2) + g) * kEwPanel;
+                        *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                        *reinterpret_cast<float4 *>(dst + (A0P / 4) * kEwPanel) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    uint8_t *dst = img + (uint32_t)((c0 >> 2) + g) * kEwPanel;
-                    *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-                    *reinterpret_cast<float4 *>(dst + (A0P / 4) * kEwPanel) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
-            }
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-                tc::mbar_arrive(&acc_free[a.slot]);
-                tc::mbar_arrive(&e0_done[d.slot]);
+                tc::fence_async_smem();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    if (h == KH - 1) tc::mbar_arrive(&acc_free[a.slot]);
+                    tc::mbar_arrive(&e0_done[d.slot * KH + h]);
+                }
             }
             a.next();
             d.next();
@@ -370,10 +383,13 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
             for (int i = 0; i < n_my; i++) {
                 const uint32_t x = (uint32_t)(i & 1);
                 tc::mbar_wait(&x0_full[x], (uint32_t)(i >> 1) & 1u);
-                if (i >= DA) tc::mbar_wait(&acc_free[a.slot], a.ph ^ 1u);
+                if (i >= DA) {
+                    if (Cf::kWide) tc::mbar_wait(&d_free[a.slot], a.ph ^ 1u);  // the slot's previous tenant: D^T(i - 2), drained by EF
+                    else tc::mbar_wait(&acc_free[a.slot], a.ph ^ 1u);
+                }
                 tc::fence_after_sync();
                 const uint64_t ah = adv(xh0, x * 4u * kEwPanel), al = adv(xl0, x * 4u * kEwPanel);
-                const uint32_t dacc = tmem + Cf::kAccCol + (uint32_t)a.slot * A0P;
+                const uint32_t dacc = tmem + Cf::kAccCol + (uint32_t)a.slot * Cf::kAccStride;
                 tc::mma_tf32(dacc, al, w0h, idesc, 0);
                 tc::mma_tf32(dacc, ah, w0l, idesc, 1);
                 tc::mma_tf32(dacc, ah, w0h, idesc, 1);
@@ -390,20 +406,25 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
             EwRing<DI> d;
             EwRing<DD> dd;
             for (int i = 0; i < n_my; i++) {
-                tc::mbar_wait(&e0_done[d.slot], d.ph);
                 if (i >= DD) tc::mbar_wait(&d_free[dd.slot], dd.ph ^ 1u);
-                tc::fence_after_sync();
                 uint64_t bh = adv(xh0, (uint32_t)d.slot * Cf::kImgBytes), bl = adv(xl0, (uint32_t)d.slot * Cf::kImgBytes);
                 const uint32_t dc = tmem + Cf::kDCol + (uint32_t)dd.slot * 128u;
 #pragma unroll 1
-                for (int ks = 0; ks < A0P / 8; ks++) {
-                    ew_mma_ts(dc, w_lo + (uint32_t)ks * 8u, bh, idesc, ks > 0);
-                    ew_mma_ts(dc, w_hi + (uint32_t)ks * 8u, bl, idesc, 1);
-                    ew_mma_ts(dc, w_hi + (uint32_t)ks * 8u, bh, idesc, 1);
-                    bh = adv(bh, 2u * kEwPanel); bl = adv(bl, 2u * kEwPanel);
+                for (int h = 0; h < KH; h++) {
+                    // (kWide: D^T shares the slot of S0 -- every K half must have left it before the first MMA)
+                    for (int hw = (Cf::kWide ? 0 : h); hw < (Cf::kWide ? (h == 0 ? KH : 0) : h + 1); hw++)
+                        tc::mbar_wait(&e0_done[d.slot * KH + hw], d.ph);
+                    tc::fence_after_sync();
+#pragma unroll 1
+                    for (int ks = h * (A0P / 8 / KH); ks < (h + 1) * (A0P / 8 / KH); ks++) {
+                        ew_mma_ts(dc, w_lo + (uint32_t)ks * 8u, bh, idesc, ks > 0);
+                        ew_mma_ts(dc, w_hi + (uint32_t)ks * 8u, bl, idesc, 1);
+                        ew_mma_ts(dc, w_hi + (uint32_t)ks * 8u, bh, idesc, 1);
+                        bh = adv(bh, 2u * kEwPanel); bl = adv(bl, 2u * kEwPanel);
+                    }
+                    tc::mma_commit(&img_free[d.slot * KH + h]);
                 }
                 tc::mma_commit(&d_full[dd.slot]);
-                tc::mma_commit(&img_free[d.slot]);
                 d.next();
                 dd.next();
             }
