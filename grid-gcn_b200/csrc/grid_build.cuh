@@ -18,6 +18,42 @@
 namespace gg {
 
 constexpr int kBuildThreads = 1024;
+// Segments (points of one voxel) longer than this are ranked by an ordered block scan over the cloud's points instead
+// of the per-point O(len) count: a degenerate cloud (every point in one voxel) would otherwise cost O(N^2).
+constexpr int kHeavySeg = 1024;
+constexpr int kMaxHeavy = 128;  // heavy voxels handled per cloud (N / kHeavySeg <= 128 up to N = 131072); more: quadratic path
+
+// Ranks the points of the heavy voxels of one cloud (called by all threads of a CTA).  key[i] = linear voxel of point i,
+// vend[c] = END offset of dense voxel c, tmp = unordered scatter; writes sorted[] and the first-occurrence bits.
+template <int THREADS, typename FirstFn>
+__device__ __forceinline__ void rank_heavy_segments(const int *key, const int *vend, const int *tmp, int *sorted, int nocc,
+                                                    int npts, int *scratch, int *heavy, int *nheavy, FirstFn mark_first) {
+    if (threadIdx.x == 0) *nheavy = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < nocc; c += THREADS) {
+        const int s = c ? vend[c - 1] : 0;
+        if (vend[c] - s > kHeavySeg) {
+            const int k = atomicAdd(nheavy, 1);
+            if (k < kMaxHeavy) heavy[k] = c;
+        }
+    }
+    __syncthreads();
+    const int nh = *nheavy;
+    if (nh > kMaxHeavy) return;  // (the per-point pass ranks everything itself in that case)
+    for (int h = 0; h < nh; h++) {
+        const int c = heavy[h];
+        const int s = c ? vend[c - 1] : 0;
+        const int lin = key[tmp[s]];
+        block_excl_scan<THREADS>(
+            npts, scratch, [&](int i) { return key[i] == lin ? 1 : 0; },
+            [&](int i, int v) {
+                if (key[i] == lin) {
+                    sorted[s + v] = i;
+                    if (v == 0) mark_first(i);
+                }
+            });
+    }
+}
 
 // Shared-memory budget of the build kernel in 32-bit words: bitmap + wordpfx + first-point bitmap
 // and its prefix + scan scratch, and (when the cloud fits) key/vend/tmp per point.
@@ -108,12 +144,19 @@ grid_build_kernel(const float4 *__restrict__ data, const int *__restrict__ npts_
     __syncthreads();
 
     // P6: rank sort inside each segment -> ascending ids; the segment minimum marks the voxel's
-    // first occurrence in point order
+    // first occurrence in point order.  Long segments first, by ordered scans (rank_heavy_segments).
+    __shared__ int heavy[kMaxHeavy];
+    __shared__ int nheavy;
+    rank_heavy_segments<THREADS>(key, vend, tmp, sorted, nocc, npts, scratch, heavy, &nheavy, [&](int i) {
+        if (want_centers) atomicOr(&firstmap[i >> 5], 1u << (i & 31));
+    });
+    const bool heavy_done = nheavy <= kMaxHeavy;
     for (int i = tid; i < npts; i += THREADS) {
         int lin = key[i];
         if (lin >= 0) {
             int c = dense_of(lin);
             int s = c ? vend[c - 1] : 0, e = vend[c];
+            if (heavy_done && e - s > kHeavySeg) continue;
             int r = 0;
             for (int j = s; j < e; j++) r += (tmp[j] < i);
             sorted[s + r] = i;

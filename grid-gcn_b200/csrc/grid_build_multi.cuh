@@ -104,11 +104,28 @@ bm_rank_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, WsL
         if (lin < 0) continue;
         const int c = bm_dense_of(ws, L, lin);
         const int s = c ? ws[L.vend + c - 1] : 0, e = ws[L.vend + c];
+        if (e - s > kHeavySeg && ws[0] > 0 && ws[1] <= kMaxHeavy) continue;  // ranked by bm_rank_heavy_kernel (ws[1] = its count)
         int r = 0;
         for (int q = s; q < e; q++) r += (ws[L.tmp + q] < j);
         ws[L.sorted + s + r] = j;
         if (r == 0 && want_centers) atomicOr(reinterpret_cast<unsigned *>(ws + L.firstmap + (j >> 5)), 1u << (j & 31));
     }
+}
+
+// one CTA per cloud: long segments ranked by ordered scans (grid_build.cuh rank_heavy_segments); header word 1 = number
+// of heavy voxels of the cloud (bm_rank_kernel skips them when the list did not overflow).  Runs BEFORE bm_rank_kernel.
+__global__ void __launch_bounds__(1024)
+bm_rank_heavy_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, WsLayout L, int want_centers) {
+    __shared__ int scratch[64];
+    __shared__ int heavy[kMaxHeavy];
+    __shared__ int nheavy;
+    const int b = blockIdx.x;
+    int *ws = ws_base + (size_t)b * L.stride;
+    rank_heavy_segments<1024>(ws + L.key, ws + L.vend, ws + L.tmp, ws + L.sorted, ws[0], bm_npts(npts_arr, b, g.N), scratch, heavy,
+                              &nheavy, [&](int i) {
+                                  if (want_centers) atomicOr(reinterpret_cast<unsigned *>(ws + L.firstmap + (i >> 5)), 1u << (i & 31));
+                              });
+    if (threadIdx.x == 0) ws[1] = nheavy;
 }
 
 // one CTA per cloud: first-point prefix; centre mask and count (gridify.cu:179, :222-224)

@@ -37,6 +37,7 @@
 #include "gridconv_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace gg {
 
@@ -1764,6 +1765,9 @@ static int launch_point_mlp_chain(const TcParams &p, cudaStream_t st) {
     for (int s = 0; s < c.n_feat; s++)
         if (c.cout[s] & 3) return -1;
     const long long rows = (long long)c.B * c.Nprev;
+    // GRIDGCN_POINT_MLP_CHAIN_MIN_ROWS: below this many source points the fused kernel-A variants run instead
+    static const long long min_rows = [] { const char *e = getenv("GRIDGCN_POINT_MLP_CHAIN_MIN_ROWS"); return e ? atoll(e) : 0LL; }();
+    if (rows < min_rows) return -1;
     int hmax = 0;
     for (int s = 0; s + 1 < c.n_feat; s++) hmax = std::max(hmax, c.cout[s]);
     float *tmp[2] = {p.ftab + rows * c.Cout, p.ftab + rows * ((long long)c.Cout + hmax)};

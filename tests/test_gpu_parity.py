@@ -93,6 +93,28 @@ def test_gridify_strict_reservoir_matches_oracle(gg, cuda_dev, oracle_mod, name,
             oracle_mod.gridify(data, npts, strict_reservoir=True, **kw), name + "/Gridify strict, weights")
 
 
+@pytest.mark.parametrize("N,frac", [(8192, 0.6), (8192, 1.0), (40000, 0.7)], ids=["smem_build", "all_in_one_voxel", "multi_kernel_build"])
+def test_dense_voxels_ranked_by_scans(gg, cuda_dev, oracle_mod, N, frac):
+    """Voxel segments longer than 1024 points (clustered / duplicated points) are ranked by ordered block scans instead
+    of the per-point count (grid_build.cuh rank_heavy_segments, both build paths): same table, bit-exact operators."""
+    data, npts = synth.make_batch(2, N, seed0=900, kind="ball", voxels=(0.1,))
+    rng = np.random.default_rng(5)
+    for b in range(2):
+        k = int(N * frac)
+        sel = rng.permutation(N)[:k]
+        data[b, sel, :3] = 0.033 * rng.random((k, 3)).astype(np.float32) + (0.31 if b == 0 else -0.47)  # inside one voxel
+        if frac == 1.0:
+            data[b, :, :3] = data[b, 0, :3]  # every point identical: exact ties everywhere
+    kw = dict(max_p_grid=64, max_o_grid=512, kernel_size=3, loc=1, coord_shift=(1.0, 1.0, 1.0), voxel_size=(0.1,) * 3,
+              grid_size=(20,) * 3)
+    d, n = _t(data, cuda_dev), _t(npts, cuda_dev)
+    _check5(gg.Gridify(d, n, stride=1, strict_reservoir=False, **kw), oracle_mod.gridify(data, npts, strict_reservoir=False, **kw),
+            "dense/Gridify")
+    _check5(gg.Gridify(d, n, stride=1, strict_reservoir=True, **kw), oracle_mod.gridify(data, npts, strict_reservoir=True, **kw),
+            "dense/Gridify strict")
+    _check5(gg.GridifyKNN(d, n, stride=1, **kw), oracle_mod.gridify_knn(data, npts, **kw), "dense/GridifyKNN")
+
+
 def test_edge_cases(gg, cuda_dev, oracle_mod):
     data, npts = synth.make_batch(3, 64, seed0=1)
     npts[0, 0] = 0
