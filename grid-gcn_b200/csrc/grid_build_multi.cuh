@@ -76,8 +76,15 @@ bm_count_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, Ws
 // one CTA per cloud: counts -> segment starts (cursors)
 __global__ void __launch_bounds__(1024) bm_scan_kernel(int *ws_base, WsLayout L) {
     __shared__ int scratch[64];
+    __shared__ int nheavy;
     int *ws = ws_base + (size_t)blockIdx.x * L.stride;
     const int nocc = ws[0];
+    if (threadIdx.x == 0) nheavy = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nocc; i += 1024)
+        if (ws[L.vend + i] > kHeavySeg) atomicAdd(&nheavy, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) ws[1] = nheavy;  // header word 1: long segments of this cloud (ranked by scans, see below)
     block_excl_scan<1024>(nocc, scratch, [&](int i) { return ws[L.vend + i]; }, [&](int i, int v) { ws[L.vend + i] = v; });
 }
 
@@ -104,7 +111,7 @@ bm_rank_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, WsL
         if (lin < 0) continue;
         const int c = bm_dense_of(ws, L, lin);
         const int s = c ? ws[L.vend + c - 1] : 0, e = ws[L.vend + c];
-        if (e - s > kHeavySeg && ws[0] > 0 && ws[1] <= kMaxHeavy) continue;  // ranked by bm_rank_heavy_kernel (ws[1] = its count)
+        if (e - s > kHeavySeg && ws[1] <= kMaxHeavy) continue;  // long segment: ranked by ordered scans (bm_rank_heavy)
         int r = 0;
         for (int q = s; q < e; q++) r += (ws[L.tmp + q] < j);
         ws[L.sorted + s + r] = j;
@@ -112,28 +119,34 @@ bm_rank_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, WsL
     }
 }
 
-// one CTA per cloud: long segments ranked by ordered scans (grid_build.cuh rank_heavy_segments); header word 1 = number
-// of heavy voxels of the cloud (bm_rank_kernel skips them when the list did not overflow).  Runs BEFORE bm_rank_kernel.
-__global__ void __launch_bounds__(1024)
-bm_rank_heavy_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, WsLayout L, int want_centers) {
-    __shared__ int scratch[64];
+// one CTA per cloud: long segments ranked by ordered scans (grid_build.cuh rank_heavy_segments); header word 1 (written
+// by bm_scan_kernel) = number of long segments of the cloud, bm_rank_kernel skips them when the list does not overflow.
+// Folded into bm_firstpfx_kernel when centres are wanted (one launch less); on its own otherwise.
+__device__ __forceinline__ void bm_rank_heavy(const int *__restrict__ npts_arr, const GridParams &g, int *ws, const WsLayout &L,
+                                              int b, int want_centers, int *scratch) {
     __shared__ int heavy[kMaxHeavy];
     __shared__ int nheavy;
-    const int b = blockIdx.x;
-    int *ws = ws_base + (size_t)b * L.stride;
+    if (ws[1] == 0) return;  // uniform over the CTA
     rank_heavy_segments<1024>(ws + L.key, ws + L.vend, ws + L.tmp, ws + L.sorted, ws[0], bm_npts(npts_arr, b, g.N), scratch, heavy,
                               &nheavy, [&](int i) {
                                   if (want_centers) atomicOr(reinterpret_cast<unsigned *>(ws + L.firstmap + (i >> 5)), 1u << (i & 31));
                               });
-    if (threadIdx.x == 0) ws[1] = nheavy;
+    __syncthreads();
+}
+__global__ void __launch_bounds__(1024)
+bm_rank_heavy_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, WsLayout L, int want_centers) {
+    __shared__ int scratch[64];
+    bm_rank_heavy(npts_arr, g, ws_base + (size_t)blockIdx.x * L.stride, L, blockIdx.x, want_centers, scratch);
 }
 
 // one CTA per cloud: first-point prefix; centre mask and count (gridify.cu:179, :222-224)
 __global__ void __launch_bounds__(1024)
-bm_firstpfx_kernel(GridParams g, int *ws_base, WsLayout L, float *__restrict__ centmsk, int *__restrict__ centnum) {
+bm_firstpfx_kernel(const int *__restrict__ npts_arr, GridParams g, int *ws_base, WsLayout L, float *__restrict__ centmsk,
+                   int *__restrict__ centnum) {
     __shared__ int scratch[64];
     const int b = blockIdx.x;
     int *ws = ws_base + (size_t)b * L.stride;
+    bm_rank_heavy(npts_arr, g, ws, L, b, 1, scratch);  // sets the first-occurrence bits of the long segments
     const int NW = (g.N + 31) / 32;
     block_excl_scan<1024>(
         NW, scratch, [&](int i) { return __popc((unsigned)ws[L.firstmap + i]); }, [&](int i, int v) { ws[L.firstpfx + i] = v; });

@@ -83,10 +83,10 @@ static cudaError_t launch_build_multi(const float *data, const int *npts, const 
     bm_count_kernel<<<blocks(BN), kBmThreads, 0, st>>>(npts, g, ws, L);
     bm_scan_kernel<<<g.B, 1024, 0, st>>>(ws, L);
     bm_scatter_kernel<<<blocks(BN), kBmThreads, 0, st>>>(npts, g, ws, L);
-    bm_rank_heavy_kernel<<<g.B, 1024, 0, st>>>(npts, g, ws, L, want_centers);
     bm_rank_kernel<<<blocks(BN), kBmThreads, 0, st>>>(npts, g, ws, L, want_centers);
+    if (!want_centers) bm_rank_heavy_kernel<<<g.B, 1024, 0, st>>>(npts, g, ws, L, 0);
     if (want_centers) {
-        bm_firstpfx_kernel<<<g.B, 1024, 0, st>>>(g, ws, L, centmsk, centnum);
+        bm_firstpfx_kernel<<<g.B, 1024, 0, st>>>(npts, g, ws, L, centmsk, centnum);
         bm_centers_kernel<<<blocks((long long)g.B * V), kBmThreads, 0, st>>>(d4, g, ws, L);
     }
     return cudaGetLastError();
