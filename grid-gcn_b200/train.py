@@ -178,8 +178,9 @@ class GraphedTrainStep:
     Same arithmetic as ``train_step``.  Inputs are copied into static buffers before each replay; shapes are fixed at
     construction.  Autograd graphs of earlier eager steps of the same model must be gone (``del loss``): their
     AccumulateGrad nodes are tied to the stream they ran on and would invalidate the capture.  The caller must not call ``optimizer.zero_grad(set_to_none=True)`` afterwards (it would detach the
-    gradients from the bucket).  Warm-up iterations run on copies of the parameters / buffers / optimiser state, which
-    are restored before capture, so constructing this object does not train the model."""
+    gradients from the bucket).  Parameters, buffers and optimiser state are restored after the warm-up iterations, so
+    constructing this object does not train the model.  Stateful optimisers must be capture-safe (e.g.
+    ``torch.optim.Adam(..., capturable=True)``)."""
 
     def __init__(self, model, optimizer, data, actual_numpoints, labels, warmup=3):
         if not data.is_cuda:
@@ -197,7 +198,7 @@ class GraphedTrainStep:
         self.loss = None
         model.train()
         saved_model = {k: v.clone() for k, v in model.state_dict().items()}
-        saved_opt = _clone_state(optimizer.state_dict())
+        saved_opt = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()} for p, st in optimizer.state.items()}
         side = torch.cuda.Stream(device=data.device)
         side.wait_stream(torch.cuda.current_stream(data.device))
         with torch.cuda.stream(side):
@@ -210,7 +211,7 @@ class GraphedTrainStep:
         self.loss = None  # drops the warm-up autograd graph (its AccumulateGrad nodes are tied to the warm-up stream)
         with torch.no_grad():
             model.load_state_dict(saved_model)
-        optimizer.load_state_dict(saved_opt)
+        self._restore_optimizer(saved_opt)
         self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g1):
             self._fwd_bwd()
@@ -219,6 +220,22 @@ class GraphedTrainStep:
         # capture executed nothing, but BatchNorm's python-side counters / moving statistics must match "no step yet"
         with torch.no_grad():
             model.load_state_dict(saved_model)
+
+    def _restore_optimizer(self, saved):
+        """Optimiser state back to what it was before the warm-up steps, IN PLACE (the graphs must see the same tensors
+        on every replay): saved values where the state existed, zeros where the warm-up created it (the initial state
+        of Adam / AdamW / RMSprop / momentum SGD without dampening)."""
+        with torch.no_grad():
+            for p, st in self.optimizer.state.items():
+                old = saved.get(p, {})
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if k in old and torch.is_tensor(old[k]):
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()
+                    elif k in old:
+                        st[k] = old[k]
 
     def _fwd_bwd(self):
         self.bucket.zero_()
@@ -246,11 +263,3 @@ class GraphedTrainStep:
         self._reduce()
         self.g2.replay()
         return self.loss.detach()
-
-
-def _clone_state(sd):
-    import copy
-    out = copy.deepcopy({k: v for k, v in sd.items() if k != "state"})
-    out["state"] = {k: {kk: (vv.clone() if torch.is_tensor(vv) else copy.deepcopy(vv)) for kk, vv in st.items()}
-                    for k, st in sd["state"].items()}
-    return out

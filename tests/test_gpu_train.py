@@ -118,8 +118,8 @@ def test_training_step_on_cuda_kernels(gg, cuda_dev):
     assert losses[-1] < 0.5 * losses[0], losses[::5]
 
 
-@pytest.mark.parametrize("block", ["cuda", "torch"])
-def test_graphed_train_step_matches_eager(gg, cuda_dev, block):
+@pytest.mark.parametrize("block,optim", [("cuda", "sgd"), ("torch", "sgd"), ("cuda", "adam")])
+def test_graphed_train_step_matches_eager(gg, cuda_dev, block, optim):
     """train.GraphedTrainStep (forward + backward and the update replayed as CUDA graphs, gradients in one flat bucket)
     is the same arithmetic as train.train_step: after 5 SGD steps from the same start the parameters, the BatchNorm
     moving statistics and the losses agree (1e-4: the weight-gradient kernels sum with atomics), and constructing the
@@ -132,6 +132,8 @@ def test_graphed_train_step_matches_eager(gg, cuda_dev, block):
     def make():
         torch.manual_seed(0)
         m = train.GridGcnClassifier(cfg, stack.init_params(cfg, seed=2), num_classes=4, block=block).to(cuda_dev)
+        if optim == "adam":  # stateful: the state created by the warm-up steps must be back at its initial value
+            return m, torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
         return m, torch.optim.SGD(m.parameters(), lr=1e-2)
 
     m0, o0 = make()
@@ -142,8 +144,9 @@ def test_graphed_train_step_matches_eager(gg, cuda_dev, block):
     for k, v in m1.state_dict().items():
         assert torch.equal(v, before[k]), "construction changed " + k
     graphed = [float(step(d, n, labels)) for _ in range(5)]
-    assert np.allclose(graphed, eager, rtol=1e-4, atol=1e-6), (graphed, eager)
+    tol = 1e-4 if optim == "sgd" else 2e-3  # Adam divides by sqrt(v): the atomics' rounding noise is amplified where g ~ 0
+    assert np.allclose(graphed, eager, rtol=tol, atol=1e-6), (graphed, eager)
     s0, s1 = m0.state_dict(), m1.state_dict()
     for k in s0:
         a, b = s0[k].float().cpu().numpy(), s1[k].float().cpu().numpy()
-        assert _rel_err(b, a) <= 1e-4, k
+        assert _rel_err(b, a) <= tol, k
