@@ -147,6 +147,9 @@ def test_graphed_train_step_matches_eager(gg, cuda_dev, block, optim):
     tol = 1e-4 if optim == "sgd" else 2e-3  # Adam divides by sqrt(v): the atomics' rounding noise is amplified where g ~ 0
     assert np.allclose(graphed, eager, rtol=tol, atol=1e-6), (graphed, eager)
     s0, s1 = m0.state_dict(), m1.state_dict()
+    import re
     for k in s0:
+        if optim == "adam" and re.search(r"\.(feat|att)\.\d+\.bias$", k):
+            continue  # conv bias in front of a batch-stat BN: its gradient is pure rounding noise, which Adam turns into +-lr steps
         a, b = s0[k].float().cpu().numpy(), s1[k].float().cpu().numpy()
         assert _rel_err(b, a) <= tol, k
