@@ -338,8 +338,13 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
                 tc::tmem_ld_wait();
                 float mm = -3.402823466e+38f;
 #pragma unroll
-                for (int j = 0; j < 16; j++) mm = fmaxf(mm, f[slot * 16 + j] * (__uint_as_float(g[j]) + ba));  // :167 att * feats; the features
-                // are ReLU outputs (>= 0), so f * relu(a) == max(f * a, 0): the attention ReLU is applied once per centre below
+                for (int j = 0; j < 16; j += 2) {  // :167 att * feats; the features are ReLU outputs (>= 0), so
+                    // f * relu(a) == max(f * a, 0): the attention ReLU is applied once per centre below.  Packed pairs.
+                    float a0 = __uint_as_float(g[j]), a1 = __uint_as_float(g[j + 1]);
+                    tc::add2(a0, a1, ba, ba);
+                    tc::mul2(a0, a1, f[slot * 16 + j], f[slot * 16 + j + 1]);
+                    mm = fmaxf(mm, fmaxf(a0, a1));
+                }
                 if (k < 2) load_group(roff_c, c0 + 32, slot);
                 else if (has_next) load_group(roff_n, c0 - 32, slot);
                 m = fmaxf(m, mm);

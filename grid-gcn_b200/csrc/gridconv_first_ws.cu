@@ -462,10 +462,19 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
             auto reduce16 = [&](const uint32_t (&fv)[16], const uint32_t (&gv)[16], int c0) {
                 float pr[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++)
+                for (int j = 0; j < 16; j += 2) {
                     // :167 att * feats.  relu(F) >= 0, so relu(F) * relu(G) == max(relu(F) * G, 0): the attention ReLU is
-                    // hoisted out of the max over K (applied once per centre below)
-                    pr[j] = fmaxf(__uint_as_float(fv[j]) + bf, 0.f) * (__uint_as_float(gv[j]) + bg);
+                    // hoisted out of the max over K (applied once per centre below).  Packed fp32 pairs (FADD2 / FMUL2).
+                    float x0 = __uint_as_float(fv[j]), x1 = __uint_as_float(fv[j + 1]);
+                    float a0 = __uint_as_float(gv[j]), a1 = __uint_as_float(gv[j + 1]);
+                    tc::add2(x0, x1, bf, bf);
+                    tc::add2(a0, a1, bg, bg);
+                    x0 = fmaxf(x0, 0.f);
+                    x1 = fmaxf(x1, 0.f);
+                    tc::mul2(x0, x1, a0, a1);
+                    pr[j] = x0;
+                    pr[j + 1] = x1;
+                }
                 float mm = pr[0];
 #pragma unroll
                 for (int j = 1; j < 16; j++) mm = fmaxf(mm, pr[j]);

@@ -217,5 +217,23 @@ __device__ __forceinline__ void split_op(float v, float &hi, float &lo) {
     }
 }
 
+
+// Packed fp32 pairs (sm_100a FADD2 / FMUL2: one instruction for two IEEE round-to-nearest results, bit-identical to
+// the scalar operations).  Used by the epilogue roles, whose CUDA-core instruction count is what bounds them.
+__device__ __forceinline__ void add2(float &x0, float &x1, float b0, float b1) {
+    uint64_t a, b;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(a));
+}
+__device__ __forceinline__ void mul2(float &x0, float &x1, float b0, float b1) {
+    uint64_t a, b;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(a));
+}
+
 }  // namespace tc
 }  // namespace gg
