@@ -266,10 +266,9 @@ edge_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt, int l
                     for (int g = 0; g < 4; g++) {
                         float x[4], lo[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            x[j] = fmaxf(__uint_as_float(v[4 * g + j]), 0.f);
-                            lo[j] = x[j] - __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
-                        }
+                        for (int j = 0; j < 4; j++) x[j] = fmaxf(__uint_as_float(v[4 * g + j]), 0.f);
+                        tc::split_lo2(x[0], x[1], lo[0], lo[1]);  // packed pairs: bit-identical to x - trunc(x)
+                        tc::split_lo2(x[2], x[3], lo[2], lo[3]);
                         uint8_t *dst = img + (uint32_t)((c0 >> 2) + g) * kEwPanel;
                         *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
                         *reinterpret_cast<float4 *>(dst + (A0P / 4) * kEwPanel) = make_float4(lo[0], lo[1], lo[2], lo[3]);

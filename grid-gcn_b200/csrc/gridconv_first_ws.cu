@@ -140,23 +140,22 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *v) {
 // relu -> hi/lo split (hardware truncation model, tc_common.cuh split_op<3>) of four accumulator columns,
 // one 16-byte store per image
 __device__ __forceinline__ void relu_split_store4(const uint32_t *v, const float4 b, uint8_t *dst_hi, uint8_t *dst_lo) {
-    float x[4], lo[4];
-    x[0] = fmaxf(__uint_as_float(v[0]) + b.x, 0.f);
-    x[1] = fmaxf(__uint_as_float(v[1]) + b.y, 0.f);
-    x[2] = fmaxf(__uint_as_float(v[2]) + b.z, 0.f);
-    x[3] = fmaxf(__uint_as_float(v[3]) + b.w, 0.f);
+    float x[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])}, lo[4];
+    tc::add2(x[0], x[1], b.x, b.y);  // packed pairs (FADD2): bit-identical to the scalar operations
+    tc::add2(x[2], x[3], b.z, b.w);
 #pragma unroll
-    for (int i = 0; i < 4; i++) lo[i] = x[i] - __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+    for (int i = 0; i < 4; i++) x[i] = fmaxf(x[i], 0.f);
+    tc::split_lo2(x[0], x[1], lo[0], lo[1]);
+    tc::split_lo2(x[2], x[3], lo[2], lo[3]);
     *reinterpret_cast<float4 *>(dst_hi) = make_float4(x[0], x[1], x[2], x[3]);
     *reinterpret_cast<float4 *>(dst_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 __device__ __forceinline__ void relu_split_store4_nobias(const uint32_t *v, uint8_t *dst_hi, uint8_t *dst_lo) {
     float x[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        x[i] = fmaxf(__uint_as_float(v[i]), 0.f);
-        lo[i] = x[i] - __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
-    }
+    for (int i = 0; i < 4; i++) x[i] = fmaxf(__uint_as_float(v[i]), 0.f);
+    tc::split_lo2(x[0], x[1], lo[0], lo[1]);
+    tc::split_lo2(x[2], x[3], lo[2], lo[3]);
     *reinterpret_cast<float4 *>(dst_hi) = make_float4(x[0], x[1], x[2], x[3]);
     *reinterpret_cast<float4 *>(dst_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
@@ -421,9 +420,10 @@ edge_first_ws_kernel(const __grid_constant__ TcParams p, int num_units, int cpt,
                 tc::tmem_ld_wait();
                 float xh[16], xl[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
+                for (int j = 0; j < 16; j += 2) {
                     xh[j] = fmaxf(__uint_as_float(v[j]), 0.f);
-                    xl[j] = xh[j] - __uint_as_float(__float_as_uint(xh[j]) & 0xFFFFE000u);
+                    xh[j + 1] = fmaxf(__uint_as_float(v[j + 1]), 0.f);
+                    tc::split_lo2(xh[j], xh[j + 1], xl[j], xl[j + 1]);
                 }
                 tmem_st16(taddr + (uint32_t)c0, xh);
                 tmem_st16(taddr + kXfLoCol + (uint32_t)c0, xl);

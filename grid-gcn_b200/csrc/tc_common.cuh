@@ -227,6 +227,14 @@ __device__ __forceinline__ void add2(float &x0, float &x1, float b0, float b1) {
     asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(a));
 }
+// lo parts of the activation split (split_op<3>: lo = v - trunc_tf32(v)) of a pair: two LOP3 + one FADD2
+__device__ __forceinline__ void split_lo2(float x0, float x1, float &lo0, float &lo1) {
+    uint64_t a, b;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(__float_as_uint(x0) & 0xFFFFE000u), "r"(__float_as_uint(x1) & 0xFFFFE000u));
+    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo0), "=f"(lo1) : "l"(a));
+}
 __device__ __forceinline__ void mul2(float &x0, float &x1, float b0, float b1) {
     uint64_t a, b;
     asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
