@@ -12,8 +12,8 @@
 // tensor-core row GEMM (rowgemm_tc.cu), which computes every 1x1 convolution of the forward (Z = X W^T + b) and every
 // input gradient of the backward (dX = dZ W); the kernels here are everything around those GEMMs:
 //     edge rows + gather indices, per-channel batch statistics, normalise + ReLU, max pool with arg-max, its routing
-//     backward, BatchNorm + ReLU backward (two passes: sums, then elementwise), weight gradient (dW = dZ^T X), and the
-//     scatter-add of the gather.
+//     backward, BatchNorm + ReLU backward (two passes: ReLU backward + per-channel sums, then elementwise), weight and
+//     bias gradient (dW = dZ^T X, register-tiled), and the scatter-add of the gather.
 // They are orchestrated from the host (grid-gcn_b200/train_cuda.py); this is an un-fused training path -- one HBM
 // round trip per operator, like the reference's MXNet graph -- whose GEMMs run on tcgen05.
 #include "gridconv_common.cuh"

@@ -10,11 +10,12 @@ backward of gather / MLP / attention product / max-pool.  The index operators in
 (gridify-inl.h:227-231) they have no gradient.  One step = forward, backward, ONE all-reduce of the
 flattened gradient bucket (shard.allreduce_gradients; the north star's only collective), optimiser update.
 
-What this is NOT: a fused training kernel.  The fused sm_100a kernels of this repository implement the
-inference form (BatchNorm folded into the convs); the training-mode math here runs on PyTorch's library
-kernels.  `GridConvTrain.export_layer()` hands the trained parameters to the fused kernels, and the
-eval-mode forward of this module is held to the same oracle as they are (tests), which is what ties the
-two together.
+This module is the autograd statement of the block (PyTorch's library kernels do the math).  The same block with
+forward AND backward on this library's own kernels is train_cuda.GridConvTrainCuda (`block="cuda"` below; csrc/train_ops.cu
++ the tcgen05 row GEMM), held to this module within 1e-3 by tests/test_gpu_train.py.  `GridConvTrain.export_layer()` hands
+the trained parameters to the fused inference kernels (BatchNorm folded into the convs), and the eval-mode forward of
+this module is held to the same oracle as they are (tests), which is what ties the forms together.  `GraphedTrainStep`
+replays a whole training step as CUDA graphs around the one gradient all-reduce.
 """
 import numpy as np
 import torch
