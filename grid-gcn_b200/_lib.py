@@ -51,7 +51,7 @@ SIGNATURES = {
     # training-mode block kernels (csrc/train_ops.cu)
     "gridgcn_train_edge_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gridgcn_train_col_sums": (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp]),
-    "gridgcn_train_bn_finalize": (_i, [_vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),
+    "gridgcn_train_bn_finalize": (_i, [_vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gridgcn_train_bn_relu_fwd": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gridgcn_train_relu_bwd_xhat": (_i, [_vp, _vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp, _vp, _vp]),
     "gridgcn_train_bn_bwd": (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -79,8 +79,9 @@ train_col_sums_kernel(const float *__restrict__ a, const float *__restrict__ b, 
 __global__ void __launch_bounds__(kTrThreads)
 train_bn_finalize_kernel(const float *__restrict__ s0, const float *__restrict__ s1, float rows, int C, float eps, float momentum,
                          float *__restrict__ mean, float *__restrict__ invstd, float *__restrict__ running_mean,
-                         float *__restrict__ running_var) {
+                         float *__restrict__ running_var, long long *__restrict__ num_batches) {
     const int c = blockIdx.x * kTrThreads + threadIdx.x;
+    if (c == 0 && num_batches) *num_batches += 1;
     if (c >= C) return;
     const float mu = s0[c] / rows;
     const float var = fmaxf(s1[c] / rows - mu * mu, 0.f);
@@ -481,10 +482,11 @@ int gridgcn_train_col_sums(const float *a, const float *b, long long rows, int C
 }
 
 int gridgcn_train_bn_finalize(const float *s0, const float *s1, long long rows, int C, float eps, float momentum, float *mean,
-                              float *invstd, float *running_mean, float *running_var, void *stream) {
+                              float *invstd, float *running_mean, float *running_var, long long *num_batches_tracked,
+                              void *stream) {
     if (!s0 || !s1 || !mean || !invstd || rows < 1 || C < 1) return GRIDGCN_EINVAL;
     train_bn_finalize_kernel<<<(C + kTrThreads - 1) / kTrThreads, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        s0, s1, (float)rows, C, eps, momentum, mean, invstd, running_mean, running_var);
+        s0, s1, (float)rows, C, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked);
     return (int)cudaGetLastError();
 }
 

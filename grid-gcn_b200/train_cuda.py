@@ -66,21 +66,25 @@ class _Fn(torch.autograd.Function):
                                                  mod.attfdim, xf.data_ptr(), xa.data_ptr(), rowidx.data_ptr(), _stream(table)),
                        "gridgcn_train_edge_rows")
             saved = []
+            widths = [int(st_.weight.shape[0]) for st_ in mod._stages()]
+            pool = torch.zeros(4 * sum(widths), dtype=torch.float32, device=dev)   # ONE fill for every stage's statistics
+            pool_off = [0]
 
             def stage(x, idx):
                 w, b, gamma, beta = params[4 * idx:4 * idx + 4]
                 wp = mod._pad_w(idx, w)                       # zero columns for the padded input layouts
                 z = _gemm(x, wp, b, False)
                 rows, Cout = z.shape
-                st = torch.zeros((4, Cout), dtype=torch.float32, device=dev)   # sum, sum of squares -> mean, invstd
+                st = pool[pool_off[0]:pool_off[0] + 4 * Cout].view(4, Cout)   # sum, sum of squares -> mean, invstd
+                pool_off[0] += 4 * Cout
                 mean, invstd = st[2], st[3]
                 _lib.check(L.gridgcn_train_col_sums(z.data_ptr(), None, rows, Cout, st[0].data_ptr(), st[1].data_ptr(),
                                                     _stream(z)), "gridgcn_train_col_sums")
                 bn = mod._stages()[idx].bn   # biased variance normalises; the moving one is unbiased (torch convention)
                 _lib.check(L.gridgcn_train_bn_finalize(st[0].data_ptr(), st[1].data_ptr(), rows, Cout, BN_EPS, float(bn.momentum),
                                                        mean.data_ptr(), invstd.data_ptr(), bn.running_mean.data_ptr(),
-                                                       bn.running_var.data_ptr(), _stream(z)), "gridgcn_train_bn_finalize")
-                bn.num_batches_tracked += 1
+                                                       bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _stream(z)),
+                           "gridgcn_train_bn_finalize")
                 y = torch.empty_like(z)
                 _lib.check(L.gridgcn_train_bn_relu_fwd(z.data_ptr(), rows, Cout, mean.data_ptr(), invstd.data_ptr(),
                                                        gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _stream(z)),
@@ -126,13 +130,24 @@ class _Fn(torch.autograd.Function):
                                                 dA.data_ptr() if dA is not None else None, _stream(dout)),
                        "gridgcn_train_pool_bwd")
 
+            wps = [mod._pad_w(i, params[4 * i]) for i in range(len(saved))]   # padded (Cout, Cin) weights
+            need = 0   # ONE fill for every stage's sums and weight / bias gradients
+            for i, wp_ in enumerate(wps):
+                need += 3 * wp_.shape[0] + wp_.numel()
+            gpool = torch.zeros(need, dtype=torch.float32, device=dev)
+            gpool_off = [0]
+
+            def take(n):
+                v = gpool[gpool_off[0]:gpool_off[0] + n]
+                gpool_off[0] += n
+                return v
+
             def stage_bwd(dy, idx, need_dx):
                 x, z, y, mean, invstd = saved[idx]
                 w, b, gamma, beta = params[4 * idx:4 * idx + 4]
                 rows, Cout = z.shape
                 # dy <- dz = dy * (y > 0);  z <- xhat;  per-channel sum dz, sum dz * xhat in the same pass
-                sums = torch.zeros((2, Cout), dtype=torch.float32, device=dev)
-                sum_dz, sum_dzx = sums[0], sums[1]
+                sum_dz, sum_dzx = take(Cout), take(Cout)
                 _lib.check(L.gridgcn_train_relu_bwd_xhat(dy.data_ptr(), y.data_ptr(), z.data_ptr(), rows, Cout, mean.data_ptr(),
                                                          invstd.data_ptr(), sum_dz.data_ptr(), sum_dzx.data_ptr(), _stream(dy)),
                            "gridgcn_train_relu_bwd_xhat")
@@ -140,9 +155,8 @@ class _Fn(torch.autograd.Function):
                 _lib.check(L.gridgcn_train_bn_bwd(dy.data_ptr(), z.data_ptr(), rows, Cout, gamma.data_ptr(), invstd.data_ptr(),
                                                   sum_dz.data_ptr(), sum_dzx.data_ptr(), dzpre.data_ptr(), _stream(dy)),
                            "gridgcn_train_bn_bwd")
-                wp = mod._pad_w(idx, w)
-                dwb = torch.zeros(wp.numel() + Cout, dtype=torch.float32, device=dev)   # dW | db
-                dwp, dbias = dwb[:wp.numel()].view_as(wp), dwb[wp.numel():]
+                wp = wps[idx]
+                dwp, dbias = take(wp.numel()).view_as(wp), take(Cout)   # dW | db
                 _lib.check(L.gridgcn_train_wgrad(dzpre.data_ptr(), Cout, x.data_ptr(), x.stride(0), x.shape[1], None, 0, 0, rows,
                                                  dwp.data_ptr(), dbias.data_ptr(), _stream(dy)), "gridgcn_train_wgrad")
                 grads[4 * idx] = mod._unpad_w(idx, dwp).reshape(w.shape)

@@ -244,9 +244,11 @@ int gridgcn_train_edge_rows(const float *table, const int *nebidx, const float *
 /* s0[c] += sum_r a[r,c] * (b ? b[r,c] : 1);  s1[c] += sum_r a[r,c]^2 (s1 may be NULL); zero them first */
 int gridgcn_train_col_sums(const float *a, const float *b, long long rows, int C, float *s0, float *s1, void *stream);
 /* mean = s0 / rows, invstd = rsqrt(max(s1 / rows - mean^2, 0) + eps); moving statistics (may be NULL) updated as   */
-/* running = (1 - momentum) * running + momentum * new, variance unbiased (torch.nn.BatchNorm convention)            */
+/* running = (1 - momentum) * running + momentum * new, variance unbiased (torch.nn.BatchNorm convention);           */
+/* *num_batches_tracked (int64, may be NULL) += 1                                                                    */
 int gridgcn_train_bn_finalize(const float *s0, const float *s1, long long rows, int C, float eps, float momentum, float *mean,
-                              float *invstd, float *running_mean, float *running_var, void *stream);
+                              float *invstd, float *running_mean, float *running_var, long long *num_batches_tracked,
+                              void *stream);
 int gridgcn_train_bn_relu_fwd(const float *z, long long rows, int C, const float *mean, const float *invstd,
                               const float *gamma, const float *beta, float *y, void *stream);
 /* in place: dy <- dz = dy * (y > 0), z <- xhat = (z - mean) * invstd; when sum_dz / sum_dzx are given (both or    */
