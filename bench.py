@@ -127,7 +127,7 @@ class ClockSampler(threading.Thread):
                         self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.005 if self.nvml is not None else 0.25)
+            time.sleep(0.01 if self.nvml is not None else 0.25)
 
     def summary(self):
         if not self.samples:
