@@ -129,3 +129,38 @@ def test_data_parallel_step_two_gloo_ranks():
         assert np.allclose(res[0][1][k], want, atol=1e-6), k
         assert np.array_equal(res[0][1][k], res[1][1][k]), k
     assert res[0][0] != res[1][0]  # different shards, different local losses
+
+
+def test_cuda_block_host_logic_without_gpu():
+    """train_cuda.GridConvTrainCuda: the host side that needs no GPU -- padded weight layouts ([geo, 0] for the first
+    feature stage, trailing zeros of att_vec) round-trip, the classification flavours are refused, and on CPU tensors
+    the module is its parent (same parameters, same forward), so a model built with block="cuda" still runs the CPU
+    tests' op-by-op path."""
+    import pytest
+    from gridgcn_b200 import train_cuda
+    cfg = stack.tiny(8)
+    params = stack.init_params(cfg, seed=4)
+    m = train_cuda.GridConvTrainCuda(params[0])       # first layer: no input features
+    w0 = m.feat[0].weight
+    wp = m._pad_w(0, w0)
+    assert wp.shape == (w0.shape[0], 4) and torch.equal(wp[:, :3], w0) and float(wp[:, 3].abs().max()) == 0.0
+    assert torch.equal(m._unpad_w(0, wp), w0)
+    ia = m.n_feat                                      # first attention stage: att_vec padded to a multiple of 4
+    wa = m._pad_w(ia, m.att[0].weight)
+    assert wa.shape[1] == m.ain_p and m.ain_p % 4 == 0
+    assert torch.equal(m._unpad_w(ia, wa), m.att[0].weight.reshape(wa.shape[0], -1))
+    m1 = train_cuda.GridConvTrainCuda(params[1])       # layer with input features: nothing to pad in the feature chain
+    assert m1._pad_w(0, m1.feat[0].weight).shape == m1.feat[0].weight.reshape(m1.feat[0].weight.shape[0], -1).shape
+    with pytest.raises(NotImplementedError):
+        train_cuda.GridConvTrainCuda(dict(params[1], localfdim=3))
+    # CPU tensors: the parent's forward, bit for bit
+    ref = train.GridConvTrain(params[0])
+    ref.load_state_dict(m.state_dict())
+    B, Np, O, K = 2, 32, 8, 4
+    g = torch.Generator().manual_seed(0)
+    table = torch.rand((B, Np, 4), generator=g)
+    nebidx = torch.randint(0, Np, (B, O, K), generator=g, dtype=torch.int32)
+    cent = torch.rand((B, O, 4), generator=g)
+    msk = torch.ones((B, O))
+    m.train(), ref.train()
+    assert torch.equal(m(table, nebidx, cent, msk), ref(table, nebidx, cent, msk))
